@@ -1,0 +1,124 @@
+/*
+ * b200mol.h — C-ABI of libb200mol.so, the B200 (sm_100a) batched-molecule hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers + sizes + an opaque stream
+ * (a cudaStream_t passed as void*), returns an int status (0 = OK) and never throws.
+ * `b200mol_last_error()` returns the thread-local message of the last failing call.
+ *
+ * Pointer naming:  d_* = device memory, h_* = host memory.  Inputs are borrowed.
+ * Outputs are caller-allocated unless the comment says "callee-allocated"
+ * (then release with b200mol_free_async on the same stream).
+ * Nothing here synchronises the stream unless the comment says so.
+ *
+ * Each declaration cites the interface of the reference (NVIDIA-Digital-Bio/nvMolKit
+ * v0.5.0, paths relative to its checkout) that it replaces.
+ */
+#ifndef B200MOL_H
+#define B200MOL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MOL_OK 0
+#define B200MOL_ERR_INVALID 1 /* bad argument (maps to ValueError / std::invalid_argument) */
+#define B200MOL_ERR_CUDA 2    /* CUDA runtime failure (maps to RuntimeError / CudaBadReturnCode) */
+#define B200MOL_ERR_NODEVICE 3 /* no sm_100 device visible: the product path has no CPU fallback */
+
+#define B200MOL_METRIC_TANIMOTO 0
+#define B200MOL_METRIC_COSINE 1
+
+const char* b200mol_last_error(void);
+/* ABI version, bumped on any signature change. */
+int b200mol_abi_version(void);
+/* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
+uint64_t b200mol_launch_count(void);
+/* 0 when device `dev` is compute capability 10.x; B200MOL_ERR_NODEVICE otherwise. */
+int b200mol_check_device(int dev);
+int b200mol_free_async(void* d_ptr, void* stream);
+/* Per-phase CUDA-event timing inside the library (off by default). Phases: "neighbor_pass" (the N^2 tile kernel
+ * alone), "csr_build", "cluster_loop", "bfgs". b200mol_profile_read waits for the phase's stop event. */
+int b200mol_profile_enable(int on);
+int b200mol_profile_read(const char* phase, float* ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Fingerprint similarity.
+ * Fingerprints are u32 fp[n][words], bit j of row i = fp[i][j>>5] & (1u << (j&31))
+ * (reference wire format: src/data_structures/flat_bit_vect.h:129-144, nvmolkit/fingerprints.py:25-72).
+ * ---------------------------------------------------------------------------------------- */
+
+/* S[i][j] = |A_i & B_j| / |A_i | B_j| as fp64, 0 when the intersection is empty; row-major d_out[nA*nB].
+ * Integer popcounts and ONE correctly rounded fp64 divide (identical to RDKit TanimotoSimilarity in fp64).
+ * Replaces launchCrossTanimotoSimilarity (src/similarity_kernels.h:51-56, .cu:505-582) and
+ * crossTanimotoSimilarityGpuResult (src/similarity.cpp:38-58). */
+int b200mol_tanimoto_cross(const uint32_t* d_a, size_t nA, const uint32_t* d_b, size_t nB, int words, double* d_out,
+                           void* stream);
+/* Cosine twin: |A&B| / sqrt(|A||B|), 0 when the intersection is empty.
+ * Replaces launchCrossCosineSimilarity (src/similarity_kernels.cu:602-631). */
+int b200mol_cosine_cross(const uint32_t* d_a, size_t nA, const uint32_t* d_b, size_t nB, int words, double* d_out,
+                         void* stream);
+/* Host-in / host-out variant: fingerprints in host memory, result matrix to host memory, row blocks of A
+ * streamed through two device buffers with overlapped D2H. Synchronous. metric = B200MOL_METRIC_*.
+ * Replaces crossTanimotoSimilarityMemoryConstrained / crossSimilarityImpl (src/similarity.cpp:105-236). */
+int b200mol_similarity_cross_host(const uint32_t* h_a, size_t nA, const uint32_t* h_b, size_t nB, int words, int metric,
+                                  double* h_out, size_t maxDeviceBytes);
+
+/* Fused threshold count: d_counts[i] (+= or -=, sign = +1/-1) #{ j : 1 - sim(X_i, Y_j) <= cutoff }, the comparison
+ * evaluated exactly as fp64 `1.0 - c/u <= cutoff` through an integer threshold table, the similarity matrix never
+ * materialised. Replaces the Triton kernel _update_neighbor_count_kernel (nvmolkit/_fusedButina.py:99-179, 249-289). */
+int b200mol_tanimoto_count_ge(const uint32_t* d_x, size_t nX, const uint32_t* d_y, size_t nY, int words, int metric,
+                              double cutoff, int sign, int32_t* d_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Butina clustering.  Definition (RDKit ML.Cluster.Butina.ClusterData(reordering=True), the CPU baseline the
+ * reference benchmarks against, benchmarks/butina_clustering_bench.py:97-99): repeatedly take the unassigned point
+ * with the most unassigned neighbours (ties -> highest index); the cluster is that point plus its unassigned
+ * neighbours; ids are assigned in creation order, so cluster 0 is the largest and sizes are non-increasing;
+ * when no unassigned point has a neighbour left the rest become singletons in descending index order.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Fingerprints in, cluster ids out, O(N + edges) memory.  d_cluster_ids[N]; d_centroids[N] (first *nClusters valid,
+ * may be NULL); *h_n_clusters written after an internal stream synchronisation (may be NULL to stay asynchronous,
+ * in which case d_n_clusters (device int32, may be NULL) receives it).
+ * Replaces fused_butina (nvmolkit/clustering.py:99-189, nvmolkit/_fusedButina.py:99-346). */
+int b200mol_butina_fused(const uint32_t* d_fp, size_t n, int words, int metric, double cutoff, int32_t* d_cluster_ids,
+                         int32_t* d_centroids, int32_t* d_n_clusters, int32_t* h_n_clusters, void* stream);
+/* The two stages of b200mol_butina_fused, exposed so that the N^2 pass can be sharded over GPUs by tile-row group
+ * (a group = 32 x 128 fingerprint rows): rank r of R passes group_offset = r, group_stride = R, then the ranks
+ * all-reduce d_counts and all-gather their edge lists, and every rank (or rank 0) clusters.
+ *   d_counts[n]  += number of neighbours of each point found in this rank's tiles (caller zeroes it)
+ *   d_edges      int32 pairs (i, j), i < j, appended; entries beyond edge_cap are dropped but still counted
+ *   *h_n_edges   total found (host, written after an internal stream sync; > edge_cap means: retry with more room) */
+int b200mol_neighbor_edges(const uint32_t* d_fp, size_t n, int words, int metric, double cutoff, uint32_t group_offset,
+                           uint32_t group_stride, int32_t* d_counts, int32_t* d_edges, uint64_t edge_cap,
+                           uint64_t* h_n_edges, void* stream);
+/* d_counts[n] = full degrees (consumed: decremented in place), d_edges = all n_edges (i<j) pairs. */
+int b200mol_butina_from_edges(size_t n, int32_t* d_counts, const int32_t* d_edges, uint64_t n_edges,
+                              int32_t* d_cluster_ids, int32_t* d_centroids, int32_t* d_n_clusters,
+                              int32_t* h_n_clusters, void* stream);
+/* Dense fp64 distance matrix in (neighbours: dist <= cutoff, src/butina.cu:1043-1051).
+ * Replaces butinaGpu (src/butina.h:45-50, src/butina.cu:914-1071). */
+int b200mol_butina_dense(const double* d_dist, size_t n, double cutoff, int32_t* d_cluster_ids, int32_t* d_centroids,
+                         int32_t* d_n_clusters, int32_t* h_n_clusters, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Morgan fingerprints from flattened molecular graphs (the seam below RDKit: atom/bond invariants are the
+ * output of RDKit's MorganAtomInvGenerator / bond types, src/morgan_fingerprint_common.cpp:43-124).
+ *   d_atom_starts[nMols+1], d_bond_starts[nMols+1]  CSR offsets
+ *   d_atom_inv[totalAtoms]  u32 atom invariants;  d_bond_inv[totalBonds] u32 bond invariants (bond type)
+ *   d_bond_a / d_bond_b [totalBonds]  molecule-local atom indices (u16)
+ *   d_out  u32[nMols][fpBits/32], overwritten.
+ * Molecules may have up to 1024 atoms and 1024 bonds, and any atom up to 8 bonds (kMaxBondsPerAtom).
+ * Replaces launchMorganFingerprintKernelBatch<fpSize> (src/morgan_fingerprint_kernels.h:90-95, .cu:152-432) and its
+ * CPU twin for large molecules (src/morgan_fingerprint_cpu.cpp:61-255). */
+int b200mol_morgan(const int32_t* d_atom_starts, const int32_t* d_bond_starts, const uint32_t* d_atom_inv,
+                   const uint32_t* d_bond_inv, const uint16_t* d_bond_a, const uint16_t* d_bond_b, size_t nMols,
+                   int maxAtomsPerMol, int maxBondsPerMol, int radius, int fpBits, uint32_t* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MOL_H */

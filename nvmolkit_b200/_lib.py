@@ -1,0 +1,92 @@
+"""ctypes binding of the C-ABI in ``include/b200mol.h`` (``nvmolkit_b200/lib/libb200mol.so``).
+
+There is no CPU fallback: if the CUDA library is missing, or a call fails, this module raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200mol.so")
+
+B200MOL_OK, ERR_INVALID, ERR_CUDA, ERR_NODEVICE = 0, 1, 2, 3
+METRIC = {"tanimoto": 0, "cosine": 1}
+
+_u32p = C.c_void_p  # device/host pointers travel as integers
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/b200mol.h declares (tests/test_abi.py checks this).
+SIGNATURES = {
+    "b200mol_last_error": (C.c_char_p, []),
+    "b200mol_abi_version": (C.c_int, []),
+    "b200mol_launch_count": (C.c_uint64, []),
+    "b200mol_check_device": (C.c_int, [C.c_int]),
+    "b200mol_free_async": (C.c_int, [_vp, _vp]),
+    "b200mol_profile_enable": (C.c_int, [C.c_int]),
+    "b200mol_profile_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_float)]),
+    "b200mol_tanimoto_cross": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, _vp, _vp]),
+    "b200mol_cosine_cross": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, _vp, _vp]),
+    "b200mol_similarity_cross_host": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, C.c_int, _vp, C.c_size_t]),
+    "b200mol_tanimoto_count_ge": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, C.c_int, C.c_double, C.c_int,
+                                            _vp, _vp]),
+    "b200mol_butina_fused": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_neighbor_edges": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_int, C.c_double, C.c_uint32, C.c_uint32, _vp,
+                                         _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp]),
+    "b200mol_butina_from_edges": (C.c_int, [C.c_size_t, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_butina_dense": (C.c_int, [_vp, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_morgan": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
+                                 _vp]),
+}
+
+_lib = None
+
+
+class B200MolError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libb200mol.so (once). Raises ImportError when it has not been built — there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). nvmolkit_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    """Translate a C-ABI status into the exception types the reference's bindings raise."""
+    if status == B200MOL_OK:
+        return
+    msg = load().b200mol_last_error().decode("utf-8", "replace")
+    if status == ERR_INVALID:
+        raise ValueError(msg)
+    raise B200MolError(msg)
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args))
+
+
+def launch_count() -> int:
+    return int(load().b200mol_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(load().b200mol_profile_enable(1 if on else 0))
+
+
+def profile_read(phase: str) -> float:
+    ms = C.c_float(0.0)
+    check(load().b200mol_profile_read(phase.encode(), C.byref(ms)))
+    return float(ms.value)

@@ -1,0 +1,110 @@
+// Shared host/device helpers for libb200mol (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/b200mol.h"
+
+namespace b200 {
+
+extern thread_local std::string g_lastError;
+extern std::atomic<uint64_t>    g_launchCount;
+
+struct Failure {
+  int         code;
+  std::string msg;
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+  char    buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Failure{code, buf};
+}
+
+#define B200_CUDA(expr)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t e_ = (expr);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      ::b200::fail(B200MOL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define B200_REQUIRE(cond, ...)                             \
+  do {                                                      \
+    if (!(cond)) ::b200::fail(B200MOL_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Count a kernel launch and check it.
+#define B200_LAUNCHED()                 \
+  do {                                  \
+    ::b200::g_launchCount.fetch_add(1); \
+    B200_CUDA(cudaGetLastError());      \
+  } while (0)
+
+// Wrap the body of an extern "C" entry point.
+template <class F>
+inline int guarded(F&& f) noexcept {
+  try {
+    f();
+    return B200MOL_OK;
+  } catch (const Failure& e) {
+    g_lastError = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    g_lastError = e.what();
+    return B200MOL_ERR_CUDA;
+  } catch (...) {
+    g_lastError = "unknown failure";
+    return B200MOL_ERR_CUDA;
+  }
+}
+
+// Stream-ordered scratch allocation (RAII).
+template <class T>
+struct Scratch {
+  T*           p = nullptr;
+  cudaStream_t s = nullptr;
+  Scratch() = default;
+  Scratch(size_t n, cudaStream_t stream) : s(stream) {
+    if (n) B200_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), stream));
+  }
+  Scratch(const Scratch&)            = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  Scratch(Scratch&& o) noexcept : p(o.p), s(o.s) { o.p = nullptr; }
+  Scratch& operator=(Scratch&& o) noexcept {
+    if (this != &o) {
+      release();
+      p   = o.p;
+      s   = o.s;
+      o.p = nullptr;
+    }
+    return *this;
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+  }
+  ~Scratch() { release(); }
+  T* get() const { return p; }
+};
+
+inline int smCount() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+inline cudaStream_t asStream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace b200

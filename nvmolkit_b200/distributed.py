@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing: one process per GPU over torch.distributed (NCCL on the box, gloo in CPU tests).
+
+The hot path shards by independent units (tile-row groups of the pair matrix, molecule ranges of a conformer batch);
+the only collectives are the result exchanges at the end of a step.
+"""
+
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def rank_world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def molecule_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Plain contiguous molecule-range split [lo, hi) (north_star: 'plain molecule-range split')."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_v(t: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather of tensors whose first dimension differs per rank. Returns (concatenated, sizes[world]).
+
+    One all-gather of the sizes, one all-gather of max-padded payloads (NCCL has no native all-gather-v)."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return t, torch.tensor([t.shape[0]], dtype=torch.int64)
+    size = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(sizes, size, group=group)
+    sizes_h = sizes.cpu()
+    mx = int(sizes_h.max().item())
+    padded = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    padded[: t.shape[0]] = t
+    gathered = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    parts = [gathered[r * mx: r * mx + int(sizes_h[r])] for r in range(world)]
+    return torch.cat(parts, dim=0), sizes_h

@@ -1,0 +1,257 @@
+"""GPU parity of path A (through the Python surface, which calls the C-ABI): bit-exact vs the CPU oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from nvmolkit_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(fp, cuda):
+    return torch.from_numpy(np.ascontiguousarray(fp).view(np.int32)).to(cuda)
+
+
+# ------------------------------------------------------------------ similarity
+@pytest.mark.parametrize("bits", [128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 300), (127, 129), (128, 128), (257, 513)])
+def test_cross_tanimoto_bit_exact(cuda, bits, n, m):
+    from nvmolkit_b200.similarity import crossTanimotoSimilarity
+
+    a = S.random_fingerprints(n, bits=bits, p=0.05, seed=n * 7 + bits, near_dups=n // 4)
+    b = S.random_fingerprints(m, bits=bits, p=0.05, seed=m * 11 + bits + 1, near_dups=m // 4)
+    b[: min(n, m) // 2] = a[: min(n, m) // 2]
+    got = crossTanimotoSimilarity(_dev(a, cuda), _dev(b, cuda)).numpy()
+    assert got.dtype == np.float64 and got.shape == (n, m)
+    assert (got == oracle.similarity_cross(a, b)).all()
+
+
+def test_cross_tanimoto_config1_1k_x_1k(cuda):
+    # BASELINE config 1 stand-in: u32[1000][64] x2, Bernoulli(0.025) bits + planted near duplicates, seed 20260924
+    from nvmolkit_b200.similarity import crossTanimotoSimilarity
+
+    a = S.random_fingerprints(1000, seed=S.SEED, near_dups=100)
+    b = S.random_fingerprints(1000, seed=S.SEED + 1, near_dups=100)
+    b[:50] = a[:50]
+    got = crossTanimotoSimilarity(_dev(a, cuda), _dev(b, cuda)).numpy()
+    want = oracle.similarity_cross(a, b)
+    assert (got == want).all()
+    assert got.max() == 1.0 and got.min() == 0.0
+
+
+def test_self_similarity_and_empty_rows(cuda):
+    from nvmolkit_b200.similarity import crossCosineSimilarity, crossTanimotoSimilarity
+
+    a = S.random_fingerprints(200, seed=5, near_dups=40)
+    a[3] = 0  # empty fingerprint: similarity 0 to everything, itself included (src/load_store.cuh:264-269)
+    d = _dev(a, cuda)
+    t = crossTanimotoSimilarity(d).numpy()
+    assert (t == oracle.similarity_cross(a)).all()
+    assert t[3].max() == 0.0 and np.allclose(np.delete(np.diag(t), 3), 1.0)
+    c = crossCosineSimilarity(d).numpy()
+    assert (c == oracle.similarity_cross(a, metric="cosine")).all()
+
+
+def test_zero_rows_and_errors(cuda):
+    from nvmolkit_b200.similarity import crossTanimotoSimilarity
+
+    a = _dev(S.random_fingerprints(5), cuda)
+    assert crossTanimotoSimilarity(a[:0], a).numpy().shape == (0, 5)
+    with pytest.raises(TypeError):
+        crossTanimotoSimilarity(a, a, stream="not a stream")
+    with pytest.raises(ValueError):
+        crossTanimotoSimilarity(a, a[:, :32].contiguous())
+    with pytest.raises(ValueError):
+        crossTanimotoSimilarity(a.to(torch.float32))
+
+
+def test_non_default_stream(cuda):
+    from nvmolkit_b200.similarity import crossTanimotoSimilarity
+
+    a = S.random_fingerprints(300, seed=9, near_dups=50)
+    d = _dev(a, cuda)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    res = crossTanimotoSimilarity(d, stream=s)
+    s.synchronize()
+    assert (res.torch().cpu().numpy() == oracle.similarity_cross(a)).all()
+
+
+def test_memory_constrained_host_variant(cuda):
+    from nvmolkit_b200 import _lib
+    from nvmolkit_b200.similarity import crossCosineSimilarityMemoryConstrained, crossTanimotoSimilarityMemoryConstrained
+
+    a = S.random_fingerprints(700, seed=21, near_dups=100)
+    b = S.random_fingerprints(333, seed=22, near_dups=50)
+    assert (crossTanimotoSimilarityMemoryConstrained(a.view(np.int32), b.view(np.int32)) == oracle.similarity_cross(a, b)).all()
+    assert (crossCosineSimilarityMemoryConstrained(torch.from_numpy(a.view(np.int32))) ==
+            oracle.similarity_cross(a, metric="cosine")).all()
+    # force several row blocks through the two device buffers
+    out = np.empty((700, 333))
+    _lib.call("b200mol_similarity_cross_host", a.ctypes.data, 700, b.ctypes.data, 333, 64, 0, out.ctypes.data,
+              2 * 128 * 333 * 8)
+    assert (out == oracle.similarity_cross(a, b)).all()
+
+
+@pytest.mark.parametrize("metric", ["tanimoto", "cosine"])
+@pytest.mark.parametrize("cutoff", [0.0, 0.3, 0.35, 0.65, 1.0])
+def test_count_ge_exact(cuda, metric, cutoff):
+    from nvmolkit_b200 import _lib
+
+    x = S.clustered_fingerprints(12, 25, seed=31)
+    y = S.clustered_fingerprints(12, 11, seed=31)  # same centres, other members
+    dx, dy = _dev(x, cuda), _dev(y, cuda)
+    counts = torch.full((x.shape[0],), 1000, dtype=torch.int32, device=cuda)
+    _lib.call("b200mol_tanimoto_count_ge", dx.data_ptr(), x.shape[0], dy.data_ptr(), y.shape[0], 64,
+              _lib.METRIC[metric], cutoff, -1, counts.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    want = oracle.count_ge(x, y, cutoff, metric=metric, sign=-1, counts=np.full(x.shape[0], 1000, dtype=np.int32))
+    assert (counts.cpu().numpy() == want).all()
+
+
+def test_threshold_boundary_is_fp64_exact(cuda):
+    """Pairs whose 1 - c/u sits exactly on / next to the cutoff: integer table must agree with the fp64 predicate."""
+    from nvmolkit_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    rows = []
+    for u, c in [(10, 7), (20, 14), (100, 70), (1000, 700), (10, 6), (3, 2), (7, 5)]:
+        bits_a = np.zeros(2048, dtype=bool)
+        bits_b = np.zeros(2048, dtype=bool)
+        perm = rng.permutation(2048)
+        bits_a[perm[:u]] = True  # |A| = u, B subset of A with |B| = c  -> sim = c/u
+        bits_b[perm[:c]] = True
+        rows.append((S.pack_bits(bits_a[None])[0], S.pack_bits(bits_b[None])[0]))
+    x = np.stack([r[0] for r in rows])
+    y = np.stack([r[1] for r in rows])
+    for cutoff in (0.3, 1.0 - 0.7, 0.30000000000000004, 0.29999999999999993, 1 / 3, 0.4):
+        counts = torch.zeros(len(x), dtype=torch.int32, device=cuda)
+        _lib.call("b200mol_tanimoto_count_ge", _dev(x, cuda).data_ptr(), len(x), _dev(y, cuda).data_ptr(), len(y), 64,
+                  0, cutoff, 1, counts.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert (counts.cpu().numpy() == oracle.count_ge(x, y, cutoff)).all(), cutoff
+
+
+# ------------------------------------------------------------------ butina
+def _assert_same_clustering(ids, cen, ids_cpu, cen_cpu):
+    assert (ids == ids_cpu).all()
+    assert (cen == cen_cpu).all()
+
+
+@pytest.mark.parametrize("metric", ["tanimoto", "cosine"])
+@pytest.mark.parametrize("centres,members,cutoff", [(1, 1, 0.3), (3, 1, 0.3), (40, 25, 0.3), (25, 40, 0.2), (60, 17, 0.5)])
+def test_fused_butina_equals_rdkit_definition(cuda, metric, centres, members, cutoff):
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    fp = S.clustered_fingerprints(centres, members, seed=centres * 100 + members)
+    ids, cen = fused_butina_device(_dev(fp, cuda), cutoff, metric=metric)
+    ids_cpu, cen_cpu = oracle.butina_fp(fp, cutoff, metric=metric)
+    _assert_same_clustering(ids.cpu().numpy(), cen.cpu().numpy(), ids_cpu, cen_cpu)
+
+
+def test_fused_butina_5k(cuda):
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    fp = S.clustered_fingerprints(100, 50, seed=S.SEED)
+    ids, cen = fused_butina_device(_dev(fp, cuda), 0.3)
+    ids_cpu, cen_cpu = oracle.butina_fp(fp, 0.3)
+    _assert_same_clustering(ids.cpu().numpy(), cen.cpu().numpy(), ids_cpu, cen_cpu)
+    sizes = np.bincount(ids.cpu().numpy())
+    assert (np.diff(sizes) <= 0).all()  # cluster 0 is the largest, sizes non-increasing
+
+
+def test_fused_butina_python_return_shape(cuda):
+    from nvmolkit_b200.clustering import fused_butina
+
+    fp = S.clustered_fingerprints(10, 9, seed=3)
+    clusters, sizes, centroids = fused_butina(_dev(fp, cuda), 0.3, return_centroids=True)
+    assert sizes[0] == 0 and sizes[-1] == 90 and len(sizes) == len(clusters) + 1
+    assert sorted(m for c in clusters for m in c) == list(range(90))
+    for c, cen in zip(clusters, centroids):
+        assert c[0] == cen
+    with pytest.raises(ValueError):
+        fused_butina(_dev(fp, cuda), 1.5)
+    with pytest.raises(ValueError):
+        fused_butina(_dev(fp, cuda), 0.3, metric="dice")
+
+
+def test_fused_butina_identical_and_all_distinct(cuda):
+    # nvmolkit/tests/test_clustering.py:154-295: all-identical -> one cluster; random -> all singletons
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    one = np.repeat(S.random_fingerprints(1, seed=1), 300, axis=0)  # dense graph: exercises the edge-buffer regrow
+    ids, cen = fused_butina_device(_dev(one, cuda), 0.3)
+    assert (ids.cpu().numpy() == 0).all() and cen.cpu().numpy().tolist() == [299]
+    rnd = S.random_fingerprints(500, seed=2)
+    ids, cen = fused_butina_device(_dev(rnd, cuda), 0.3)
+    assert sorted(ids.cpu().numpy().tolist()) == list(range(500))
+    assert cen.cpu().numpy().tolist() == list(range(499, -1, -1))
+
+
+def test_dense_butina_known_answer_and_oracle(cuda):
+    from nvmolkit_b200.clustering import butina
+
+    d = np.ones((10, 10))
+    np.fill_diagonal(d, 0.0)
+    for j in (1, 2, 3):
+        d[0, j] = d[j, 0] = 0.05
+    for j in (5, 6):
+        d[4, j] = d[j, 4] = 0.05
+    ids, cen = butina(torch.from_numpy(d).to(cuda), 0.1, return_centroids=True)
+    ids, cen = ids.numpy(), cen.numpy()
+    assert sorted(np.nonzero(ids == 0)[0].tolist()) == [0, 1, 2, 3] and cen[0] == 0  # tests/test_butina.cpp:241-273
+    assert sorted(np.nonzero(ids == 1)[0].tolist()) == [4, 5, 6] and cen[1] == 4
+    assert len(cen) == 5
+
+    fp = S.clustered_fingerprints(30, 30, seed=77)
+    dist = 1.0 - oracle.similarity_cross(fp)
+    for cutoff in (0.1, 0.3, 0.6):
+        ids, cen = butina(torch.from_numpy(dist).to(cuda), cutoff, return_centroids=True)
+        ids_cpu, cen_cpu = oracle.butina_dense(dist, cutoff)
+        _assert_same_clustering(ids.numpy(), cen.numpy(), ids_cpu, cen_cpu)
+    with pytest.raises(ValueError):
+        butina(torch.from_numpy(dist).to(cuda), 0.3, neighborlist_max_size=17)
+
+
+# ------------------------------------------------------------------ morgan
+@pytest.mark.parametrize("radius", [0, 1, 2, 3, 5])
+@pytest.mark.parametrize("fp_size", [128, 1024, 2048])
+def test_morgan_bit_exact(cuda, radius, fp_size):
+    from nvmolkit_b200.fingerprints import MorganFingerprintGenerator
+
+    g = S.random_molgraphs(400, min_atoms=1, max_atoms=70, seed=radius * 10 + fp_size)
+    got = MorganFingerprintGenerator(radius, fp_size).GetFingerprints(g).numpy().view(np.uint32)
+    want = oracle.morgan(g.atom_starts, g.bond_starts, g.atom_inv, g.bond_inv, g.bond_a, g.bond_b, radius, fp_size)
+    assert got.shape == want.shape and (got == want).all()
+    assert (got != 0).any(axis=1).all()  # regression test_gh_issue_84: never empty
+
+
+def test_morgan_large_molecules_on_gpu(cuda):
+    # the reference sends >=128-atom molecules to a CPU twin (src/morgan_fingerprint_gpu.cpp:181-198); here they stay on the GPU
+    from nvmolkit_b200.fingerprints import MorganFingerprintGenerator
+
+    g = S.random_molgraphs(40, min_atoms=120, max_atoms=300, seed=5)
+    got = MorganFingerprintGenerator(3, 2048).GetFingerprints(g).numpy().view(np.uint32)
+    want = oracle.morgan(g.atom_starts, g.bond_starts, g.atom_inv, g.bond_inv, g.bond_a, g.bond_b, 3, 2048)
+    assert (got == want).all()
+
+
+def test_morgan_known_answer_bits(cuda):
+    """Bits of pentane at radius 2 = the 7 distinct codes of the golden test, folded."""
+    from nvmolkit_b200.fingerprints import MorganFingerprintGenerator, unpack_fingerprint
+    from nvmolkit_b200.molgraph import MolGraphBatch, atom_invariant
+
+    t, m = atom_invariant(6, 4, 3, 0, 0, False), atom_invariant(6, 4, 2, 0, 0, False)
+    g = MolGraphBatch([0, 5], [0, 4], [t, m, m, m, t], [1, 1, 1, 1], [0, 1, 2, 3], [1, 2, 3, 4])
+    fp = MorganFingerprintGenerator(2, 2048).GetFingerprints(g)
+    bits = unpack_fingerprint(fp.torch()).cpu().numpy()[0]
+    codes = oracle.morgan_codes([t, m, m, m, t], [1, 1, 1, 1], [0, 1, 2, 3], [1, 2, 3, 4], 2)
+    assert set(np.nonzero(bits)[0].tolist()) == {int(c) % 2048 for c in codes}
+    assert len(set(codes.tolist())) == 7
+
+
+def test_pack_unpack_roundtrip(cuda):
+    from nvmolkit_b200.fingerprints import pack_fingerprint, unpack_fingerprint
+
+    fp = torch.from_numpy(S.random_fingerprints(9, bits=256).view(np.int32)).to(cuda)
+    assert (pack_fingerprint(unpack_fingerprint(fp)) == fp).all()
