@@ -70,8 +70,10 @@ __global__ void threshTableKernel(int maxS, double cutoff, uint16_t* __restrict_
   int found = 0xFFFF;
   for (int c = 0; c <= s / 2; ++c) {
     const int    u   = s - c;
-    const double sim = (c == 0 || u == 0) ? 0.0 : static_cast<double>(c) / static_cast<double>(u);
-    if (1.0 - sim <= cutoff) {
+    // explicit round-to-nearest intrinsics: never contracted into an FMA, so the result is the two-rounding value
+    // a CPU computes for `1.0 - c/u`
+    const double sim = (c == 0 || u == 0) ? 0.0 : __ddiv_rn(static_cast<double>(c), static_cast<double>(u));
+    if (__dsub_rn(1.0, sim) <= cutoff) {
       found = c;
       break;
     }
@@ -190,9 +192,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         double    v = 0.0;
         if (c != 0) {
           if constexpr (MODE == kMaterialiseTanimoto) {
-            v = static_cast<double>(c) / static_cast<double>(pa[i] + pb[j] - c);
+            v = __ddiv_rn(static_cast<double>(c), static_cast<double>(pa[i] + pb[j] - c));
           } else {
-            v = static_cast<double>(c) / sqrt(static_cast<double>(pa[i]) * static_cast<double>(pb[j]));
+            v = __ddiv_rn(static_cast<double>(c),
+                          __dsqrt_rn(__dmul_rn(static_cast<double>(pa[i]), static_cast<double>(pb[j]))));
           }
         }
         __stcs(orow + col, v);
@@ -213,8 +216,11 @@ __global__ void __launch_bounds__(kThreads, 2)
         if constexpr (MODE == kCountTanimoto) {
           h = c >= static_cast<int>(__ldg(p.thresh + pa[i] + pb[j]));
         } else {
-          const double sim = (c == 0) ? 0.0 : static_cast<double>(c) / sqrt(static_cast<double>(pa[i]) * pb[j]);
-          h                = (1.0 - sim <= p.cutoff);
+          const double sim =
+            (c == 0) ? 0.0
+                     : __ddiv_rn(static_cast<double>(c),
+                                 __dsqrt_rn(__dmul_rn(static_cast<double>(pa[i]), static_cast<double>(pb[j]))));
+          h = (__dsub_rn(1.0, sim) <= p.cutoff);
         }
         if (ok && h) hits |= 1ull << (i * 8 + j);
       }
