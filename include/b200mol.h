@@ -118,6 +118,90 @@ int b200mol_morgan(const int32_t* d_atom_starts, const int32_t* d_bond_starts, c
                    const uint32_t* d_bond_inv, const uint16_t* d_bond_a, const uint16_t* d_bond_b, size_t nMols,
                    int maxAtomsPerMol, int maxBondsPerMol, int radius, int fpBits, uint32_t* d_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched force fields + BFGS (the conformer hot path).
+ *
+ * Data model (replaces the reference's BatchedMolecularSystemHost/Device, src/forcefields/mmff.h:153-436,
+ * src/forcefields/dist_geom.h:31-586): a MOLECULE table holds the flattened terms once per molecule, CSR by
+ * molecule, with molecule-LOCAL int16 atom indices [n][K] and fp64 parameter records [n][P]; a CONFORMER batch
+ * points into it (conformer c is molecule conf_mol[c], its coordinates start at atom conf_atom_start[c]), so the
+ * conformers of one molecule share one term block. All pointers inside the structs are DEVICE pointers; the structs
+ * themselves are passed from host memory.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct b200mol_term_table {
+  const int32_t* starts; /* [nMols+1] */
+  const int16_t* idx;    /* [n][K] */
+  const double*  par;    /* [n][P] */
+} b200mol_term_table;
+
+/* MMFF94 (term math: src/forcefields/mmff_kernels_device.cuh:241-661; layout source: src/forcefields/mmff.h:37-145)
+ *   bond    K2 P2 {r0, kb}                  angle   K3 P3 {theta0, ka, isLinear}
+ *   strbend K3 P5 {theta0, r0_ij, r0_kj, kba_ijk, kba_kji}      oop K4 P1 {koop}   (j = idx[1] is the centre)
+ *   torsion K4 P3 {V1, V2, V3}              vdw     K2 P2 {R*_ij, eps_ij}
+ *   ele     K2 P3 {q_i q_j / dielectric, dielModel (1 | 2), is14} */
+typedef struct b200mol_mmff_system {
+  int32_t            nMols;
+  const int32_t*     atomCounts; /* [nMols] */
+  b200mol_term_table bond, angle, strbend, oop, torsion, vdw, ele;
+} b200mol_mmff_system;
+
+/* Distance geometry (src/forcefields/dist_geom_kernels_device.cuh:37-231; src/forcefields/dist_geom.h:31-56)
+ *   dist K2 P3 {lb^2, ub^2, weight}    chiral K4 P2 {volUpper, volLower}    fourth K1 P0 (par may be NULL) */
+typedef struct b200mol_dg_system {
+  int32_t            nMols;
+  const int32_t*     atomCounts;
+  b200mol_term_table dist, chiral, fourth;
+} b200mol_dg_system;
+
+/* ETK / 3-D refinement terms on 4-D coordinate storage (dist_geom_kernels_device.cuh:237-830; dist_geom.h:73-128)
+ *   torsion K4 P12 {V1..V6, sign1..sign6}   improper K4 P4 {C0, C1, C2, k}
+ *   dist12 / dist13 / longrange K2 P3 {min, max, k}     angle13 K3 P2 {minDeg, maxDeg} */
+typedef struct b200mol_etk_system {
+  int32_t            nMols;
+  const int32_t*     atomCounts;
+  b200mol_term_table torsion, improper, dist12, dist13, angle13, longrange;
+} b200mol_etk_system;
+
+/* Energies (d_energy[nConf]) and, when d_grad != NULL, gradients (d_grad[totalAtoms*dim], overwritten) of a
+ * conformer batch. Replaces launch*EnergyKernel / launch*GradientKernel + combinedEnergies/GradKernel
+ * (src/forcefields/mmff_kernels.h, mmff_kernels.cu:1067-1125; dist_geom_kernels.cu). */
+int b200mol_mmff_energy_grad(const b200mol_mmff_system* sys, int32_t nConf, const int32_t* d_conf_mol,
+                             const int32_t* d_conf_atom_start, const double* d_pos, double* d_energy, double* d_grad,
+                             void* stream);
+int b200mol_dg_energy_grad(const b200mol_dg_system* sys, int dim, double chiralWeight, double fourthDimWeight,
+                           int32_t nConf, const int32_t* d_conf_mol, const int32_t* d_conf_atom_start,
+                           const double* d_pos, double* d_energy, double* d_grad, void* stream);
+int b200mol_etk_energy_grad(const b200mol_etk_system* sys, int plain, int32_t nConf, const int32_t* d_conf_mol,
+                            const int32_t* d_conf_atom_start, const double* d_pos, double* d_energy, double* d_grad,
+                            void* stream);
+
+/* BFGS minimisation of every conformer of the batch (RDKit BFGSOpt.h semantics incl. ForceField::minimize gradient
+ * scaling, RDKit >= 2025.09 rule), one CTA per conformer, whole minimisation in one persistent kernel launch.
+ *   d_pos      in/out coordinates [totalAtoms*dim]        d_energy  out, energy at the returned coordinates
+ *   d_status   out int8[nConf]: 0 = converged, 1 = max_iters reached (same meaning as the reference's statuses)
+ *   d_iters    out int32[nConf] BFGS iterations used (may be NULL)
+ *   d_active   optional uint8[nConf]: conformers with 0 are skipped (reference: activeThisStage)
+ *   max_atoms  largest atom count in the batch (sizes shared memory and the inverse-Hessian slabs)
+ * Replaces launchBfgsMinimizePerMolKernel[ETK|DG] (src/minimizer/bfgs_minimize.cu:1086-1146), BfgsBatchMinimizer::
+ * minimize (:978-1053) and updateInverseHessianBFGSBatch (src/minimizer/bfgs_hessian.cu:373-438). */
+int b200mol_mmff_minimize(const b200mol_mmff_system* sys, int32_t nConf, const int32_t* d_conf_mol,
+                          const int32_t* d_conf_atom_start, int max_atoms, double* d_pos, int max_iters,
+                          double grad_tol, const uint8_t* d_active, double* d_energy, int8_t* d_status,
+                          int32_t* d_iters, void* stream);
+int b200mol_dg_minimize(const b200mol_dg_system* sys, int dim, double chiralWeight, double fourthDimWeight,
+                        int32_t nConf, const int32_t* d_conf_mol, const int32_t* d_conf_atom_start, int max_atoms,
+                        double* d_pos, int max_iters, double grad_tol, const uint8_t* d_active, double* d_energy,
+                        int8_t* d_status, int32_t* d_iters, void* stream);
+int b200mol_etk_minimize(const b200mol_etk_system* sys, int plain, int32_t nConf, const int32_t* d_conf_mol,
+                         const int32_t* d_conf_atom_start, int max_atoms, double* d_pos, int max_iters,
+                         double grad_tol, const uint8_t* d_active, double* d_energy, int8_t* d_status,
+                         int32_t* d_iters, void* stream);
+/* Analytic test potential E = sum_i w_i (x_i - c_i)^power, power in {2, 4}; system s owns x[starts[s]..starts[s+1])
+ * (the reference drives its BFGS tests through such a user force field, tests/test_bfgs_minimizer.cu:822-930). */
+int b200mol_poly_minimize(int32_t nSys, const int32_t* d_starts, int max_dim, int power, const double* d_w,
+                          const double* d_c, double* d_x, int max_iters, double grad_tol, int scale_grads,
+                          double* d_energy, int8_t* d_status, int32_t* d_iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

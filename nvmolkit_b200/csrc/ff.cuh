@@ -1,0 +1,520 @@
+// Flattened force fields, block-cooperative evaluation for ONE conformer held in shared memory (sm_100a).
+//
+// Every force field exposes   View (this molecule's term ranges),
+//                             energy(view, pos, tid, nT)  -> this thread's partial energy,
+//                             grad(view, pos, grad, tid, nT) -> accumulates into shared-memory grad (fp64 atomics).
+// Threads stride over the CSR term ranges; records are [n][K] int16 indices + [n][P] fp64 parameters, so a warp
+// reads one contiguous span per term type. All arithmetic is fp64 (the reference drops to fp32 inside most terms,
+// src/forcefields/mmff_kernels_device.cuh:37-107,196-237; its own acceptance bars are looser than north_star's 1e-4).
+//
+// Term math follows RDKit as restated by the reference: MMFF src/forcefields/mmff_kernels_device.cuh:28-661,
+// DG/ETK src/forcefields/dist_geom_kernels_device.cuh:37-830 (including RDKit's quirks: chiral/4th-dim gradient
+// without the factor 2, 6-fold ETK torsion gradient using V5).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+namespace ff {
+
+constexpr double kDeg2Rad = 3.14159265358979323846 / 180.0;
+constexpr double kRad2Deg = 180.0 / 3.14159265358979323846;
+
+struct V3 {
+  double x, y, z;
+};
+__device__ __forceinline__ V3 operator-(const V3& a, const V3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator+(const V3& a, const V3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator*(const V3& a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator-(const V3& a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(const V3& a, const V3& b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+template <int DIM>
+__device__ __forceinline__ V3 ld(const double* pos, int a) {
+  return {pos[a * DIM], pos[a * DIM + 1], pos[a * DIM + 2]};
+}
+template <int DIM>
+__device__ __forceinline__ void acc(double* grad, int a, const V3& g) {
+  atomicAdd(&grad[a * DIM], g.x);
+  atomicAdd(&grad[a * DIM + 1], g.y);
+  atomicAdd(&grad[a * DIM + 2], g.z);
+}
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(hi, fmax(lo, v)); }
+__device__ __forceinline__ bool   isZero(double v) { return v < 1.0e-10 && v > -1.0e-10; }
+
+struct Range {
+  int beg, end;
+};
+__device__ __forceinline__ Range range(const b200mol_term_table& t, int mol) { return {t.starts[mol], t.starts[mol + 1]}; }
+
+// ============================================================================================ MMFF94
+struct Mmff {
+  static constexpr int kDim = 3;
+  using System            = b200mol_mmff_system;
+  struct Params {};
+  struct View {
+    const System* s;
+    Range         bond, angle, strbend, oop, torsion, vdw, ele;
+  };
+  __device__ static View view(const System& s, int mol, const Params&) {
+    return {&s,          range(s.bond, mol),    range(s.angle, mol), range(s.strbend, mol),
+            range(s.oop, mol), range(s.torsion, mol), range(s.vdw, mol),   range(s.ele, mol)};
+  }
+
+  template <bool GRAD>
+  __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
+    const System& s = *v.s;
+    double        e = 0.0;
+    // ---- bond stretch ----
+    for (int t = v.bond.beg + tid; t < v.bond.end; t += nT) {
+      const int    i = s.bond.idx[2 * t], j = s.bond.idx[2 * t + 1];
+      const double r0 = s.bond.par[2 * t], kb = s.bond.par[2 * t + 1];
+      const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
+      const double dist = sqrt(dot(d, d)), dr = dist - r0;
+      constexpr double cs = -2.0;
+      if (!GRAD) {
+        e += 143.9325 / 2.0 * kb * dr * dr * (1.0 + cs * dr + 7.0 / 12.0 * cs * cs * dr * dr);
+      } else {
+        const double de = 143.9325 * kb * dr * (1.0 + 1.5 * cs * dr + 2.0 * 7.0 / 12.0 * cs * cs * dr * dr);
+        const V3     g  = dist > 0.0 ? d * (de / dist) : V3{kb * 0.01, kb * 0.01, kb * 0.01};
+        acc<3>(grad, i, g);
+        acc<3>(grad, j, -g);
+      }
+    }
+    // ---- angle bend ----
+    for (int t = v.angle.beg + tid; t < v.angle.end; t += nT) {
+      const int    i = s.angle.idx[3 * t], j = s.angle.idx[3 * t + 1], k = s.angle.idx[3 * t + 2];
+      const double theta0 = s.angle.par[3 * t], ka = s.angle.par[3 * t + 1];
+      const bool   linear = s.angle.par[3 * t + 2] != 0.0;
+      const V3     d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
+      const double l1sq = dot(d1, d1), l2sq = dot(d2, d2), l1 = sqrt(l1sq), l2 = sqrt(l2sq);
+      const double cosT = clampd(dot(d1, d2) / (l1 * l2), -1.0, 1.0);
+      const double dT   = kRad2Deg * acos(cosT) - theta0;
+      if (!GRAD) {
+        e += linear ? 143.9325 * ka * (1.0 + cosT)
+                    : 0.5 * 143.9325 * kDeg2Rad * kDeg2Rad * ka * dT * dT * (1.0 + (-0.4 * kDeg2Rad) * dT);
+      } else {
+        const double sinSq = 1.0 - cosT * cosT;
+        if (isZero(sinSq) || isZero(l1sq) || isZero(l2sq)) continue;
+        const double de = linear ? -143.9325 * ka * sqrt(sinSq)
+                                 : 143.9325 * kDeg2Rad * ka * dT * (1.0 + (-0.006981317 * 1.5) * dT);
+        const double cf = -de / sqrt(sinSq);
+        const V3     n1 = d1 * (1.0 / l1), n2 = d2 * (1.0 / l2);
+        const V3     a = (n2 - n1 * cosT) * (cf / l1), b = (n1 - n2 * cosT) * (cf / l2);
+        acc<3>(grad, i, a);
+        acc<3>(grad, j, -(a + b));
+        acc<3>(grad, k, b);
+      }
+    }
+    // ---- stretch-bend ----
+    for (int t = v.strbend.beg + tid; t < v.strbend.end; t += nT) {
+      const int     i = s.strbend.idx[3 * t], j = s.strbend.idx[3 * t + 1], k = s.strbend.idx[3 * t + 2];
+      const double* q = s.strbend.par + 5 * t;
+      const V3      d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
+      const double  l1 = sqrt(dot(d1, d1)), l2 = sqrt(dot(d2, d2));
+      const double  cosT = clampd(dot(d1, d2) / (l1 * l2), -1.0, 1.0);
+      const double  dT = kRad2Deg * acos(cosT) - q[0], dr1 = l1 - q[1], dr2 = l2 - q[2];
+      if (!GRAD) {
+        e += 2.51210 * dT * (dr1 * q[3] + dr2 * q[4]);
+      } else {
+        constexpr double pre = 143.9325 * kDeg2Rad;
+        const double     invSin = fmin(1.0 / sqrt(1.0 - cosT * cosT), 1.0e8);
+        const double     bt = kRad2Deg * (q[3] * dr1 + q[4] * dr2) * invSin;
+        const V3         n1 = d1 * (1.0 / l1), n2 = d2 * (1.0 / l2);
+        const V3         a = (n2 - n1 * cosT) * (1.0 / l1), b = (n1 - n2 * cosT) * (1.0 / l2);
+        acc<3>(grad, i, (n1 * (dT * q[3]) - a * bt) * pre);
+        acc<3>(grad, j, ((n1 * q[3] + n2 * q[4]) * (-dT) + (a + b) * bt) * pre);
+        acc<3>(grad, k, (n2 * (dT * q[4]) - b * bt) * pre);
+      }
+    }
+    // ---- out-of-plane ----
+    for (int t = v.oop.beg + tid; t < v.oop.end; t += nT) {
+      const int    i = s.oop.idx[4 * t], j = s.oop.idx[4 * t + 1], k = s.oop.idx[4 * t + 2], l = s.oop.idx[4 * t + 3];
+      const double koop = s.oop.par[t];
+      V3           ji = ld<3>(pos, i) - ld<3>(pos, j), jk = ld<3>(pos, k) - ld<3>(pos, j), jl = ld<3>(pos, l) - ld<3>(pos, j);
+      const double li = sqrt(dot(ji, ji)), lk = sqrt(dot(jk, jk)), ll = sqrt(dot(jl, jl));
+      ji = ji * (1.0 / li);
+      jk = jk * (1.0 / lk);
+      jl = jl * (1.0 / ll);
+      V3 n = cross(-ji, jk);
+      n    = n * (1.0 / sqrt(dot(n, n)));
+      const double sinChi = clampd(dot(jl, n), -1.0, 1.0);
+      const double chi    = kRad2Deg * asin(sinChi);
+      if (!GRAD) {
+        e += 0.5 * 143.9325 * kDeg2Rad * kDeg2Rad * koop * chi * chi;
+      } else {
+        const double cosChiSq = 1.0 - sinChi * sinChi;
+        const double invCosChi = cosChiSq > 0.0 ? 1.0 / sqrt(cosChiSq) : 1.0e8;
+        const double cosT = clampd(dot(ji, jk), -1.0, 1.0);
+        const double invSinT = 1.0 / sqrt(fmax(1.0 - cosT * cosT, 1.0e-8));
+        const double de = 143.9325 * kDeg2Rad * koop * chi;
+        const V3     t1 = cross(jl, jk), t2 = cross(ji, jl), t3 = cross(jk, ji);
+        const double term1 = invCosChi * invSinT, term2 = sinChi * invCosChi * invSinT * invSinT;
+        const V3     g1 = (t1 * term1 - (ji - jk * cosT) * term2) * (1.0 / li);
+        const V3     g3 = (t2 * term1 - (jk - ji * cosT) * term2) * (1.0 / lk);
+        const V3     g4 = (t3 * term1 - jl * (sinChi * invCosChi)) * (1.0 / ll);
+        acc<3>(grad, i, g1 * de);
+        acc<3>(grad, j, (g1 + g3 + g4) * (-de));
+        acc<3>(grad, k, g3 * de);
+        acc<3>(grad, l, g4 * de);
+      }
+    }
+    // ---- torsion ----
+    for (int t = v.torsion.beg + tid; t < v.torsion.end; t += nT) {
+      const int16_t* ix = s.torsion.idx + 4 * t;
+      const double   V1 = s.torsion.par[3 * t], V2 = s.torsion.par[3 * t + 1], V3c = s.torsion.par[3 * t + 2];
+      const V3       d1 = ld<3>(pos, ix[0]) - ld<3>(pos, ix[1]), d2 = ld<3>(pos, ix[2]) - ld<3>(pos, ix[1]),
+               d4 = ld<3>(pos, ix[3]) - ld<3>(pos, ix[2]);
+      V3           c1 = cross(d1, d2), c2 = cross(-d2, d4);
+      const double n1 = 1.0 / sqrt(dot(c1, c1)), n2 = 1.0 / sqrt(dot(c2, c2));
+      if (!GRAD) {
+        const double cosPhi = clampd(dot(c1, c2) * n1 * n2, -1.0, 1.0);
+        const double phi    = acos(cosPhi);
+        e += 0.5 * (V1 * (1.0 + cosPhi) + V2 * (1.0 - cos(2.0 * phi)) + V3c * (1.0 + cos(3.0 * phi)));
+      } else {
+        const double i1 = fmin(n1, 1.0e5), i2 = fmin(n2, 1.0e5);
+        c1 = c1 * i1;
+        c2 = c2 * i2;
+        const double cosPhi = clampd(dot(c1, c2), -1.0, 1.0);
+        const double sinSq  = 1.0 - cosPhi * cosPhi;
+        double       sinTerm = 0.0;
+        if (sinSq > 0.0) sinTerm = 0.5 * (V1 - 2.0 * V2 * (2.0 * cosPhi) + 3.0 * V3c * (3.0 - 4.0 * sinSq));
+        const V3 a = (c2 - c1 * cosPhi) * i1, b = (c1 - c2 * cosPhi) * i2;
+        acc<3>(grad, ix[0], V3{a.z * d2.y - a.y * d2.z, a.x * d2.z - a.z * d2.x, a.y * d2.x - a.x * d2.y} * sinTerm);
+        acc<3>(grad, ix[1],
+               V3{a.y * (d2.z - d1.z) + a.z * (d1.y - d2.y) + b.y * (-d4.z) + b.z * (d4.y),
+                  a.x * (d1.z - d2.z) + a.z * (d2.x - d1.x) + b.x * (d4.z) + b.z * (-d4.x),
+                  a.x * (d2.y - d1.y) + a.y * (d1.x - d2.x) + b.x * (-d4.y) + b.y * (d4.x)} * sinTerm);
+        acc<3>(grad, ix[2],
+               V3{a.y * (d1.z) + a.z * (-d1.y) + b.y * (d4.z + d2.z) + b.z * (-d4.y - d2.y),
+                  a.x * (-d1.z) + a.z * (d1.x) + b.x * (-d4.z - d2.z) + b.z * (d4.x + d2.x),
+                  a.x * (d1.y) + a.y * (-d1.x) + b.x * (d4.y + d2.y) + b.y * (-d4.x - d2.x)} * sinTerm);
+        acc<3>(grad, ix[3],
+               V3{b.y * (-d2.z) - b.z * (-d2.y), b.z * (-d2.x) - b.x * (-d2.z), b.x * (-d2.y) - b.y * (-d2.x)} * sinTerm);
+      }
+    }
+    // ---- buffered 14-7 van der Waals ----
+    for (int t = v.vdw.beg + tid; t < v.vdw.end; t += nT) {
+      const int    i = s.vdw.idx[2 * t], j = s.vdw.idx[2 * t + 1];
+      const double R = s.vdw.par[2 * t], eps = s.vdw.par[2 * t + 1];
+      const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
+      const double d2   = dot(d, d), dist = sqrt(d2);
+      if (!GRAD) {
+        const double R2 = R * R, R7 = R2 * R2 * R2 * R, dist7 = d2 * d2 * d2 * dist;
+        const double t1 = 1.07 * R / (dist + 0.07 * R), t1sq = t1 * t1, t17 = t1sq * t1sq * t1sq * t1;
+        e += eps * t17 * (1.12 * R7 / (dist7 + 0.12 * R7) - 2.0);
+      } else {
+        const double q = dist / R, q2 = q * q, q6 = q2 * q2 * q2, q7p = q6 * q + 0.12;
+        const double tt = 1.07 / (q + 0.07), tt2 = tt * tt, t7 = tt2 * tt2 * tt2 * tt;
+        const double de = eps / R * t7 * (-1.12 * 7.0 * q6 / (q7p * q7p) + ((-1.12 * 7.0 / q7p + 14.0) / (q + 0.07)));
+        const V3     g  = dist <= 0.0 ? V3{R * 0.01, R * 0.01, R * 0.01} : d * (de / dist);
+        acc<3>(grad, i, g);
+        acc<3>(grad, j, -g);
+      }
+    }
+    // ---- buffered Coulomb ----
+    for (int t = v.ele.beg + tid; t < v.ele.end; t += nT) {
+      const int    i = s.ele.idx[2 * t], j = s.ele.idx[2 * t + 1];
+      const double ct = s.ele.par[3 * t];
+      const bool   sq = s.ele.par[3 * t + 1] == 2.0, is14 = s.ele.par[3 * t + 2] != 0.0;
+      const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
+      const double dist = sqrt(dot(d, d)), rb = dist + 0.05;
+      if (!GRAD) {
+        double en = 332.0716 * ct / (sq ? rb * rb : rb);
+        if (is14) en *= 0.75;
+        e += en;
+      } else {
+        double de = sq ? -2.0 * 332.0716 * ct / (rb * rb * rb) : -332.0716 * ct / (rb * rb);
+        if (is14) de *= 0.75;
+        const V3 g = d * (de / dist);
+        acc<3>(grad, i, g);
+        acc<3>(grad, j, -g);
+      }
+    }
+    return e;
+  }
+};
+
+// ============================================================================================ distance geometry
+template <int DIM>
+struct Dg {
+  static constexpr int kDim = DIM;
+  using System            = b200mol_dg_system;
+  struct Params {
+    double chiralWeight, fourthWeight;
+  };
+  struct View {
+    const System* s;
+    Range         dist, chiral, fourth;
+    double        cw, fw;
+  };
+  __device__ static View view(const System& s, int mol, const Params& p) {
+    return {&s, range(s.dist, mol), range(s.chiral, mol), range(s.fourth, mol), p.chiralWeight, p.fourthWeight};
+  }
+  template <bool GRAD>
+  __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
+    const System& s = *v.s;
+    double        e = 0.0;
+    for (int t = v.dist.beg + tid; t < v.dist.end; t += nT) {
+      const int    i = s.dist.idx[2 * t], j = s.dist.idx[2 * t + 1];
+      const double lb2 = s.dist.par[3 * t], ub2 = s.dist.par[3 * t + 1], w = s.dist.par[3 * t + 2];
+      double       dd[DIM], d2 = 0.0;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) {
+        dd[c] = pos[i * DIM + c] - pos[j * DIM + c];
+        d2 += dd[c] * dd[c];
+      }
+      if (d2 > ub2) {
+        const double val = d2 / ub2 - 1.0;
+        if (!GRAD) {
+          if (val > 0.0) e += w * val * val;
+        } else {
+          const double pre = w * 4.0 * val / ub2;
+#pragma unroll
+          for (int c = 0; c < DIM; ++c) {
+            atomicAdd(&grad[i * DIM + c], pre * dd[c]);
+            atomicAdd(&grad[j * DIM + c], -pre * dd[c]);
+          }
+        }
+      } else if (d2 < lb2) {
+        const double l2d2 = d2 + lb2;
+        if (!GRAD) {
+          const double val = 2.0 * lb2 / l2d2 - 1.0;
+          if (val > 0.0) e += w * val * val;
+        } else {
+          const double pre = w * 8.0 * lb2 * (1.0 - 2.0 * lb2 / l2d2) / (l2d2 * l2d2);
+#pragma unroll
+          for (int c = 0; c < DIM; ++c) {
+            atomicAdd(&grad[i * DIM + c], pre * dd[c]);
+            atomicAdd(&grad[j * DIM + c], -pre * dd[c]);
+          }
+        }
+      }
+    }
+    for (int t = v.chiral.beg + tid; t < v.chiral.end; t += nT) {
+      const int16_t* ix = s.chiral.idx + 4 * t;
+      const double   ub = s.chiral.par[2 * t], lb = s.chiral.par[2 * t + 1];
+      const V3       p1 = ld<DIM>(pos, ix[0]), p2 = ld<DIM>(pos, ix[1]), p3 = ld<DIM>(pos, ix[2]), p4 = ld<DIM>(pos, ix[3]);
+      const V3       v1 = p1 - p4, v2 = p2 - p4, v3 = p3 - p4;
+      const double   vol = dot(v1, cross(v2, v3));
+      double         diff;
+      if (vol < lb) diff = vol - lb;
+      else if (vol > ub) diff = vol - ub;
+      else continue;
+      if (!GRAD) {
+        e += v.cw * diff * diff;
+      } else {
+        const double pre = v.cw * diff;  // RDKit: no factor 2
+        acc<DIM>(grad, ix[0], cross(v2, v3) * pre);
+        acc<DIM>(grad, ix[1], cross(v3, v1) * pre);
+        acc<DIM>(grad, ix[2], V3{v2.z * v1.y - v2.y * v1.z, v2.x * v1.z - v2.z * v1.x, v2.y * v1.x - v2.x * v1.y} * pre);
+        acc<DIM>(grad, ix[3],
+                 V3{p1.z * (p2.y - p3.y) + p2.z * (p3.y - p1.y) + p3.z * (p1.y - p2.y),
+                    p1.x * (p2.z - p3.z) + p2.x * (p3.z - p1.z) + p3.x * (p1.z - p2.z),
+                    p1.y * (p2.x - p3.x) + p2.y * (p3.x - p1.x) + p3.y * (p1.x - p2.x)} * pre);
+      }
+    }
+    if constexpr (DIM == 4) {
+      for (int t = v.fourth.beg + tid; t < v.fourth.end; t += nT) {
+        const int    a  = s.fourth.idx[t];
+        const double w4 = pos[a * 4 + 3];
+        if (!GRAD) e += v.fw * w4 * w4;
+        else atomicAdd(&grad[a * 4 + 3], v.fw * w4);  // RDKit: no factor 2
+      }
+    }
+    return e;
+  }
+};
+
+// ============================================================================================ ETK (4-D storage)
+struct Etk {
+  static constexpr int kDim = 4;
+  using System            = b200mol_etk_system;
+  struct Params {
+    int plain;  // 1 = skip improper terms (ETDG variant)
+  };
+  struct View {
+    const System* s;
+    Range         torsion, improper, d12, d13, a13, lr;
+  };
+  __device__ static View view(const System& s, int mol, const Params& p) {
+    Range imp = range(s.improper, mol);
+    if (p.plain) imp.end = imp.beg;
+    return {&s, range(s.torsion, mol), imp, range(s.dist12, mol), range(s.dist13, mol), range(s.angle13, mol),
+            range(s.longrange, mol)};
+  }
+
+  template <bool GRAD>
+  __device__ static double distTerms(const b200mol_term_table& T, Range r, const double* pos, double* grad, int tid, int nT) {
+    double e = 0.0;
+    for (int t = r.beg + tid; t < r.end; t += nT) {
+      const int    i = T.idx[2 * t], j = T.idx[2 * t + 1];
+      const double mn = T.par[3 * t], mx = T.par[3 * t + 1], fk = T.par[3 * t + 2];
+      const V3     d  = ld<4>(pos, i) - ld<4>(pos, j);
+      const double d2 = dot(d, d);
+      double       ref;
+      if (d2 < mn * mn) ref = mn;
+      else if (d2 > mx * mx) ref = mx;
+      else continue;
+      const double dist = sqrt(d2);
+      if (!GRAD) {
+        e += 0.5 * fk * (dist - ref) * (dist - ref);
+      } else {
+        const V3 g = d * (fk * (dist - ref) / fmax(1.0e-8, dist));
+        acc<4>(grad, i, g);
+        acc<4>(grad, j, -g);
+      }
+    }
+    return e;
+  }
+
+  template <bool GRAD>
+  __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
+    const System& s = *v.s;
+    double        e = 0.0;
+    for (int t = v.torsion.beg + tid; t < v.torsion.end; t += nT) {
+      const int16_t* ix = s.torsion.idx + 4 * t;
+      const double*  fc = s.torsion.par + 12 * t;
+      const double*  sg = fc + 6;
+      const V3       p1 = ld<4>(pos, ix[0]), p2 = ld<4>(pos, ix[1]), p3 = ld<4>(pos, ix[2]), p4 = ld<4>(pos, ix[3]);
+      const V3       r1 = p1 - p2, r2 = p3 - p2, r3 = p2 - p3, r4 = p4 - p3;
+      V3             t0 = cross(r1, r2), t1 = cross(r3, r4);
+      const double   d02 = dot(t0, t0), d12 = dot(t1, t1);
+      if (!GRAD) {
+        const double comb = d02 * d12;
+        const double c    = isZero(comb) ? 0.0 : clampd(dot(t0, t1) / sqrt(comb), -1.0, 1.0);
+        const double c2 = c * c, c3 = c * c2, c4 = c * c3, c5 = c * c4, c6 = c * c5;
+        e += fc[0] * (1.0 + sg[0] * c) + fc[1] * (1.0 + sg[1] * (2.0 * c2 - 1.0)) +
+             fc[2] * (1.0 + sg[2] * (4.0 * c3 - 3.0 * c)) + fc[3] * (1.0 + sg[3] * (8.0 * c4 - 8.0 * c2 + 1.0)) +
+             fc[4] * (1.0 + sg[4] * (16.0 * c5 - 20.0 * c3 + 5.0 * c)) +
+             fc[5] * (1.0 + sg[5] * (32.0 * c6 - 48.0 * c4 + 18.0 * c2 - 1.0));
+      } else {
+        if (isZero(d02) || isZero(d12)) continue;
+        const double i0 = 1.0 / sqrt(d02), i1 = 1.0 / sqrt(d12);
+        t0 = t0 * i0;
+        t1 = t1 * i1;
+        const double cp = clampd(dot(t0, t1), -1.0, 1.0);
+        const double sSq = 1.0 - cp * cp, sp = sSq > 0.0 ? sqrt(sSq) : 0.0;
+        const double q2 = cp * cp, q3 = cp * q2, q4 = cp * q3, q5 = cp * q4;
+        const double dE = (-fc[0] * sg[0] * sp - 2.0 * fc[1] * sg[1] * (2.0 * cp * sp) -
+                           3.0 * fc[2] * sg[2] * (4.0 * q2 * sp - sp) - 4.0 * fc[3] * sg[3] * (8.0 * q3 * sp - 4.0 * cp * sp) -
+                           5.0 * fc[4] * sg[4] * (16.0 * q4 * sp - 12.0 * q2 * sp + sp) -
+                           6.0 * fc[4] * sg[4] * (32.0 * q5 * sp - 32.0 * q3 * sp + 6.0 * sp));  // V5 twice: RDKit quirk
+        const double sinTerm = -dE * (isZero(sp) ? 1.0 / cp : 1.0 / sp);
+        const V3     a = (t1 - t0 * cp) * i0, b = (t0 - t1 * cp) * i1;
+        acc<4>(grad, ix[0], V3{a.z * r2.y - a.y * r2.z, a.x * r2.z - a.z * r2.x, a.y * r2.x - a.x * r2.y} * sinTerm);
+        acc<4>(grad, ix[3], V3{b.y * r3.z - b.z * r3.y, b.z * r3.x - b.x * r3.z, b.x * r3.y - b.y * r3.x} * sinTerm);
+        acc<4>(grad, ix[1],
+               V3{a.y * (r2.z - r1.z) + a.z * (r1.y - r2.y) + b.y * (-r4.z) + b.z * (r4.y),
+                  a.x * (r1.z - r2.z) + a.z * (r2.x - r1.x) + b.x * (r4.z) + b.z * (-r4.x),
+                  a.x * (r2.y - r1.y) + a.y * (r1.x - r2.x) + b.x * (-r4.y) + b.y * (r4.x)} * sinTerm);
+        acc<4>(grad, ix[2],
+               V3{a.y * r1.z + a.z * (-r1.y) + b.y * (r4.z - r3.z) + b.z * (r3.y - r4.y),
+                  a.x * (-r1.z) + a.z * r1.x + b.x * (r3.z - r4.z) + b.z * (r4.x - r3.x),
+                  a.x * r1.y + a.y * (-r1.x) + b.x * (r4.y - r3.y) + b.y * (r3.x - r4.x)} * sinTerm);
+      }
+    }
+    for (int t = v.improper.beg + tid; t < v.improper.end; t += nT) {
+      const int16_t* ix = s.improper.idx + 4 * t;
+      const double   C0 = s.improper.par[4 * t], C1 = s.improper.par[4 * t + 1], C2 = s.improper.par[4 * t + 2],
+                   fk = s.improper.par[4 * t + 3];
+      const V3     ji = ld<4>(pos, ix[0]) - ld<4>(pos, ix[1]), jk = ld<4>(pos, ix[2]) - ld<4>(pos, ix[1]),
+               jl = ld<4>(pos, ix[3]) - ld<4>(pos, ix[1]);
+      const double l2i = dot(ji, ji), l2k = dot(jk, jk), l2l = dot(jl, jl);
+      if (!GRAD) {
+        double cosY = 0.0;
+        if (!(l2i < 1.0e-16 || l2k < 1.0e-16 || l2l < 1.0e-16)) {
+          const V3     n   = cross(ji, jk) * (1.0 / sqrt(l2i * l2k));
+          const double l2n = dot(n, n);
+          if (!(l2n < 1.0e-16)) cosY = dot(n, jl) / sqrt(l2l) / sqrt(l2n);
+        }
+        const double sSq = 1.0 - cosY * cosY, sinY = sSq > 0.0 ? sqrt(sSq) : 0.0;
+        e += fk * (C0 + C1 * sinY + C2 * (2.0 * sinY * sinY - 1.0));
+      } else {
+        if (isZero(l2i) || isZero(l2k) || isZero(l2l)) continue;
+        const double ii = 1.0 / sqrt(l2i), ik = 1.0 / sqrt(l2k), il = 1.0 / sqrt(l2l);
+        const V3     a = ji * ii, b = jk * ik, c = jl * il;
+        V3           n = cross(-a, b);
+        n              = n * (1.0 / sqrt(dot(n, n)));
+        const double cY = clampd(dot(n, c), -1.0, 1.0), sY = fmax(sqrt(1.0 - cY * cY), 1.0e-8);
+        const double cT = clampd(dot(a, b), -1.0, 1.0), sTsq = 1.0 - cT * cT, sT = fmax(sqrt(sTsq), 1.0e-8);
+        const double dE = -fk * (C1 * cY - 4.0 * C2 * cY * sY);
+        const V3     t1 = cross(c, b), t2 = cross(a, c), t3 = cross(b, a);
+        const double inv1 = 1.0 / (sY * sT), term2 = cY / (sY * sTsq), cOs = cY / sY;
+        const V3     g1 = (t1 * inv1 - (a - b * cT) * term2) * ii;
+        const V3     g3 = (t2 * inv1 - (b - a * cT) * term2) * ik;
+        const V3     g4 = (t3 * inv1 - c * cOs) * il;
+        acc<4>(grad, ix[0], g1 * dE);
+        acc<4>(grad, ix[1], (g1 + g3 + g4) * (-dE));
+        acc<4>(grad, ix[2], g3 * dE);
+        acc<4>(grad, ix[3], g4 * dE);
+      }
+    }
+    e += distTerms<GRAD>(s.dist12, v.d12, pos, grad, tid, nT);
+    e += distTerms<GRAD>(s.dist13, v.d13, pos, grad, tid, nT);
+    e += distTerms<GRAD>(s.longrange, v.lr, pos, grad, tid, nT);
+    for (int t = v.a13.beg + tid; t < v.a13.end; t += nT) {
+      const int16_t* ix = s.angle13.idx + 3 * t;
+      const double   mn = s.angle13.par[2 * t], mx = s.angle13.par[2 * t + 1];
+      const V3       r1 = ld<4>(pos, ix[0]) - ld<4>(pos, ix[1]), r2 = ld<4>(pos, ix[2]) - ld<4>(pos, ix[1]);
+      const double   l1 = dot(r1, r1), l2 = dot(r2, r2);
+      if (!GRAD) {
+        if (isZero(l1 * l2)) continue;
+        const double ang = kRad2Deg * acos(clampd(dot(r1, r2) / sqrt(l1 * l2), -1.0, 1.0));
+        const double at  = ang < mn ? ang - mn : (ang > mx ? ang - mx : 0.0);
+        e += at * at;
+      } else {
+        const double m1 = fmax(1.0e-5, l1), m2 = fmax(1.0e-5, l2);
+        const double ang = kRad2Deg * acos(clampd(dot(r1, r2) / sqrt(m1 * m2), -1.0, 1.0));
+        const double at  = ang < mn ? ang - mn : (ang > mx ? ang - mx : 0.0);
+        const double dE  = 2.0 * kRad2Deg * at;
+        const V3     rp  = cross(r2, r1);
+        const double pre = dE / sqrt(fmax(dot(rp, rp), 1.0e-10));
+        const V3     a = cross(r1, rp) * (-pre / m1), b = cross(r2, rp) * (pre / m2);
+        acc<4>(grad, ix[0], a);
+        acc<4>(grad, ix[1], -(a + b));
+        acc<4>(grad, ix[2], b);
+      }
+    }
+    return e;
+  }
+};
+
+// ============================================================================================ analytic test potential
+struct Poly {
+  static constexpr int kDim = 1;
+  struct System {
+    int           power;
+    const double* w;
+    const double* c;
+    const int32_t* starts;
+  };
+  struct Params {};
+  struct View {
+    const double* w;
+    const double* c;
+    int           n, power;
+  };
+  __device__ static View view(const System& s, int sys, const Params&) {
+    return {s.w + s.starts[sys], s.c + s.starts[sys], s.starts[sys + 1] - s.starts[sys], s.power};
+  }
+  template <bool GRAD>
+  __device__ static double eval(const View& v, const double* x, double* grad, int tid, int nT) {
+    double e = 0.0;
+    for (int i = tid; i < v.n; i += nT) {
+      const double d = x[i] - v.c[i];
+      if (v.power == 2) {
+        if (!GRAD) e += v.w[i] * d * d;
+        else atomicAdd(&grad[i], 2.0 * v.w[i] * d);
+      } else {
+        if (!GRAD) e += v.w[i] * d * d * d * d;
+        else atomicAdd(&grad[i], 4.0 * v.w[i] * d * d * d);
+      }
+    }
+    return e;
+  }
+};
+
+}  // namespace ff
+}  // namespace b200
