@@ -155,7 +155,11 @@ typedef struct b200mol_dg_system {
 
 /* ETK / 3-D refinement terms on 4-D coordinate storage (dist_geom_kernels_device.cuh:237-830; dist_geom.h:73-128)
  *   torsion K4 P12 {V1..V6, sign1..sign6}   improper K4 P4 {C0, C1, C2, k}
- *   dist12 / dist13 / longrange K2 P3 {min, max, k}     angle13 K3 P2 {minDeg, maxDeg} */
+ *   dist12 / dist13 K2 P4 {min, max, k, fixed}   longrange K2 P3 {min, max, k}   angle13 K3 P2 {minDeg, maxDeg}
+ * `fixed` = the reference's isImproperConstrained: with recentre = 1 every 1-2 / 1-3 window whose fixed flag is 0 is
+ * re-centred on the distance in the STARTING geometry keeping its half-width (the refresh the reference does before its
+ * ETK minimisation, src/etkdg_stage_etk_minimization.cu:32-64,176-202) — evaluated on the fly, the tables stay
+ * read-only and shared by all conformers of the molecule. */
 typedef struct b200mol_etk_system {
   int32_t            nMols;
   const int32_t*     atomCounts;
@@ -171,7 +175,8 @@ int b200mol_mmff_energy_grad(const b200mol_mmff_system* sys, int32_t nConf, cons
 int b200mol_dg_energy_grad(const b200mol_dg_system* sys, int dim, double chiralWeight, double fourthDimWeight,
                            int32_t nConf, const int32_t* d_conf_mol, const int32_t* d_conf_atom_start,
                            const double* d_pos, double* d_energy, double* d_grad, void* stream);
-int b200mol_etk_energy_grad(const b200mol_etk_system* sys, int plain, int32_t nConf, const int32_t* d_conf_mol,
+int b200mol_etk_energy_grad(const b200mol_etk_system* sys, int plain, int recentre, int32_t nConf,
+                            const int32_t* d_conf_mol,
                             const int32_t* d_conf_atom_start, const double* d_pos, double* d_energy, double* d_grad,
                             void* stream);
 
@@ -192,7 +197,8 @@ int b200mol_dg_minimize(const b200mol_dg_system* sys, int dim, double chiralWeig
                         int32_t nConf, const int32_t* d_conf_mol, const int32_t* d_conf_atom_start, int max_atoms,
                         double* d_pos, int max_iters, double grad_tol, const uint8_t* d_active, double* d_energy,
                         int8_t* d_status, int32_t* d_iters, void* stream);
-int b200mol_etk_minimize(const b200mol_etk_system* sys, int plain, int32_t nConf, const int32_t* d_conf_mol,
+int b200mol_etk_minimize(const b200mol_etk_system* sys, int plain, int recentre, int32_t nConf,
+                         const int32_t* d_conf_mol,
                          const int32_t* d_conf_atom_start, int max_atoms, double* d_pos, int max_iters,
                          double grad_tol, const uint8_t* d_active, double* d_energy, int8_t* d_status,
                          int32_t* d_iters, void* stream);
@@ -201,6 +207,70 @@ int b200mol_etk_minimize(const b200mol_etk_system* sys, int plain, int32_t nConf
 int b200mol_poly_minimize(int32_t nSys, const int32_t* d_starts, int max_dim, int power, const double* d_w,
                           const double* d_c, double* d_x, int max_iters, double grad_tol, int scale_grads,
                           double* d_energy, int8_t* d_status, int32_t* d_iters, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ETKDG conformer embedding (replaces nvMolKit::embedMolecules' device pipeline: ETKDGDriver / Scheduler / stages,
+ * src/etkdg.cpp:90-484, src/etkdg_impl.cpp:111-312, src/etkdg_stage_*.cu).
+ * Stereo / geometry check tables, CSR by molecule like the force-field tables:
+ *   tetrahedral K5 {centre, n1, n2, n3, n4 (= centre for 3-coordinate)} P1 {inFusedSmallRings}
+ *   chiral      K5 {centre, a1, a2, a3, a4}  P2 {volLower, volUpper}      (RDKit ChiralSet)
+ *   chiralDist  K2 P2 {lower, upper}          dbStereo K4 P1 {sign}        dbGeom K3 P0
+ *   numImpropers[nMols]: planarity tolerance count (improper energy must stay <= 0.7 * numImpropers)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct b200mol_etkdg_checks {
+  b200mol_term_table tetrahedral, chiral, chiralDist, dbStereo, dbGeom;
+  const int32_t*     numImpropers;
+} b200mol_etkdg_checks;
+
+typedef struct b200mol_embed_params {
+  uint64_t seed;              /* counter-based RNG key: coordinates depend on (seed, slot, attempt, element) only */
+  double   boxSize;           /* 5 * boxSizeMult (or -boxSizeMult when negative), src/etkdg_stage_coordgen.cu:102-107 */
+  double   optimizerForceTol; /* RDKit EmbedParameters::optimizerForceTol (1e-3) */
+  int32_t  enforceChirality, useExpTorsions, useBasicKnowledge;
+  int32_t  maxAttempts;       /* per conformer slot (reference: maxIterations) */
+  int32_t  dgIters, fourthIters, etkIters; /* 400, 200, 300 */
+  int32_t  maxRestarts;       /* cap on "repeat until converged" of the first minimisation */
+} b200mol_embed_params;
+
+/* One conformer per slot: slot s embeds molecule d_slot_mol[s] into d_coords[d_slot_atom_start[s]*3 ...] (xyz fp64).
+ * d_ok[s] = 1 on success (else the coordinates are untouched); d_attempts[s] attempts used; d_energy[s] DG energy of
+ * the accepted attempt; d_stage_failures[11] (optional) failure counts per stage. Asynchronous. */
+int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_etk_system* etk, const b200mol_etkdg_checks* checks,
+                        const b200mol_embed_params* params, int32_t nSlots, const int32_t* d_slot_mol,
+                        const int32_t* d_slot_atom_start, int max_atoms, double* d_coords, int8_t* d_ok,
+                        int32_t* d_attempts, double* d_energy, uint64_t* d_stage_failures, void* stream);
+/* The acceptance checks alone on given 4-D coordinates d_pos4[atom*4 ...]: bit s of d_fail_masks[slot] = stage s fails
+ * (1 energy/atom, 2 tetrahedral, 3 chirality, 5 planarity, 6 double-bond geometry, 7 chirality, 8 chiral distances,
+ * 9 centre-in-volume, 10 double-bond stereo). Replaces the kernels of src/etkdg_stage_stereochem_checks.cu:52-440. */
+int b200mol_etkdg_check(const b200mol_dg_system* dg, const b200mol_etk_system* etk, const b200mol_etkdg_checks* checks,
+                        const b200mol_embed_params* params, int32_t nSlots, const int32_t* d_slot_mol,
+                        const int32_t* d_slot_atom_start, int max_atoms, const double* d_pos4, uint32_t* d_fail_masks,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Distance-geometry preparation (per-molecule, matrix resident in shared memory).
+ * Matrices are concatenated: matrix m occupies d_x[starts[m] .. starts[m+1]) = n_m * n_m doubles, row-major.
+ * ---------------------------------------------------------------------------------------- */
+/* In-place triangle-inequality smoothing of RDKit bounds matrices ([i][j], i<j = upper bound; [j][i] = lower bound).
+ * d_ok[m] = 1 consistent / 0 inconsistent (lb > ub found; matrix left partially smoothed). tol as in RDKit
+ * triangleSmoothBounds (0 = strict). Replaces triangleSmoothBoundsBatch (src/triangle_smooth.cu:132-247) and the CPU
+ * call DistGeom::triangleSmoothBounds in src/embedder_utils.cpp:313,324. */
+int b200mol_triangle_smooth(double* d_bounds, const int64_t* d_matrix_starts, int32_t nMats, double tol, int8_t* d_ok,
+                            void* stream);
+/* Top-numEigs eigenpairs by power iteration with deflation (RDKit PowerEigenSolver: tol 1e-3, <= 1000 iterations).
+ * d_mats is destroyed. d_v0 (optional) start vectors, numEigs * n_m per matrix at d_v0_starts[m]; NULL = hashed
+ * counter sequence from `seed`. d_eigvals[m][numEigs]; d_eigvecs row e of matrix m at d_vec_starts[m] + e * n_m;
+ * d_n_converged[m] = number of eigenpairs found. Replaces BatchedEigenSolver::solve
+ * (src/symmetric_eigensolver.cu:62-247). */
+int b200mol_eig_topk(double* d_mats, const int64_t* d_matrix_starts, int32_t nMats, int numEigs, const double* d_v0,
+                     const int64_t* d_v0_starts, uint32_t seed, double* d_eigvals, double* d_eigvecs,
+                     const int64_t* d_vec_starts, int8_t* d_n_converged, void* stream);
+/* Distance matrix -> metric matrix -> top-`dim` eigenpairs -> coordinates d_coords[(atom_starts[m]+i)*dim + j] =
+ * sqrt(lambda_j) v_j[i]; d_ok[m] = 0 when an eigenvalue is not positive or did not converge (3-D AND 4-D; the
+ * reference's InitialCoordinateGenerator is 3-D only, src/forcefields/coord_gen.cu:64,160). d_dist is destroyed. */
+int b200mol_metric_embed(double* d_dist, const int64_t* d_matrix_starts, const int32_t* d_atom_starts, int32_t nMats,
+                         int dim, const double* d_v0, const int64_t* d_v0_starts, uint32_t seed, double* d_coords,
+                         int8_t* d_ok, void* stream);
 
 #ifdef __cplusplus
 }

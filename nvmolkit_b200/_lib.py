@@ -36,6 +36,22 @@ SIGNATURES = {
                                          _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp]),
     "b200mol_butina_from_edges": (C.c_int, [C.c_size_t, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "b200mol_butina_dense": (C.c_int, [_vp, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_mmff_energy_grad": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_dg_energy_grad": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_etk_energy_grad": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_mmff_minimize": (C.c_int, [_vp, C.c_int32, _vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp,
+                                        _vp]),
+    "b200mol_dg_minimize": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int32, _vp, _vp, C.c_int, _vp, C.c_int,
+                                      C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_etk_minimize": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int32, _vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _vp,
+                                       _vp, _vp, _vp]),
+    "b200mol_poly_minimize": (C.c_int, [C.c_int32, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int,
+                                        _vp, _vp, _vp, _vp]),
+    "b200mol_etkdg_embed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_etkdg_check": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "b200mol_triangle_smooth": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, _vp, _vp]),
+    "b200mol_eig_topk": (C.c_int, [_vp, _vp, C.c_int32, C.c_int, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_metric_embed": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int, _vp, _vp, C.c_uint32, _vp, _vp, _vp]),
     "b200mol_morgan": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                                  _vp]),
 }

@@ -11,14 +11,11 @@
 //   * the inverse Hessian is a per-CTA slab that stays hot in the 126 MB L2, updated with a fused
 //     "rank-2 update + next direction" pass (H read twice and written once per iteration, warp-per-row, coalesced);
 //   * no global atomics: gradients accumulate with shared-memory fp64 atomics.
-#include "ff.cuh"
+#include "bfgs_device.cuh"
 #include "profile.cuh"
 
 namespace b200 {
 namespace {
-
-constexpr int kT     = 256;  // threads per CTA
-constexpr int kWarps = kT / 32;
 
 struct Batch {
   int            nConf;
@@ -28,6 +25,7 @@ struct Batch {
   int            maxIters;
   double         gradTol;
   int            scaleGrads;
+  int            maxRestarts;
   const uint8_t* active;
   double*        energy;
   int8_t*        status;
@@ -38,85 +36,14 @@ struct Batch {
   int            maxN;
 };
 
-__device__ __forceinline__ double warpSum(double v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ double warpMaxD(double v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-// Block-wide reductions; every thread receives the same value. `red` is kWarps doubles of shared memory.
-__device__ __forceinline__ double blockSum(double v, double* red) {
-  v = warpSum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-#pragma unroll
-  for (int w = 0; w < kWarps; ++w) t += red[w];
-  return t;
-}
-__device__ __forceinline__ double blockMax(double v, double* red) {
-  v = warpMaxD(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = red[0];
-#pragma unroll
-  for (int w = 1; w < kWarps; ++w) t = fmax(t, red[w]);
-  return t;
-}
-
-// RDKit ForceField::minimize gradient cap (>= 2025.09: |g|), bfgs_minimize.cu:797-851.
-__device__ double scaleGrad(int n, double* grad, bool scaleGrads, double* red) {
-  const int tid       = threadIdx.x;
-  double    gradScale = scaleGrads ? 0.1 : 1.0, mx = 0.0;
-  for (int i = tid; i < n; i += kT) {
-    if (scaleGrads) grad[i] *= gradScale;
-    mx = fmax(mx, fabs(grad[i]));
-  }
-  mx = blockMax(mx, red);
-  if (scaleGrads && mx > 10.0) {
-    while (mx * gradScale > 10.0) gradScale *= 0.5;
-    for (int i = tid; i < n; i += kT) grad[i] *= gradScale;
-  }
-  __syncthreads();
-  return gradScale;
-}
-
-template <class FF>
-__device__ double energyOf(const typename FF::View& v, const double* x, double* red) {
-  return blockSum(FF::template eval<false>(v, x, nullptr, threadIdx.x, kT), red);
-}
-template <class FF>
-__device__ void gradOf(const typename FF::View& v, const double* x, double* grad, int n) {
-  for (int i = threadIdx.x; i < n; i += kT) grad[i] = 0.0;
-  __syncthreads();
-  FF::template eval<true>(v, x, grad, threadIdx.x, kT);
-  __syncthreads();
-}
-
 template <class FF>
 __global__ void __launch_bounds__(kT) bfgsKernel(const typename FF::System sys, const typename FF::Params par, const Batch b) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kWarps];
   __shared__ int                        nextConf;
-  constexpr double FUNCTOL = 1e-4, MOVETOL = 1e-7, TOLX = 4. * 3e-8, EPS = 3e-8;
-  constexpr int    DIM = FF::kDim;
-
-  double* pos    = sm;
-  double* grad   = pos + b.maxN;
-  double* dir    = grad + b.maxN;
-  double* newPos = dir + b.maxN;
-  double* dGrad  = newPos + b.maxN;
-  double* hdg    = dGrad + b.maxN;
-  double* H      = b.hessWs + static_cast<size_t>(blockIdx.x) * b.hessStride;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
+  constexpr int                         DIM = FF::kDim;
+  const BfgsWork w = carveWork(sm, b.maxN, b.hessWs + static_cast<size_t>(blockIdx.x) * b.hessStride, red);
+  const int      tid = threadIdx.x;
   for (;;) {
     __syncthreads();
     if (tid == 0) nextConf = atomicAdd(b.queue, 1);
@@ -124,160 +51,26 @@ __global__ void __launch_bounds__(kT) bfgsKernel(const typename FF::System sys, 
     const int conf = nextConf;
     if (conf >= b.nConf) break;
     if (b.active && !b.active[conf]) continue;
-    const int mol    = b.confMol ? b.confMol[conf] : conf;
-    const int a0     = b.confAtomStart[conf];
-    const int n      = DIM * (b.confAtomStart[conf + 1] - a0);
-    double*   gpos   = b.pos + static_cast<size_t>(a0) * DIM;
-    const auto view  = FF::view(sys, mol, par);
-
-    for (int i = tid; i < n; i += kT) pos[i] = gpos[i];
-    for (size_t i = tid; i < static_cast<size_t>(n) * n; i += kT) H[i] = 0.0;
-    __syncthreads();
-    for (int i = tid; i < n; i += kT) H[static_cast<size_t>(i) * n + i] = 1.0;
-
-    double fp = energyOf<FF>(view, pos, red);
-    gradOf<FF>(view, pos, grad, n);
-    double gradScale = scaleGrad(n, grad, b.scaleGrads != 0, red);
-    double s2        = 0.0;
-    for (int i = tid; i < n; i += kT) {
-      dir[i] = -grad[i];
-      s2 += pos[i] * pos[i];
-    }
-    const double maxStep = 100.0 * fmax(sqrt(blockSum(s2, red)), static_cast<double>(n));
-    int          status = 1, iter = 0;
-
-    for (iter = 0; iter < b.maxIters; ++iter) {
-      // ---------------- line search (bfgs_minimize.cu:80-162, 202-356) ----------------
-      double t = 0.0;
-      for (int i = tid; i < n; i += kT) t += dir[i] * dir[i];
-      const double dsum = sqrt(blockSum(t, red));
-      if (dsum > maxStep) {
-        const double sc = maxStep / dsum;
-        for (int i = tid; i < n; i += kT) dir[i] *= sc;
+    const int  mol  = b.confMol ? b.confMol[conf] : conf;
+    const int  a0   = b.confAtomStart[conf];
+    const int  n    = DIM * (b.confAtomStart[conf + 1] - a0);
+    double*    gpos = b.pos + static_cast<size_t>(a0) * DIM;
+    auto       view = FF::view(sys, mol, par);
+    for (int i = tid; i < n; i += kT) w.pos[i] = gpos[i];
+    if constexpr (FF::kHasRef) {
+      if (par.recentre) {  // seventh shared vector: the reference geometry of the window refresh
+        double* ref = sm + 6 * b.maxN;
+        for (int i = tid; i < n; i += kT) ref[i] = gpos[i];
+        view.refPos = ref;
       }
-      double sl = 0.0, tst = 0.0;
-      for (int i = tid; i < n; i += kT) {
-        sl += dir[i] * grad[i];
-        tst = fmax(tst, fabs(dir[i]) / fmax(fabs(pos[i]), 1.0));
-      }
-      const double slope     = blockSum(sl, red);
-      const double lambdaMin = MOVETOL / blockMax(tst, red);
-      double       lambda = 1.0, lambda2 = 0.0, val2 = 0.0, newVal = fp;
-      bool         accepted = false;
-      for (int it = 0; it < 1000; ++it) {
-        if (lambda < lambdaMin) break;
-        for (int i = tid; i < n; i += kT) newPos[i] = pos[i] + lambda * dir[i];
-        __syncthreads();
-        newVal = energyOf<FF>(view, newPos, red);
-        if (newVal - fp <= FUNCTOL * lambda * slope) {
-          accepted = true;
-          break;
-        }
-        double tmp;
-        if (it == 0) {
-          tmp = -slope / (2.0 * (newVal - fp - slope));
-        } else {
-          const double rhs1 = newVal - fp - lambda * slope, rhs2 = val2 - fp - lambda2 * slope;
-          const double a    = (rhs1 / (lambda * lambda) - rhs2 / (lambda2 * lambda2)) / (lambda - lambda2);
-          const double bq   = (-lambda2 * rhs1 / (lambda * lambda) + lambda * rhs2 / (lambda2 * lambda2)) / (lambda - lambda2);
-          if (a == 0.0) {
-            tmp = -slope / (2.0 * bq);
-          } else {
-            const double disc = bq * bq - 3 * a * slope;
-            if (disc < 0.0) tmp = 0.5 * lambda;
-            else if (bq <= 0.0) tmp = (-bq + sqrt(disc)) / (3.0 * a);
-            else tmp = -slope / (bq + sqrt(disc));
-          }
-          if (tmp > 0.5 * lambda) tmp = 0.5 * lambda;
-        }
-        lambda2 = lambda;
-        val2    = newVal;
-        lambda  = fmax(tmp, 0.1 * lambda);
-      }
-      __syncthreads();
-      if (!accepted)
-        for (int i = tid; i < n; i += kT) newPos[i] = pos[i];  // "nothing was done"
-      fp = newVal;
-      // ---------------- direction, TOLX (bfgs_minimize.cu:732-776) ----------------
-      tst = 0.0;
-      for (int i = tid; i < n; i += kT) {
-        const double xi = newPos[i] - pos[i];
-        dir[i]          = xi;
-        pos[i]          = newPos[i];
-        tst             = fmax(tst, fabs(xi) / fmax(fabs(pos[i]), 1.0));
-        dGrad[i]        = grad[i];
-      }
-      if (blockMax(tst, red) < TOLX) {
-        status = 0;
-        break;
-      }
-      gradOf<FF>(view, pos, grad, n);
-      gradScale = scaleGrad(n, grad, b.scaleGrads != 0, red);
-      tst       = 0.0;
-      for (int i = tid; i < n; i += kT) {
-        tst      = fmax(tst, fabs(grad[i]) * fmax(fabs(pos[i]), 1.0));
-        dGrad[i] = grad[i] - dGrad[i];
-      }
-      if (blockMax(tst, red) / fmax(fp * gradScale, 1.0) < b.gradTol) {
-        status = 0;
-        break;
-      }
-      // ---------------- inverse Hessian (bfgs_hessian.cu:37-239) ----------------
-      for (int row = warp; row < n; row += kWarps) {
-        const double* hr = H + static_cast<size_t>(row) * n;
-        double        a  = 0.0;
-        for (int c = lane; c < n; c += 32) a += hr[c] * dGrad[c];
-        a = warpSum(a);
-        if (lane == 0) hdg[row] = a;
-      }
-      __syncthreads();
-      double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
-      for (int i = tid; i < n; i += kT) {
-        f1 += dGrad[i] * dir[i];
-        f2 += dGrad[i] * hdg[i];
-        f3 += dGrad[i] * dGrad[i];
-        f4 += dir[i] * dir[i];
-      }
-      double       fac      = blockSum(f1, red);
-      const double fae      = blockSum(f2, red);
-      const double sumDGrad = blockSum(f3, red);
-      const double sumXi    = blockSum(f4, red);
-      const bool   update   = fac > sqrt(EPS * sumDGrad * sumXi);
-      double       fad      = 0.0;
-      if (update) {
-        fac = 1.0 / fac;
-        fad = 1.0 / fae;
-        for (int i = tid; i < n; i += kT) dGrad[i] = fac * dir[i] - fad * hdg[i];
-      }
-      __syncthreads();
-      // fused: rank-2 update of row + dot with the new gradient -> next direction (into newPos, free here)
-      for (int row = warp; row < n; row += kWarps) {
-        double*      hr  = H + static_cast<size_t>(row) * n;
-        const double pxi = fac * dir[row], hdgi = fad * hdg[row], dgi = fae * dGrad[row];
-        double       a   = 0.0;
-        if (update) {
-          for (int c = lane; c < n; c += 32) {
-            const double h = hr[c] + (pxi * dir[c] - hdgi * hdg[c] + dgi * dGrad[c]);
-            hr[c]          = h;
-            a += h * grad[c];
-          }
-        } else {
-          for (int c = lane; c < n; c += 32) a += hr[c] * grad[c];
-        }
-        a = warpSum(a);
-        if (lane == 0) newPos[row] = -a;
-      }
-      __syncthreads();
-      for (int i = tid; i < n; i += kT) dir[i] = newPos[i];
-      __syncthreads();
     }
     __syncthreads();
-    const double eFinal = energyOf<FF>(view, pos, red);
-    for (int i = tid; i < n; i += kT) gpos[i] = pos[i];
+    const BfgsOutcome o = bfgsMinimize<FF>(view, w, n, b.maxIters, b.gradTol, b.scaleGrads != 0, b.maxRestarts);
+    for (int i = tid; i < n; i += kT) gpos[i] = w.pos[i];
     if (tid == 0) {
-      b.energy[conf] = eFinal;
-      if (b.status) b.status[conf] = static_cast<int8_t>(status);
-      if (b.iters) b.iters[conf] = iter;
+      b.energy[conf] = o.energy;
+      if (b.status) b.status[conf] = static_cast<int8_t>(o.status);
+      if (b.iters) b.iters[conf] = o.iters;
     }
   }
 }
@@ -299,8 +92,11 @@ __global__ void __launch_bounds__(kT) energyGradKernel(const typename FF::System
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += kT) pos[i] = posIn[static_cast<size_t>(a0) * DIM + i];
     __syncthreads();
-    const auto   view = FF::view(sys, mol, par);
-    const double e    = energyOf<FF>(view, pos, red);
+    auto view = FF::view(sys, mol, par);
+    if constexpr (FF::kHasRef) {
+      if (par.recentre) view.refPos = pos;
+    }
+    const double e = energyOf<FF>(view, pos, red);
     if (threadIdx.x == 0) energy[conf] = e;
     if (gradOut) {
       gradOf<FF>(view, pos, grad, n);
@@ -317,7 +113,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   B200_REQUIRE(nConf > 0 && maxAtoms > 0 && maxIters >= 0, "bad batch arguments");
   B200_REQUIRE(confAtomStart && pos && energy, "null pointer");
   const int    maxN = FF::kDim * maxAtoms;
-  const size_t smem = static_cast<size_t>(6) * maxN * sizeof(double);
+  const size_t smem = static_cast<size_t>(FF::kHasRef ? 7 : 6) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large for the shared-memory BFGS (%d atoms)", maxAtoms);
   static size_t configured = 0;  // per instantiation
   if (smem > 48 * 1024 && smem > configured) {
@@ -334,7 +130,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   Scratch<double>    hess(stride * blocks, s);
   Scratch<int>       queue(1, s);
   B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));
-  Batch b{nConf, confMol, confAtomStart, pos, maxIters, gradTol, scaleGrads, active, energy, status, iters,
+  Batch b{nConf, confMol, confAtomStart, pos, maxIters, gradTol, scaleGrads, 0, active, energy, status, iters,
           hess.get(), stride, queue.get(), maxN};
   PhaseTimer t("bfgs", s);
   bfgsKernel<FF><<<blocks, kT, smem, s>>>(sys, par, b);
@@ -410,14 +206,14 @@ extern "C" int b200mol_dg_energy_grad(const b200mol_dg_system* sys, int dim, dou
                                d_energy, d_grad, asStream(stream));
   });
 }
-extern "C" int b200mol_etk_energy_grad(const b200mol_etk_system* sys, int plain, int32_t nConf, const int32_t* d_conf_mol,
+extern "C" int b200mol_etk_energy_grad(const b200mol_etk_system* sys, int plain, int recentre, int32_t nConf, const int32_t* d_conf_mol,
                                        const int32_t* d_conf_atom_start, const double* d_pos, double* d_energy,
                                        double* d_grad, void* stream) {
   return guarded([&] {
     B200_REQUIRE(sys, "null system");
     if (nConf <= 0) return;
     const int maxAtoms = maxSpan(d_conf_atom_start, nConf, asStream(stream));
-    runEnergyGrad<ff::Etk>(*sys, {plain}, nConf, d_conf_mol, d_conf_atom_start, maxAtoms, d_pos, d_energy, d_grad, asStream(stream));
+    runEnergyGrad<ff::Etk>(*sys, {plain, recentre}, nConf, d_conf_mol, d_conf_atom_start, maxAtoms, d_pos, d_energy, d_grad, asStream(stream));
   });
 }
 
@@ -446,13 +242,13 @@ extern "C" int b200mol_dg_minimize(const b200mol_dg_system* sys, int dim, double
                              max_iters, grad_tol, 1, d_active, d_energy, d_status, d_iters, asStream(stream));
   });
 }
-extern "C" int b200mol_etk_minimize(const b200mol_etk_system* sys, int plain, int32_t nConf, const int32_t* d_conf_mol,
+extern "C" int b200mol_etk_minimize(const b200mol_etk_system* sys, int plain, int recentre, int32_t nConf, const int32_t* d_conf_mol,
                                     const int32_t* d_conf_atom_start, int max_atoms, double* d_pos, int max_iters,
                                     double grad_tol, const uint8_t* d_active, double* d_energy, int8_t* d_status,
                                     int32_t* d_iters, void* stream) {
   return guarded([&] {
     B200_REQUIRE(sys, "null system");
-    runMinimize<ff::Etk>(*sys, {plain}, nConf, d_conf_mol, d_conf_atom_start, max_atoms, d_pos, max_iters, grad_tol, 1,
+    runMinimize<ff::Etk>(*sys, {plain, recentre}, nConf, d_conf_mol, d_conf_atom_start, max_atoms, d_pos, max_iters, grad_tol, 1,
                          d_active, d_energy, d_status, d_iters, asStream(stream));
   });
 }

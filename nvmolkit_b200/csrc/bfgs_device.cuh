@@ -1,0 +1,248 @@
+// Device-side BFGS over a flattened force field for ONE conformer held in shared memory (see bfgs.cu for the design).
+#pragma once
+#include "ff.cuh"
+
+namespace b200 {
+
+constexpr int kT     = 256;  // threads per CTA
+constexpr int kWarps = kT / 32;
+
+__device__ __forceinline__ double warpSum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warpMaxD(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide reductions; every thread receives the same value. `red` is kWarps doubles of shared memory.
+__device__ __forceinline__ double blockSum(double v, double* red) {
+  v = warpSum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) t += red[w];
+  return t;
+}
+__device__ __forceinline__ double blockMax(double v, double* red) {
+  v = warpMaxD(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = red[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) t = fmax(t, red[w]);
+  return t;
+}
+
+// RDKit ForceField::minimize gradient cap (>= 2025.09: |g|), bfgs_minimize.cu:797-851.
+__device__ inline double scaleGrad(int n, double* grad, bool scaleGrads, double* red) {
+  const int tid       = threadIdx.x;
+  double    gradScale = scaleGrads ? 0.1 : 1.0, mx = 0.0;
+  for (int i = tid; i < n; i += kT) {
+    if (scaleGrads) grad[i] *= gradScale;
+    mx = fmax(mx, fabs(grad[i]));
+  }
+  mx = blockMax(mx, red);
+  if (scaleGrads && mx > 10.0) {
+    while (mx * gradScale > 10.0) gradScale *= 0.5;
+    for (int i = tid; i < n; i += kT) grad[i] *= gradScale;
+  }
+  __syncthreads();
+  return gradScale;
+}
+
+template <class FF>
+__device__ double energyOf(const typename FF::View& v, const double* x, double* red) {
+  return blockSum(FF::template eval<false>(v, x, nullptr, threadIdx.x, kT), red);
+}
+template <class FF>
+__device__ void gradOf(const typename FF::View& v, const double* x, double* grad, int n) {
+  for (int i = threadIdx.x; i < n; i += kT) grad[i] = 0.0;
+  __syncthreads();
+  FF::template eval<true>(v, x, grad, threadIdx.x, kT);
+  __syncthreads();
+}
+
+// Shared-memory working set of one CTA: six vectors of maxN doubles + the per-CTA inverse-Hessian slab (global/L2).
+struct BfgsWork {
+  double *pos, *grad, *dir, *newPos, *dGrad, *hdg;  // shared memory, maxN each
+  double* H;                                        // [n*n] global slab of this CTA
+  double* red;                                      // kWarps doubles of shared memory
+};
+__device__ __forceinline__ BfgsWork carveWork(double* sm, int maxN, double* H, double* red) {
+  return {sm, sm + maxN, sm + 2 * maxN, sm + 3 * maxN, sm + 4 * maxN, sm + 5 * maxN, H, red};
+}
+
+struct BfgsOutcome {
+  int    status;  // 0 converged, 1 not
+  int    iters;   // BFGS iterations of the last (re)start
+  double energy;  // energy at w.pos (re-evaluated)
+};
+
+// Minimises w.pos[0..n) in place. maxRestarts > 0 re-runs (H = I, fresh gradient) while the run ends unconverged:
+// RDKit's `while (needMore) needMore = field->minimize(...)` (src/etkdg_stage_distgeom_minimize.cu repeatUntilConverged).
+template <class FF>
+__device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWork& w, int n, int maxIters, double gradTol,
+                                    bool scaleGrads, int maxRestarts) {
+  constexpr double FUNCTOL = 1e-4, MOVETOL = 1e-7, TOLX = 4. * 3e-8, EPS = 3e-8;
+  double *pos = w.pos, *grad = w.grad, *dir = w.dir, *newPos = w.newPos, *dGrad = w.dGrad, *hdg = w.hdg, *H = w.H,
+         *red = w.red;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int       status = 1, iter = 0;
+  for (int restart = 0;; ++restart) {
+    __syncthreads();
+    for (size_t i = tid; i < static_cast<size_t>(n) * n; i += kT) H[i] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kT) H[static_cast<size_t>(i) * n + i] = 1.0;
+
+    double fp = energyOf<FF>(view, pos, red);
+    gradOf<FF>(view, pos, grad, n);
+    double gradScale = scaleGrad(n, grad, scaleGrads, red);
+    double s2        = 0.0;
+    for (int i = tid; i < n; i += kT) {
+      dir[i] = -grad[i];
+      s2 += pos[i] * pos[i];
+    }
+    const double maxStep = 100.0 * fmax(sqrt(blockSum(s2, red)), static_cast<double>(n));
+    status               = 1;
+    for (iter = 0; iter < maxIters; ++iter) {
+      // ---------------- line search (bfgs_minimize.cu:80-162, 202-356) ----------------
+      double t = 0.0;
+      for (int i = tid; i < n; i += kT) t += dir[i] * dir[i];
+      const double dsum = sqrt(blockSum(t, red));
+      if (dsum > maxStep) {
+        const double sc = maxStep / dsum;
+        for (int i = tid; i < n; i += kT) dir[i] *= sc;
+      }
+      double sl = 0.0, tst = 0.0;
+      for (int i = tid; i < n; i += kT) {
+        sl += dir[i] * grad[i];
+        tst = fmax(tst, fabs(dir[i]) / fmax(fabs(pos[i]), 1.0));
+      }
+      const double slope     = blockSum(sl, red);
+      const double lambdaMin = MOVETOL / blockMax(tst, red);
+      double       lambda = 1.0, lambda2 = 0.0, val2 = 0.0, newVal = fp;
+      bool         accepted = false;
+      for (int it = 0; it < 1000; ++it) {
+        if (lambda < lambdaMin) break;
+        for (int i = tid; i < n; i += kT) newPos[i] = pos[i] + lambda * dir[i];
+        __syncthreads();
+        newVal = energyOf<FF>(view, newPos, red);
+        if (newVal - fp <= FUNCTOL * lambda * slope) {
+          accepted = true;
+          break;
+        }
+        double tmp;
+        if (it == 0) {
+          tmp = -slope / (2.0 * (newVal - fp - slope));
+        } else {
+          const double rhs1 = newVal - fp - lambda * slope, rhs2 = val2 - fp - lambda2 * slope;
+          const double a    = (rhs1 / (lambda * lambda) - rhs2 / (lambda2 * lambda2)) / (lambda - lambda2);
+          const double bq   = (-lambda2 * rhs1 / (lambda * lambda) + lambda * rhs2 / (lambda2 * lambda2)) / (lambda - lambda2);
+          if (a == 0.0) {
+            tmp = -slope / (2.0 * bq);
+          } else {
+            const double disc = bq * bq - 3 * a * slope;
+            if (disc < 0.0) tmp = 0.5 * lambda;
+            else if (bq <= 0.0) tmp = (-bq + sqrt(disc)) / (3.0 * a);
+            else tmp = -slope / (bq + sqrt(disc));
+          }
+          if (tmp > 0.5 * lambda) tmp = 0.5 * lambda;
+        }
+        lambda2 = lambda;
+        val2    = newVal;
+        lambda  = fmax(tmp, 0.1 * lambda);
+      }
+      __syncthreads();
+      if (!accepted)
+        for (int i = tid; i < n; i += kT) newPos[i] = pos[i];  // "nothing was done"
+      fp = newVal;
+      // ---------------- direction, TOLX (bfgs_minimize.cu:732-776) ----------------
+      tst = 0.0;
+      for (int i = tid; i < n; i += kT) {
+        const double xi = newPos[i] - pos[i];
+        dir[i]          = xi;
+        pos[i]          = newPos[i];
+        tst             = fmax(tst, fabs(xi) / fmax(fabs(pos[i]), 1.0));
+        dGrad[i]        = grad[i];
+      }
+      if (blockMax(tst, red) < TOLX) {
+        status = 0;
+        break;
+      }
+      gradOf<FF>(view, pos, grad, n);
+      gradScale = scaleGrad(n, grad, scaleGrads, red);
+      tst       = 0.0;
+      for (int i = tid; i < n; i += kT) {
+        tst      = fmax(tst, fabs(grad[i]) * fmax(fabs(pos[i]), 1.0));
+        dGrad[i] = grad[i] - dGrad[i];
+      }
+      if (blockMax(tst, red) / fmax(fp * gradScale, 1.0) < gradTol) {
+        status = 0;
+        break;
+      }
+      // ---------------- inverse Hessian (bfgs_hessian.cu:37-239) ----------------
+      for (int row = warp; row < n; row += kWarps) {
+        const double* hr = H + static_cast<size_t>(row) * n;
+        double        a  = 0.0;
+        for (int c = lane; c < n; c += 32) a += hr[c] * dGrad[c];
+        a = warpSum(a);
+        if (lane == 0) hdg[row] = a;
+      }
+      __syncthreads();
+      double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+      for (int i = tid; i < n; i += kT) {
+        f1 += dGrad[i] * dir[i];
+        f2 += dGrad[i] * hdg[i];
+        f3 += dGrad[i] * dGrad[i];
+        f4 += dir[i] * dir[i];
+      }
+      double       fac      = blockSum(f1, red);
+      const double fae      = blockSum(f2, red);
+      const double sumDGrad = blockSum(f3, red);
+      const double sumXi    = blockSum(f4, red);
+      const bool   update   = fac > sqrt(EPS * sumDGrad * sumXi);
+      double       fad      = 0.0;
+      if (update) {
+        fac = 1.0 / fac;
+        fad = 1.0 / fae;
+        for (int i = tid; i < n; i += kT) dGrad[i] = fac * dir[i] - fad * hdg[i];
+      }
+      __syncthreads();
+      // fused: rank-2 update of row + dot with the new gradient -> next direction (into newPos, free here)
+      for (int row = warp; row < n; row += kWarps) {
+        double*      hr  = H + static_cast<size_t>(row) * n;
+        const double pxi = fac * dir[row], hdgi = fad * hdg[row], dgi = fae * dGrad[row];
+        double       a   = 0.0;
+        if (update) {
+          for (int c = lane; c < n; c += 32) {
+            const double h = hr[c] + (pxi * dir[c] - hdgi * hdg[c] + dgi * dGrad[c]);
+            hr[c]          = h;
+            a += h * grad[c];
+          }
+        } else {
+          for (int c = lane; c < n; c += 32) a += hr[c] * grad[c];
+        }
+        a = warpSum(a);
+        if (lane == 0) newPos[row] = -a;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += kT) dir[i] = newPos[i];
+      __syncthreads();
+    }
+    if (status == 0 || restart >= maxRestarts) break;
+  }
+  __syncthreads();
+  BfgsOutcome out;
+  out.status = status;
+  out.iters  = iter;
+  out.energy = energyOf<FF>(view, pos, red);
+  return out;
+}
+
+}  // namespace b200

@@ -1,0 +1,346 @@
+// ETKDG conformer embedding: one CTA carries one conformer slot through the WHOLE attempt pipeline inside one persistent
+// kernel — random 4-D coordinates -> DG minimisation (repeat until converged) -> energy / tetrahedral / chirality
+// checks -> fourth-dimension collapse -> ETK refinement -> planarity, double-bond and final chirality checks — and
+// retries failed attempts itself with a fresh random stream. No host round trip between stages.
+//
+// Stage list and constants = the reference's production pipeline (src/etkdg.cpp:325-394):
+//   0 coordinates: (u - 0.5) * boxSize in all four dimensions           (src/etkdg_stage_coordgen.cu:100-122; on the CPU there)
+//   1 DG minimise  chiral 1.0 / 4th-dim 0.1, 400 iterations, repeated until converged; fail if E/atom >= 0.05
+//                                                                        (src/etkdg_stage_distgeom_minimize.cu:177-249, .h:34)
+//   2 tetrahedral check (volume >= 0.5, x0.25 in fused small rings; centre inside, tol 0.3)   (stereochem_checks.cu:52-168)
+//   3 first chirality check                                             (stereochem_checks.cu:219-268)
+//   4 DG minimise  chiral 0.2 / 4th-dim 1.0, 200 iterations             (src/etkdg.cpp:365-370)
+//   5 ETK minimise 300 iterations on xyz, 1-2 / 1-3 windows re-centred; planarity: improper energy <= 0.7 * nImpropers
+//                                                                        (src/etkdg_stage_etk_minimization.cu:66-86,204-266)
+//   6 double-bond linearity  7 final chirality  8 chiral distance matrix  9 centre-in-volume (tol 0.1)  10 double-bond stereo
+//                                                                        (stereochem_checks.cu:270-440)
+// The reference launches each stage as separate kernels over a 500-conformer batch, generates coordinates on the CPU,
+// and lets a host Scheduler re-dispatch failures (src/etkdg_impl.cpp:111-159,286-312).
+#include "bfgs_device.cuh"
+#include "profile.cuh"
+
+namespace b200 {
+namespace {
+
+using ff::V3;
+
+struct EmbedArgs {
+  b200mol_dg_system       dg;
+  b200mol_etk_system      etk;
+  b200mol_etkdg_checks    chk;
+  b200mol_embed_params    par;
+  int                     nSlots;
+  const int32_t*          slotMol;        // [nSlots]
+  const int32_t*          slotAtomStart;  // [nSlots+1] offsets into coords (atoms)
+  double*                 coords;         // [totalAtoms][3]
+  int8_t*                 ok;             // [nSlots]
+  int32_t*                attempts;       // [nSlots]
+  double*                 energy;         // [nSlots] DG energy (first-stage weights) of the accepted attempt
+  unsigned long long*     stageFailures;  // [kNumStages] (may be NULL)
+  double*                 hessWs;
+  size_t                  hessStride;
+  int*                    queue;
+  int                     maxN;
+};
+
+constexpr int kNumStages = 11;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser: counter-based, stateless
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+// u in [0,1) from (seed, slot, attempt, element)
+__device__ __forceinline__ double uniform01(uint64_t seed, uint32_t slot, uint32_t attempt, uint32_t element) {
+  const uint64_t h = mix64(mix64(seed ^ (static_cast<uint64_t>(slot) << 32 | attempt)) + element);
+  return static_cast<double>(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ V3 p3(const double* pos, int a) { return {pos[4 * a], pos[4 * a + 1], pos[4 * a + 2]}; }
+
+__device__ __forceinline__ bool sameSide(double tol, const V3& v1, const V3& v2, const V3& v3, const V3& v4, const V3& p0) {
+  const V3     c  = ff::cross(v2 - v1, v3 - v1);
+  const double d1 = ff::dot(c, v4 - v1), d2 = ff::dot(c, p0 - v1);
+  if (fabs(d1) < tol || fabs(d2) < tol) return false;
+  return !((d1 < 0.) ^ (d2 < 0.));
+}
+
+// Each check returns true when the conformer FAILS it. All threads take part; the verdict is block-uniform.
+__device__ bool anyFail(bool mine) { return __syncthreads_or(mine ? 1 : 0) != 0; }
+
+template <bool VOLUME>
+__device__ bool tetrahedralFails(const b200mol_term_table& T, int mol, const double* pos, double tol) {
+  bool bad = false;
+  for (int t = T.starts[mol] + threadIdx.x; t < T.starts[mol + 1]; t += kT) {
+    const int16_t* ix = T.idx + 5 * t;
+    const V3       p0 = p3(pos, ix[0]), p1 = p3(pos, ix[1]), p2 = p3(pos, ix[2]), q3 = p3(pos, ix[3]), p4 = p3(pos, ix[4]);
+    if (VOLUME) {
+      auto unit = [](V3 v) {
+        const double l = sqrt(ff::dot(v, v));
+        return l > 0.0 ? v * (1.0 / l) : v;
+      };
+      const V3     d1 = unit(p0 - p1), d2 = unit(p0 - p2), d3 = unit(p0 - q3), d4 = unit(p0 - p4);
+      const double lim = (T.par[t] != 0.0 ? 0.25 : 1.0) * 0.50;
+      V3           c   = ff::cross(d1, d2);
+      if (fabs(ff::dot(c, d3)) < lim || fabs(ff::dot(c, d4)) < lim) bad = true;
+      c = ff::cross(d1, d3);
+      if (fabs(ff::dot(c, d4)) < lim) bad = true;
+      c = ff::cross(d2, d3);
+      if (fabs(ff::dot(c, d4)) < lim) bad = true;
+      if (bad) continue;
+    }
+    if (ix[0] == ix[4]) continue;  // three-coordinate centre
+    if (!sameSide(tol, p1, p2, q3, p4, p0) || !sameSide(tol, p2, q3, p4, p1, p0) || !sameSide(tol, q3, p4, p1, p2, p0) ||
+        !sameSide(tol, p4, p1, p2, q3, p0))
+      bad = true;
+  }
+  return anyFail(bad);
+}
+
+__device__ bool chiralityFails(const b200mol_term_table& T, int mol, const double* pos) {
+  bool bad = false;
+  for (int t = T.starts[mol] + threadIdx.x; t < T.starts[mol + 1]; t += kT) {
+    const int16_t* ix = T.idx + 5 * t;
+    const V3       p1 = p3(pos, ix[1]), p2 = p3(pos, ix[2]), q3 = p3(pos, ix[3]), p4 = p3(pos, ix[4]);
+    const double   vol = ff::dot(p1 - p4, ff::cross(p2 - p4, q3 - p4));
+    const double   lb = T.par[2 * t], ub = T.par[2 * t + 1];
+    if ((lb > 0 && vol < lb && (vol / lb < .8 || (signbit(vol) != signbit(lb)))) ||
+        (ub < 0 && vol > ub && (vol / ub < .8 || (signbit(vol) != signbit(ub)))))
+      bad = true;
+  }
+  return anyFail(bad);
+}
+
+__device__ bool chiralDistFails(const b200mol_term_table& T, int mol, const double* pos) {
+  bool bad = false;
+  for (int t = T.starts[mol] + threadIdx.x; t < T.starts[mol + 1]; t += kT) {
+    const V3     d    = p3(pos, T.idx[2 * t]) - p3(pos, T.idx[2 * t + 1]);
+    const double dist = sqrt(ff::dot(d, d)), lb = T.par[2 * t], ub = T.par[2 * t + 1];
+    if ((dist < lb && fabs(dist - lb) > 0.1 * ub) || (dist > ub && fabs(dist - ub) > 0.1 * ub)) bad = true;
+  }
+  return anyFail(bad);
+}
+
+__device__ bool doubleBondStereoFails(const b200mol_term_table& T, int mol, const double* pos) {
+  bool bad = false;
+  for (int t = T.starts[mol] + threadIdx.x; t < T.starts[mol + 1]; t += kT) {
+    const int16_t* ix = T.idx + 4 * t;
+    const V3       p0 = p3(pos, ix[0]), p1 = p3(pos, ix[1]), p2 = p3(pos, ix[2]), q3 = p3(pos, ix[3]);
+    const V3       d1 = p2 - p1, d2 = p0 - p1, d3 = q3 - p2;
+    const V3       c1 = ff::cross(d2, d1), c2 = ff::cross(d3, d1);
+    double         dt = ff::dot(c1, c2) / sqrt(ff::dot(c1, c1) * ff::dot(c2, c2));
+    double         angle = acos(dt);
+    if (dt <= -1.0) angle = 3.14159265358979323846;
+    else if (dt >= 1.0) angle = 0.0;
+    if ((angle - 3.14159265358979323846 / 2.0) * T.par[t] < 0.0) bad = true;
+  }
+  return anyFail(bad);
+}
+
+__device__ bool doubleBondGeometryFails(const b200mol_term_table& T, int mol, const double* pos) {
+  bool bad = false;
+  for (int t = T.starts[mol] + threadIdx.x; t < T.starts[mol + 1]; t += kT) {
+    const int16_t* ix = T.idx + 3 * t;
+    V3             a = p3(pos, ix[1]) - p3(pos, ix[0]), b = p3(pos, ix[1]) - p3(pos, ix[2]);
+    a                = a * (1.0 / sqrt(ff::dot(a, a)));
+    b                = b * (1.0 / sqrt(ff::dot(b, b)));
+    if (ff::dot(a, b) + 1.0 < 1e-3) bad = true;
+  }
+  return anyFail(bad);
+}
+
+// Planarity: energy of the improper (inversion) terms alone vs 0.7 * numImpropers.
+__device__ bool planarityFails(const b200mol_etk_system& etk, const int32_t* numImpropers, int mol, const double* pos,
+                               double* red) {
+  ff::Etk::View v = ff::Etk::view(etk, mol, {0, 0});
+  v.torsion.end = v.torsion.beg;
+  v.d12.end     = v.d12.beg;
+  v.d13.end     = v.d13.beg;
+  v.a13.end     = v.a13.beg;
+  v.lr.end      = v.lr.beg;
+  const double e = blockSum(ff::Etk::eval<false>(v, pos, nullptr, threadIdx.x, kT), red);
+  return e > 0.7 * (numImpropers ? numImpropers[mol] : 0);
+}
+
+// Stage outcomes on given 4-D coordinates as a bit mask (bit s = stage s failed); used by the attempt kernel and by the
+// check-only entry point that tests compare against the CPU oracle.
+__device__ unsigned finalChecks(const EmbedArgs& a, int mol, const double* pos, double* red, bool stopAtFirst) {
+  unsigned m = 0;
+  if (doubleBondGeometryFails(a.chk.dbGeom, mol, pos)) m |= 1u << 6;
+  if (m && stopAtFirst) return m;
+  if (a.par.enforceChirality) {
+    if (chiralityFails(a.chk.chiral, mol, pos)) m |= 1u << 7;
+    if (m && stopAtFirst) return m;
+    if (chiralDistFails(a.chk.chiralDist, mol, pos)) m |= 1u << 8;
+    if (m && stopAtFirst) return m;
+    if (tetrahedralFails<false>(a.chk.chiral, mol, pos, 0.1)) m |= 1u << 9;
+    if (m && stopAtFirst) return m;
+    if (doubleBondStereoFails(a.chk.dbStereo, mol, pos)) m |= 1u << 10;
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(kT) etkdgKernel(const EmbedArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double                     red[kWarps];
+  __shared__ int                        nextSlot;
+  const BfgsWork w   = carveWork(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red);
+  double*        ref = sm + 6 * a.maxN;  // ETK reference geometry
+  const int      tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) nextSlot = atomicAdd(a.queue, 1);
+    __syncthreads();
+    const int slot = nextSlot;
+    if (slot >= a.nSlots) break;
+    const int mol = a.slotMol[slot];
+    const int nA  = a.dg.atomCounts[mol];
+    const int n   = 4 * nA;
+    bool      success = false;
+    int       attempt = 0;
+    double    eAccepted = 0.0;
+    for (attempt = 0; attempt < a.par.maxAttempts && !success; ++attempt) {
+      int failedStage = -1;
+      // 0: random coordinates in a 4-D box
+      for (int i = tid; i < n; i += kT) w.pos[i] = (uniform01(a.par.seed, slot, attempt, i) - 0.5) * a.par.boxSize;
+      __syncthreads();
+      // 1: first minimisation
+      {
+        const auto        v = ff::Dg<4>::view(a.dg, mol, {1.0, 0.1});
+        const BfgsOutcome o = bfgsMinimize<ff::Dg<4>>(v, w, n, a.par.dgIters, a.par.optimizerForceTol, true, a.par.maxRestarts);
+        eAccepted           = o.energy;
+        if (o.energy / nA >= 0.05) failedStage = 1;
+      }
+      // 2, 3: tetrahedral + first chirality checks
+      if (failedStage < 0 && tetrahedralFails<true>(a.chk.tetrahedral, mol, w.pos, 0.3)) failedStage = 2;
+      if (failedStage < 0 && a.par.enforceChirality && chiralityFails(a.chk.chiral, mol, w.pos)) failedStage = 3;
+      // 4: fourth-dimension collapse
+      if (failedStage < 0) {
+        const auto v = ff::Dg<4>::view(a.dg, mol, {0.2, 1.0});
+        bfgsMinimize<ff::Dg<4>>(v, w, n, a.par.fourthIters, a.par.optimizerForceTol, true, 0);
+      }
+      // 5: ETK refinement + planarity
+      if (failedStage < 0 && (a.par.useExpTorsions || a.par.useBasicKnowledge)) {
+        for (int i = tid; i < n; i += kT) ref[i] = w.pos[i];
+        __syncthreads();
+        auto v   = ff::Etk::view(a.etk, mol, {a.par.useBasicKnowledge ? 0 : 1, 1});
+        v.refPos = ref;
+        bfgsMinimize<ff::Etk>(v, w, n, a.par.etkIters, a.par.optimizerForceTol, true, 0);
+        if (a.par.useBasicKnowledge && planarityFails(a.etk, a.chk.numImpropers, mol, w.pos, red)) failedStage = 5;
+      }
+      // 6-10: final checks
+      if (failedStage < 0) {
+        const unsigned m = finalChecks(a, mol, w.pos, red, true);
+        if (m) failedStage = __ffs(m) - 1;
+      }
+      if (failedStage < 0) success = true;
+      else if (tid == 0 && a.stageFailures) atomicAdd(a.stageFailures + failedStage, 1ull);
+    }
+    __syncthreads();
+    const int a0 = a.slotAtomStart[slot];
+    if (success) {
+      for (int i = tid; i < nA * 3; i += kT) a.coords[static_cast<size_t>(a0) * 3 + i] = w.pos[(i / 3) * 4 + (i % 3)];
+    }
+    if (tid == 0) {
+      a.ok[slot] = success ? 1 : 0;
+      if (a.attempts) a.attempts[slot] = attempt;
+      if (a.energy) a.energy[slot] = eAccepted;
+    }
+  }
+}
+
+// Check-only: evaluates stages 1 (energy per atom), 2, 3, 5 (planarity), 6-10 on given 4-D coordinates.
+__global__ void __launch_bounds__(kT) etkdgCheckKernel(const EmbedArgs a, const double* pos4, uint32_t* masks) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double                     red[kWarps];
+  for (int slot = blockIdx.x; slot < a.nSlots; slot += gridDim.x) {
+    const int mol = a.slotMol[slot];
+    const int nA  = a.dg.atomCounts[mol];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * nA; i += kT) sm[i] = pos4[static_cast<size_t>(a.slotAtomStart[slot]) * 4 + i];
+    __syncthreads();
+    unsigned     m = 0;
+    const auto   v = ff::Dg<4>::view(a.dg, mol, {1.0, 0.1});
+    const double e = energyOf<ff::Dg<4>>(v, sm, red);
+    if (e / nA >= 0.05) m |= 1u << 1;
+    if (tetrahedralFails<true>(a.chk.tetrahedral, mol, sm, 0.3)) m |= 1u << 2;
+    if (a.par.enforceChirality && chiralityFails(a.chk.chiral, mol, sm)) m |= 1u << 3;
+    if (a.par.useBasicKnowledge && planarityFails(a.etk, a.chk.numImpropers, mol, sm, red)) m |= 1u << 5;
+    m |= finalChecks(a, mol, sm, red, false);
+    if (threadIdx.x == 0) masks[slot] = m;
+  }
+}
+
+void validate(const b200mol_embed_params& p) {
+  B200_REQUIRE(p.maxAttempts >= 1, "maxAttempts must be >= 1");
+  B200_REQUIRE(p.boxSize > 0.0, "boxSize must be positive");
+  B200_REQUIRE(p.dgIters >= 0 && p.fourthIters >= 0 && p.etkIters >= 0 && p.maxRestarts >= 0, "negative iteration count");
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_etk_system* etk,
+                                   const b200mol_etkdg_checks* checks, const b200mol_embed_params* params, int32_t nSlots,
+                                   const int32_t* d_slot_mol, const int32_t* d_slot_atom_start, int max_atoms,
+                                   double* d_coords, int8_t* d_ok, int32_t* d_attempts, double* d_energy,
+                                   uint64_t* d_stage_failures, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(dg && etk && checks && params, "null system");
+    validate(*params);
+    if (nSlots <= 0) return;
+    B200_REQUIRE(d_slot_mol && d_slot_atom_start && d_coords && d_ok, "null pointer");
+    cudaStream_t s    = asStream(stream);
+    const int    maxN = 4 * max_atoms;
+    const size_t smem = static_cast<size_t>(7) * maxN * sizeof(double);
+    B200_REQUIRE(max_atoms > 0 && smem <= 200 * 1024, "molecule too large for the shared-memory embedder (%d atoms)", max_atoms);
+    static bool configured = false;
+    if (!configured) {
+      B200_CUDA(cudaFuncSetAttribute(etkdgKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    int perSm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, etkdgKernel, kT, smem));
+    B200_REQUIRE(perSm >= 1, "embedding kernel does not fit");
+    perSm      = perSm > 2 ? 2 : perSm;
+    int blocks = smCount() * perSm;
+    if (blocks > nSlots) blocks = nSlots;
+    const size_t    stride = static_cast<size_t>(maxN) * maxN;
+    Scratch<double> hess(stride * blocks, s);
+    Scratch<int>    queue(1, s);
+    B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));
+    if (d_stage_failures) B200_CUDA(cudaMemsetAsync(d_stage_failures, 0, kNumStages * sizeof(uint64_t), s));
+    EmbedArgs a{*dg, *etk, *checks, *params, nSlots, d_slot_mol, d_slot_atom_start, d_coords, d_ok, d_attempts, d_energy,
+                reinterpret_cast<unsigned long long*>(d_stage_failures), hess.get(), stride, queue.get(), maxN};
+    PhaseTimer t("etkdg", s);
+    etkdgKernel<<<blocks, kT, smem, s>>>(a);
+    B200_LAUNCHED();
+  });
+}
+
+extern "C" int b200mol_etkdg_check(const b200mol_dg_system* dg, const b200mol_etk_system* etk,
+                                   const b200mol_etkdg_checks* checks, const b200mol_embed_params* params, int32_t nSlots,
+                                   const int32_t* d_slot_mol, const int32_t* d_slot_atom_start, int max_atoms,
+                                   const double* d_pos4, uint32_t* d_fail_masks, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(dg && etk && checks && params, "null system");
+    if (nSlots <= 0) return;
+    B200_REQUIRE(d_slot_mol && d_slot_atom_start && d_pos4 && d_fail_masks, "null pointer");
+    const size_t smem = static_cast<size_t>(4) * max_atoms * sizeof(double);
+    B200_REQUIRE(max_atoms > 0 && smem <= 200 * 1024, "molecule too large (%d atoms)", max_atoms);
+    static bool configured = false;
+    if (!configured) {
+      B200_CUDA(cudaFuncSetAttribute(etkdgCheckKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    int blocks = smCount() * 4;
+    if (blocks > nSlots) blocks = nSlots;
+    EmbedArgs a{*dg, *etk, *checks, *params, nSlots, d_slot_mol, d_slot_atom_start, nullptr, nullptr, nullptr, nullptr,
+                nullptr, nullptr, 0, nullptr, 4 * max_atoms};
+    etkdgCheckKernel<<<blocks, kT, smem, asStream(stream)>>>(a, d_pos4, d_fail_masks);
+    B200_LAUNCHED();
+  });
+}

@@ -50,7 +50,8 @@ __device__ __forceinline__ Range range(const b200mol_term_table& t, int mol) { r
 
 // ============================================================================================ MMFF94
 struct Mmff {
-  static constexpr int kDim = 3;
+  static constexpr int  kDim    = 3;
+  static constexpr bool kHasRef = false;
   using System            = b200mol_mmff_system;
   struct Params {};
   struct View {
@@ -239,7 +240,8 @@ struct Mmff {
 // ============================================================================================ distance geometry
 template <int DIM>
 struct Dg {
-  static constexpr int kDim = DIM;
+  static constexpr int  kDim    = DIM;
+  static constexpr bool kHasRef = false;
   using System            = b200mol_dg_system;
   struct Params {
     double chiralWeight, fourthWeight;
@@ -329,28 +331,42 @@ struct Dg {
 
 // ============================================================================================ ETK (4-D storage)
 struct Etk {
-  static constexpr int kDim = 4;
-  using System            = b200mol_etk_system;
+  static constexpr int  kDim    = 4;
+  static constexpr bool kHasRef = true;
+  using System                  = b200mol_etk_system;
   struct Params {
-    int plain;  // 1 = skip improper terms (ETDG variant)
+    int plain;     // 1 = skip improper terms (ETDG variant)
+    int recentre;  // 1 = re-centre the 1-2 / free 1-3 windows on the reference (= starting) geometry
   };
   struct View {
     const System* s;
     Range         torsion, improper, d12, d13, a13, lr;
+    const double* refPos;  // reference coordinates for the window refresh, or nullptr
   };
   __device__ static View view(const System& s, int mol, const Params& p) {
     Range imp = range(s.improper, mol);
     if (p.plain) imp.end = imp.beg;
     return {&s, range(s.torsion, mol), imp, range(s.dist12, mol), range(s.dist13, mol), range(s.angle13, mol),
-            range(s.longrange, mol)};
+            range(s.longrange, mol), nullptr};
   }
 
-  template <bool GRAD>
-  __device__ static double distTerms(const b200mol_term_table& T, Range r, const double* pos, double* grad, int tid, int nT) {
+  // Flat-bottom distance terms. P = 4 {min, max, k, fixed}: with a reference geometry the window of every term whose
+  // `fixed` flag is 0 is re-centred on the reference distance keeping its half-width (ETK stage refresh,
+  // src/etkdg_stage_etk_minimization.cu:32-64,176-202); long-range terms (P = 3) are never refreshed.
+  template <bool GRAD, int P>
+  __device__ static double distTerms(const b200mol_term_table& T, Range r, const double* pos, double* grad, int tid, int nT,
+                                     const double* refPos) {
     double e = 0.0;
     for (int t = r.beg + tid; t < r.end; t += nT) {
-      const int    i = T.idx[2 * t], j = T.idx[2 * t + 1];
-      const double mn = T.par[3 * t], mx = T.par[3 * t + 1], fk = T.par[3 * t + 2];
+      const int i = T.idx[2 * t], j = T.idx[2 * t + 1];
+      double    mn = T.par[P * t], mx = T.par[P * t + 1];
+      const double fk = T.par[P * t + 2];
+      if (P == 4 && refPos && T.par[P * t + 3] == 0.0) {
+        const V3     rd   = ld<4>(refPos, i) - ld<4>(refPos, j);
+        const double dref = sqrt(dot(rd, rd)), half = (mx - mn) / 2.0;
+        mn                = dref - half;
+        mx                = dref + half;
+      }
       const V3     d  = ld<4>(pos, i) - ld<4>(pos, j);
       const double d2 = dot(d, d);
       double       ref;
@@ -451,9 +467,9 @@ struct Etk {
         acc<4>(grad, ix[3], g4 * dE);
       }
     }
-    e += distTerms<GRAD>(s.dist12, v.d12, pos, grad, tid, nT);
-    e += distTerms<GRAD>(s.dist13, v.d13, pos, grad, tid, nT);
-    e += distTerms<GRAD>(s.longrange, v.lr, pos, grad, tid, nT);
+    e += distTerms<GRAD, 4>(s.dist12, v.d12, pos, grad, tid, nT, v.refPos);
+    e += distTerms<GRAD, 4>(s.dist13, v.d13, pos, grad, tid, nT, v.refPos);
+    e += distTerms<GRAD, 3>(s.longrange, v.lr, pos, grad, tid, nT, nullptr);
     for (int t = v.a13.beg + tid; t < v.a13.end; t += nT) {
       const int16_t* ix = s.angle13.idx + 3 * t;
       const double   mn = s.angle13.par[2 * t], mx = s.angle13.par[2 * t + 1];
@@ -483,7 +499,8 @@ struct Etk {
 
 // ============================================================================================ analytic test potential
 struct Poly {
-  static constexpr int kDim = 1;
+  static constexpr int  kDim    = 1;
+  static constexpr bool kHasRef = false;
   struct System {
     int           power;
     const double* w;

@@ -124,3 +124,314 @@ def random_molgraphs(n: int, min_atoms: int = 8, max_atoms: int = 50, seed: int 
         b_starts.append(len(binv))
     return MolGraphBatch(np.array(a_starts), np.array(b_starts), np.array(ainv, dtype=np.uint32),
                          np.array(binv, dtype=np.uint32), np.array(ba, dtype=np.uint16), np.array(bb, dtype=np.uint16))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Path B: pseudo drug-like molecules with MMFF-shaped term tables and 3-D coordinates (no RDKit on the box).
+# ------------------------------------------------------------------------------------------------------------------
+_VALENCE = {6: 4, 7: 3, 8: 2, 16: 2, 9: 1, 1: 1}
+_VDW_R = {1: 2.6, 6: 3.9, 7: 3.7, 8: 3.5, 9: 3.3, 16: 4.2}
+_VDW_E = {1: 0.02, 6: 0.07, 7: 0.08, 8: 0.09, 9: 0.06, 16: 0.12}
+
+
+def _grow_molecule(rng, n_heavy):
+    """Heavy-atom tree + hydrogens to fill valences; 3-D coordinates by greedy placement. Returns (z, bonds, xyz)."""
+    z = list(_ELEMENTS[rng.integers(0, len(_ELEMENTS), size=n_heavy)])
+    z[0] = 6
+    deg = [0] * n_heavy
+    bonds = []
+    for a in range(1, n_heavy):
+        cand = [q for q in range(a) if deg[q] < _VALENCE[int(z[q])] - (1 if q else 0)] or [q for q in range(a) if deg[q] < 3]
+        q = int(cand[rng.integers(0, len(cand))])
+        if deg[q] >= _VALENCE[int(z[q])]:
+            z[q] = 6
+        bonds.append((q, a))
+        deg[q] += 1
+        deg[a] += 1
+    for a in range(n_heavy):  # hydrogens
+        for _ in range(max(0, _VALENCE[int(z[a])] - deg[a])):
+            z.append(1)
+            bonds.append((a, len(z) - 1))
+    n = len(z)
+    nbrs = [[] for _ in range(n)]
+    for u, v in bonds:
+        nbrs[u].append(v)
+        nbrs[v].append(u)
+    xyz = np.zeros((n, 3))
+    placed = np.zeros(n, dtype=bool)
+    placed[0] = True
+    order = [0]
+    for a in order:
+        for b in nbrs[a]:
+            if placed[b]:
+                continue
+            r0 = 1.09 if (z[a] == 1 or z[b] == 1) else 1.5
+            dirs = rng.normal(size=(24, 3))
+            dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+            cand = xyz[a] + r0 * dirs
+            others = xyz[placed]
+            dmin = np.linalg.norm(cand[:, None, :] - others[None, :, :], axis=2)
+            dmin[:, np.nonzero(np.nonzero(placed)[0] == a)[0]] = 9.0
+            xyz[b] = cand[np.argmax(dmin.min(axis=1))]
+            placed[b] = True
+            order.append(b)
+    return np.array(z, dtype=np.int64), bonds, nbrs, xyz
+
+
+def _topological_distances(n, nbrs):
+    dist = np.full((n, n), 99, dtype=np.int16)
+    for s in range(n):
+        dist[s, s] = 0
+        frontier, d = [s], 0
+        while frontier:
+            d += 1
+            nxt = []
+            for x in frontier:
+                for y in nbrs[x]:
+                    if dist[s, y] == 99:
+                        dist[s, y] = d
+                        nxt.append(y)
+            frontier = nxt
+    return dist
+
+
+def random_mmff_molecule(rng, n_heavy):
+    """One pseudo molecule: dict of MMFF term tables (molecule-local indices) + coordinates + graph."""
+    z, bonds, nbrs, xyz = _grow_molecule(rng, n_heavy)
+    n = len(z)
+    topo = _topological_distances(n, nbrs)
+    t = {}
+    b_idx = np.array(bonds, dtype=np.int16).reshape(-1, 2)
+    is_h = (z[b_idx[:, 0]] == 1) | (z[b_idx[:, 1]] == 1)
+    t["bond"] = (b_idx, np.stack([np.where(is_h, 1.09, 1.5) + rng.normal(0, 0.01, len(b_idx)),
+                                  np.where(is_h, 4.8, 4.3) + rng.normal(0, 0.2, len(b_idx))], axis=1))
+    ang, oop, tor = [], [], []
+    for j in range(n):
+        nb = nbrs[j]
+        for x in range(len(nb)):
+            for y in range(x + 1, len(nb)):
+                ang.append((nb[x], j, nb[y]))
+        if len(nb) == 3 and z[j] in (6, 7) and rng.random() < 0.3:
+            a, b, c = nb
+            oop += [(a, j, b, c), (a, j, c, b), (b, j, c, a)]
+    for j, k in bonds:
+        for i in nbrs[j]:
+            if i == k:
+                continue
+            for l in nbrs[k]:
+                if l == j or l == i:
+                    continue
+                tor.append((i, j, k, l))
+    ang = np.array(ang, dtype=np.int16).reshape(-1, 3)
+    theta0 = np.where(rng.random(len(ang)) < 0.25, 120.0, 109.5) + rng.normal(0, 1.0, len(ang))
+    t["angle"] = (ang, np.stack([theta0, 0.5 + 0.4 * rng.random(len(ang)), np.zeros(len(ang))], axis=1))
+    r0 = lambda a, b: np.where((z[a] == 1) | (z[b] == 1), 1.09, 1.5)  # noqa: E731
+    t["strbend"] = (ang, np.stack([theta0, r0(ang[:, 0], ang[:, 1]), r0(ang[:, 2], ang[:, 1]),
+                                   0.3 * rng.random(len(ang)), 0.3 * rng.random(len(ang))], axis=1))
+    oop = np.array(oop, dtype=np.int16).reshape(-1, 4)
+    t["oop"] = (oop, 0.02 + 0.05 * rng.random((len(oop), 1)))
+    tor = np.array(tor, dtype=np.int16).reshape(-1, 4)
+    t["torsion"] = (tor, rng.normal(0, 0.3, (len(tor), 3)))
+    iu, ju = np.nonzero(np.triu(topo >= 3, k=1))
+    pairs = np.stack([iu, ju], axis=1).astype(np.int16)
+    rr = np.array([_VDW_R[int(e)] for e in z])
+    ee = np.array([_VDW_E[int(e)] for e in z])
+    t["vdw"] = (pairs, np.stack([0.5 * (rr[iu] + rr[ju]), np.sqrt(ee[iu] * ee[ju])], axis=1))
+    q = rng.normal(0, 0.15, n)
+    q -= q.mean()
+    t["ele"] = (pairs, np.stack([q[iu] * q[ju], np.ones(len(iu)), (topo[iu, ju] == 3).astype(np.float64)], axis=1))
+    return {"z": z, "bonds": bonds, "nbrs": nbrs, "topo": topo, "xyz": xyz, "terms": t}
+
+
+def random_mmff_system(n_mols: int, min_heavy: int = 10, max_heavy: int = 50, seed: int = SEED):
+    """(FlatSystem kind 'mmff', list of start coordinates [nAtoms,3], list of raw molecule dicts)."""
+    from nvmolkit_b200.forcefield import FlatSystem
+
+    rng = np.random.default_rng(seed)
+    mols = [random_mmff_molecule(rng, int(rng.integers(min_heavy, max_heavy + 1))) for _ in range(n_mols)]
+    system = FlatSystem.from_molecules("mmff", [len(m["z"]) for m in mols], [m["terms"] for m in mols])
+    return system, [m["xyz"] for m in mols], mols
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ETKDG inputs for the pseudo molecules: smoothed bounds matrix -> DG terms, ETK terms, stereo/geometry check tables.
+# ------------------------------------------------------------------------------------------------------------------
+_VDW_RADIUS = {1: 1.1, 6: 1.7, 7: 1.55, 8: 1.52, 9: 1.47, 16: 1.8}
+
+
+def smooth_bounds_numpy(ub: np.ndarray, lb: np.ndarray):
+    """Floyd-style triangle smoothing on separate symmetric upper / lower matrices (data preparation only)."""
+    n = len(ub)
+    for k in range(n):
+        ub = np.minimum(ub, ub[:, k:k + 1] + ub[k:k + 1, :])
+        lb = np.maximum(lb, np.maximum(lb[:, k:k + 1] - ub[k:k + 1, :], lb[k:k + 1, :] - ub[:, k:k + 1]))
+    np.fill_diagonal(ub, 0.0)
+    np.fill_diagonal(lb, 0.0)
+    return ub, lb
+
+
+def bounds_matrix(mol) -> np.ndarray:
+    """RDKit-layout bounds matrix ([i][j], i<j upper; [j][i] lower) from the molecule's topology, UNSMOOTHED."""
+    z, nbrs, topo = mol["z"], mol["nbrs"], mol["topo"]
+    n = len(z)
+    planar = mol.get("planar", set())
+    r0 = lambda a, b: 1.09 if (z[a] == 1 or z[b] == 1) else 1.5  # noqa: E731
+    ub = np.full((n, n), 1000.0)
+    lb = np.zeros((n, n))
+    rv = np.array([_VDW_RADIUS[int(e)] for e in z])
+    scale = np.where(topo == 4, 0.7, np.where(topo == 5, 0.85, 1.0))
+    lb[:] = scale * (rv[:, None] + rv[None, :])
+    for i in range(n):
+        for j in nbrs[i]:
+            ub[i, j], lb[i, j] = r0(i, j) + 0.01, r0(i, j) - 0.01
+    for j in range(n):
+        theta = np.deg2rad(120.0 if j in planar else 109.5)
+        nb = nbrs[j]
+        for x in range(len(nb)):
+            for y in range(x + 1, len(nb)):
+                a, b = nb[x], nb[y]
+                d = np.sqrt(r0(a, j) ** 2 + r0(b, j) ** 2 - 2 * r0(a, j) * r0(b, j) * np.cos(theta))
+                ub[a, b] = ub[b, a] = d + 0.04
+                lb[a, b] = lb[b, a] = d - 0.04
+    for (j, k) in mol["bonds"]:
+        for i in nbrs[j]:
+            if i == k:
+                continue
+            for l in nbrs[k]:
+                if l == j or l == i or topo[i, l] != 3:
+                    continue
+                tj = np.deg2rad(120.0 if j in planar else 109.5)
+                tk = np.deg2rad(120.0 if k in planar else 109.5)
+                r1, r2, r3 = r0(i, j), r0(j, k), r0(k, l)
+                # cis (torsion 0) and trans (180) 1-4 distances
+                xi, yi = -r1 * np.cos(tj), r1 * np.sin(tj)
+                xl, yl = r2 + r3 * np.cos(tk) * -1.0, r3 * np.sin(tk)
+                cis = np.hypot(xl - xi, yl - yi)
+                trans = np.hypot(xl - xi, yl + yi)
+                lo, hi = min(cis, trans) - 0.06, max(cis, trans) + 0.06
+                ub[i, l] = ub[l, i] = min(ub[i, l], hi) if ub[i, l] < 999 else hi
+                lb[i, l] = lb[l, i] = lo
+    m = np.zeros((n, n))
+    iu = np.triu_indices(n, 1)
+    m[iu] = ub[iu]
+    m.T[iu] = lb[iu]
+    return m
+
+
+def etkdg_tables(rng, mol, smoothed: np.ndarray):
+    """DG / ETK / check term tables of one pseudo molecule from its SMOOTHED bounds matrix."""
+    z, nbrs, topo = mol["z"], mol["nbrs"], mol["topo"]
+    n = len(z)
+    planar = mol.get("planar", set())
+    iu, ju = np.triu_indices(n, 1)
+    ubv, lbv = smoothed[iu, ju], smoothed[ju, iu]
+    dg = {"dist": (np.stack([iu, ju], 1), np.stack([lbv ** 2, ubv ** 2, np.ones(len(iu))], 1)),
+          "fourth": (np.arange(n).reshape(-1, 1), np.zeros((n, 0)))}
+    quat = [a for a in range(n) if len(nbrs[a]) == 4 and z[a] == 6]
+    rng.shuffle(quat)
+    chiral_idx, chiral_par, chk_chiral = [], [], []
+    for c in quat[:2]:
+        nb = list(nbrs[c])
+        if rng.random() < 0.5:
+            lo, hi = 5.0, 100.0
+        else:
+            lo, hi = -100.0, -5.0
+        chiral_idx.append(nb)
+        chiral_par.append([hi, lo])  # DG table: {volUpper, volLower}
+        chk_chiral.append(([c] + nb, [lo, hi]))
+    dg["chiral"] = (np.array(chiral_idx, dtype=np.int16).reshape(-1, 4), np.array(chiral_par).reshape(-1, 2))
+    tet = [([c] + list(nbrs[c]), [0.0]) for c in quat[2:5]]
+    pairs_cd = []
+    for (cen, par) in chk_chiral:
+        ids = cen[1:]
+        for x in range(4):
+            for y in range(x + 1, 4):
+                a, b = sorted((ids[x], ids[y]))
+                pairs_cd.append(([a, b], [smoothed[b, a], smoothed[a, b]]))
+    checks = {
+        "tetrahedral": (np.array([t[0] for t in tet], dtype=np.int16).reshape(-1, 5), np.array([t[1] for t in tet]).reshape(-1, 1)),
+        "chiral": (np.array([c[0] for c in chk_chiral], dtype=np.int16).reshape(-1, 5),
+                   np.array([c[1] for c in chk_chiral]).reshape(-1, 2)),
+        "chiralDist": (np.array([p[0] for p in pairs_cd], dtype=np.int16).reshape(-1, 2),
+                       np.array([p[1] for p in pairs_cd]).reshape(-1, 2)),
+    }
+    # ETK terms
+    tor_i, tor_p = [], []
+    db_stereo, db_geom = [], []
+    for (j, k) in mol["bonds"]:
+        if len(nbrs[j]) < 2 or len(nbrs[k]) < 2 or z[j] == 1 or z[k] == 1:
+            continue
+        i = [x for x in nbrs[j] if x != k][0]
+        l = [x for x in nbrs[k] if x != j][0]
+        v = np.zeros(6)
+        v[2] = rng.uniform(1.0, 6.0)
+        if rng.random() < 0.3:
+            v[0] = rng.uniform(0.0, 3.0)
+        sg = rng.choice([-1.0, 1.0], size=6)
+        tor_i.append([i, j, k, l])
+        tor_p.append(np.concatenate([v, sg]))
+        if j in planar and k in planar and len(db_stereo) < 1:
+            db_stereo.append(([i, j, k, l], [float(rng.choice([-1.0, 1.0]))]))
+            db_geom.append([i, j, k])
+            db_geom.append([j, k, l])
+    imp_i, imp_p = [], []
+    for c in sorted(planar):
+        a, b, d = nbrs[c]
+        for (p, q, r) in ((a, b, d), (a, d, b), (b, d, a)):
+            imp_i.append([p, c, q, r])
+            imp_p.append([1.0, -1.0, 0.0, 10.0 / 3.0])
+    d12 = [(i, j) for i, j in mol["bonds"]]
+    xyz12 = np.array([[smoothed[max(i, j), min(i, j)], smoothed[min(i, j), max(i, j)], 100.0, 0.0] for i, j in d12]).reshape(-1, 4)
+    i13, j13 = np.nonzero(np.triu(topo == 2, 1))
+    xyz13 = np.stack([smoothed[j13, i13], smoothed[i13, j13], np.full(len(i13), 100.0),
+                      np.array([1.0 if (set(nbrs[a]) & set(nbrs[b]) & planar) else 0.0 for a, b in zip(i13, j13)])], 1)
+    ang = [(a, c, b) for c in sorted(planar) for (a, b) in ((nbrs[c][0], nbrs[c][1]),)]
+    ilr, jlr = np.nonzero(np.triu(topo > 3, 1))
+    etk = {
+        "torsion": (np.array(tor_i, dtype=np.int16).reshape(-1, 4), np.array(tor_p).reshape(-1, 12)),
+        "improper": (np.array(imp_i, dtype=np.int16).reshape(-1, 4), np.array(imp_p).reshape(-1, 4)),
+        "dist12": (np.array(d12, dtype=np.int16).reshape(-1, 2), xyz12),
+        "dist13": (np.stack([i13, j13], 1), xyz13.reshape(-1, 4)),
+        "angle13": (np.array(ang, dtype=np.int16).reshape(-1, 3), np.tile([115.0, 125.0], (len(ang), 1)).reshape(-1, 2)),
+        "longrange": (np.stack([ilr, jlr], 1), np.stack([smoothed[jlr, ilr], smoothed[ilr, jlr], np.full(len(ilr), 10.0)], 1)),
+    }
+    checks["dbStereo"] = (np.array([d[0] for d in db_stereo], dtype=np.int16).reshape(-1, 4),
+                          np.array([d[1] for d in db_stereo]).reshape(-1, 1))
+    checks["dbGeom"] = (np.array(db_geom, dtype=np.int16).reshape(-1, 3), np.zeros((len(db_geom), 0)))
+    return dg, etk, checks, len(planar)
+
+
+def random_embed_molecules(n_mols: int, min_heavy: int = 6, max_heavy: int = 25, seed: int = SEED):
+    """Pseudo molecules with everything ETKDG needs. Returns (FlatEmbedMolecules, raw molecule dicts)."""
+    from nvmolkit_b200.embedMolecules import FlatEmbedMolecules
+    from nvmolkit_b200.forcefield import CheckTables, FlatSystem
+
+    rng = np.random.default_rng(seed)
+    mols, dgs, etks, chks, nimp = [], [], [], [], []
+    for _ in range(n_mols):
+        m = random_mmff_molecule(rng, int(rng.integers(min_heavy, max_heavy + 1)))
+        m["planar"] = {a for a in range(len(m["z"])) if len(m["nbrs"][a]) == 3 and m["z"][a] in (6, 7) and rng.random() < 0.4}
+        b = bounds_matrix(m)
+        n = len(m["z"])
+        iu = np.triu_indices(n, 1)
+        ub = np.zeros((n, n))
+        lb = np.zeros((n, n))
+        ub[iu] = b[iu]
+        ub.T[iu] = b[iu]
+        lb[iu] = b.T[iu]
+        lb.T[iu] = b.T[iu]
+        ub, lb = smooth_bounds_numpy(ub, lb)
+        sm = np.zeros((n, n))
+        sm[iu] = ub[iu]
+        sm.T[iu] = lb[iu]
+        m["bounds_raw"], m["bounds"] = b, sm
+        dg, etk, chk, np_ = etkdg_tables(rng, m, sm)
+        mols.append(m)
+        dgs.append(dg)
+        etks.append(etk)
+        chks.append(chk)
+        nimp.append(np_)
+    counts = [len(m["z"]) for m in mols]
+    flat = FlatEmbedMolecules(FlatSystem.from_molecules("dg", counts, dgs), FlatSystem.from_molecules("etk", counts, etks),
+                              CheckTables.from_molecules(counts, chks, nimp))
+    return flat, mols

@@ -142,3 +142,238 @@ def morgan(atom_starts, bond_starts, atom_inv, bond_inv, bond_a, bond_b, radius:
                         _p(bond_inv, C.c_uint32), _p(bond_a, C.c_uint16), _p(bond_b, C.c_uint16), n, radius, fp_bits,
                         _p(out, C.c_uint32))
     return out
+
+
+# ------------------------------------------------------------------ path B (force fields + BFGS)
+class _TermTableC(C.Structure):
+    _fields_ = [("starts", C.c_void_p), ("idx", C.c_void_p), ("par", C.c_void_p)]
+
+
+_FF_LAYOUT = {
+    "mmff": ("bond", "angle", "strbend", "oop", "torsion", "vdw", "ele"),
+    "dg": ("dist", "chiral", "fourth"),
+    "etk": ("torsion", "improper", "dist12", "dist13", "angle13", "longrange"),
+}
+
+
+def _ff_struct(kind):
+    fields = [("nMols", C.c_int32), ("atomCounts", C.c_void_p)] + [(n, _TermTableC) for n in _FF_LAYOUT[kind]]
+    return type(f"Oracle{kind}System", (C.Structure,), {"_fields_": fields})
+
+
+_FF_STRUCT = {k: _ff_struct(k) for k in _FF_LAYOUT}
+
+
+def _host_system(kind: str, atom_counts: np.ndarray, tables: dict):
+    """tables[name] = (starts int32, idx int16 [n,K], par float64 [n,P]); arrays must stay alive during the call."""
+    st = _FF_STRUCT[kind]()
+    st.nMols = len(atom_counts)
+    st.atomCounts = atom_counts.ctypes.data
+    for name in _FF_LAYOUT[kind]:
+        starts, idx, par = tables[name]
+        setattr(st, name, _TermTableC(starts.ctypes.data, idx.ctypes.data, par.ctypes.data if par.size else None))
+    return st
+
+
+def _declare_ff(L):
+    vp, f64p, i32p, i8p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int8)
+    L.oracle_mmff_energy_grad.argtypes = [vp, C.c_int, f64p, f64p, f64p]
+    L.oracle_mmff_energy_grad.restype = C.c_double
+    L.oracle_dg_energy_grad.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, f64p, f64p]
+    L.oracle_dg_energy_grad.restype = C.c_double
+    L.oracle_etk_energy_grad.argtypes = [vp, C.c_int, f64p, f64p, C.c_int]
+    L.oracle_etk_energy_grad.restype = C.c_double
+    L.oracle_mmff_minimize.argtypes = [vp, C.c_int, i32p, i32p, f64p, C.c_int, C.c_double, f64p, i8p, i32p]
+    L.oracle_mmff_minimize.restype = None
+    L.oracle_dg_minimize.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, i32p, i32p, f64p, C.c_int, C.c_double,
+                                     f64p, i8p, i32p]
+    L.oracle_dg_minimize.restype = None
+    L.oracle_etk_minimize.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, i32p, f64p, C.c_int, C.c_double, f64p, i8p, i32p]
+    L.oracle_etk_energy_grad_ref.argtypes = [vp, C.c_int, f64p, f64p, C.c_int, f64p]
+    L.oracle_etk_energy_grad_ref.restype = C.c_double
+    L.oracle_etk_minimize.restype = None
+    L.oracle_poly_minimize.argtypes = [C.c_int, C.c_int, f64p, f64p, f64p, C.c_int, C.c_double, C.c_int, f64p, i32p]
+    L.oracle_poly_minimize.restype = C.c_int
+    L.oracle_poly_energy_grad.argtypes = [C.c_int, C.c_int, f64p, f64p, f64p, f64p]
+    L.oracle_poly_energy_grad.restype = C.c_double
+
+
+_late_lib = [None]
+
+
+def _ensure_ff():
+    L = lib()
+    if _late_lib[0] is None:
+        _late_lib[0] = L
+        _declare_ff(L)
+    return L
+
+
+def ff_energy_grad(kind: str, atom_counts, tables, mol: int, pos, want_grad=True, *, dim=0, chiral_weight=1.0,
+                   fourth_dim_weight=0.1, plain=False, ref_pos=None):
+    """Energy (and gradient) of one conformer of molecule `mol`. pos: float64 [nAtoms, dim]."""
+    L = _ensure_ff()
+    atom_counts = np.ascontiguousarray(atom_counts, dtype=np.int32)
+    st = _host_system(kind, atom_counts, tables)
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    grad = np.zeros_like(pos) if want_grad else None
+    gp = _p(grad, C.c_double) if want_grad else None
+    if kind == "mmff":
+        per = np.zeros(7)
+        e = L.oracle_mmff_energy_grad(C.addressof(st), mol, _p(pos, C.c_double), gp, _p(per, C.c_double))
+        return e, grad, per
+    if kind == "dg":
+        e = L.oracle_dg_energy_grad(C.addressof(st), mol, dim or 4, chiral_weight, fourth_dim_weight, _p(pos, C.c_double), gp)
+        return e, grad, None
+    rp = None
+    if ref_pos is not None:
+        ref_pos = np.ascontiguousarray(ref_pos, dtype=np.float64)
+        rp = _p(ref_pos, C.c_double)
+    e = L.oracle_etk_energy_grad_ref(C.addressof(st), mol, _p(pos, C.c_double), gp, int(plain), rp)
+    return e, grad, None
+
+
+def ff_minimize(kind: str, atom_counts, tables, conf_mol, conf_atom_start, positions, max_iters=200, grad_tol=1e-4, *,
+                dim=0, chiral_weight=1.0, fourth_dim_weight=0.1, plain=False, recentre=True):
+    """RDKit-faithful BFGS on every conformer (OpenMP over conformers). Returns (positions, energies, converged, iters)."""
+    L = _ensure_ff()
+    atom_counts = np.ascontiguousarray(atom_counts, dtype=np.int32)
+    st = _host_system(kind, atom_counts, tables)
+    conf_mol = np.ascontiguousarray(conf_mol, dtype=np.int32)
+    starts = np.ascontiguousarray(conf_atom_start, dtype=np.int32)
+    pos = np.array(positions, dtype=np.float64, order="C", copy=True)
+    n = len(conf_mol)
+    e = np.zeros(n)
+    conv = np.zeros(n, dtype=np.int8)
+    iters = np.zeros(n, dtype=np.int32)
+    a = (n, _p(conf_mol, C.c_int32), _p(starts, C.c_int32), _p(pos, C.c_double), int(max_iters), float(grad_tol),
+         _p(e, C.c_double), _p(conv, C.c_int8), _p(iters, C.c_int32))
+    if kind == "mmff":
+        L.oracle_mmff_minimize(C.addressof(st), *a)
+    elif kind == "dg":
+        L.oracle_dg_minimize(C.addressof(st), dim or 4, chiral_weight, fourth_dim_weight, *a)
+    else:
+        L.oracle_etk_minimize(C.addressof(st), int(plain), int(recentre), *a)
+    return pos, e, conv, iters
+
+
+def poly_minimize(power, w, c, x0, max_iters, grad_tol, scale_grads=False):
+    L = _ensure_ff()
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    e = C.c_double(0)
+    it = C.c_int32(0)
+    st = L.oracle_poly_minimize(len(x), power, _p(w, C.c_double), _p(c, C.c_double), _p(x, C.c_double), max_iters,
+                                grad_tol, int(scale_grads), C.byref(e), C.byref(it))
+    return x, e.value, st, it.value
+
+
+# ------------------------------------------------------------------ DG preparation + ETKDG
+class _ChecksC(C.Structure):
+    _fields_ = [(n, _TermTableC) for n in ("tetrahedral", "chiral", "chiralDist", "dbStereo", "dbGeom")] + \
+               [("numImpropers", C.c_void_p)]
+
+
+class _EmbedParamsC(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("boxSize", C.c_double), ("optimizerForceTol", C.c_double),
+                ("enforceChirality", C.c_int32), ("useExpTorsions", C.c_int32), ("useBasicKnowledge", C.c_int32),
+                ("maxAttempts", C.c_int32), ("dgIters", C.c_int32), ("fourthIters", C.c_int32), ("etkIters", C.c_int32),
+                ("maxRestarts", C.c_int32)]
+
+
+def _checks_struct(tables: dict, num_impropers: np.ndarray):
+    st = _ChecksC()
+    for name in ("tetrahedral", "chiral", "chiralDist", "dbStereo", "dbGeom"):
+        starts, idx, par = tables[name]
+        setattr(st, name, _TermTableC(starts.ctypes.data, idx.ctypes.data, par.ctypes.data if par.size else None))
+    st.numImpropers = num_impropers.ctypes.data
+    return st
+
+
+def _embed_params(p: dict):
+    return _EmbedParamsC(**p)
+
+
+def triangle_smooth(bounds: np.ndarray, tol: float = 0.0):
+    """In-place smoothing of one RDKit-layout bounds matrix copy. Returns (matrix, ok)."""
+    L = lib()
+    b = np.array(bounds, dtype=np.float64, order="C", copy=True)
+    L.oracle_triangle_smooth.restype = C.c_int
+    ok = L.oracle_triangle_smooth(b.ctypes.data_as(C.c_void_p), C.c_int(b.shape[0]), C.c_double(tol))
+    return b, bool(ok)
+
+
+def power_eigen(mat: np.ndarray, num_eigs: int, v0: np.ndarray):
+    L = lib()
+    m = np.array(mat, dtype=np.float64, order="C", copy=True)
+    n = m.shape[0]
+    v0 = np.ascontiguousarray(v0, dtype=np.float64)
+    vals = np.zeros(num_eigs)
+    vecs = np.zeros((num_eigs, n))
+    L.oracle_power_eigen.restype = C.c_int
+    k = L.oracle_power_eigen(m.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(num_eigs), v0.ctypes.data_as(C.c_void_p),
+                             vals.ctypes.data_as(C.c_void_p), vecs.ctypes.data_as(C.c_void_p))
+    return vals, vecs, k
+
+
+def metric_embed(dist: np.ndarray, dim: int, v0: np.ndarray):
+    """Distance matrix -> coordinates [n, dim] (or None when an eigenvalue is not positive)."""
+    L = lib()
+    d = np.ascontiguousarray(dist, dtype=np.float64)
+    n = d.shape[0]
+    T = np.zeros((n, n))
+    L.oracle_metric_matrix(d.ctypes.data_as(C.c_void_p), C.c_int(n), T.ctypes.data_as(C.c_void_p))
+    vals, vecs, k = power_eigen(T, dim, v0)
+    if k < dim:
+        return None
+    coords = np.zeros((n, dim))
+    L.oracle_coords_from_eigen.restype = C.c_int
+    ok = L.oracle_coords_from_eigen(vals.ctypes.data_as(C.c_void_p), vecs.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(dim),
+                                    coords.ctypes.data_as(C.c_void_p))
+    return coords if ok else None
+
+
+def etkdg_check(dg, etk, checks, num_impropers, params: dict, mol: int, pos4: np.ndarray) -> int:
+    """dg / etk = (atom_counts, tables); checks = tables dict. Returns the failure bit mask of include/b200mol.h."""
+    L = _ensure_ff()
+    d = _host_system("dg", np.ascontiguousarray(dg[0], dtype=np.int32), dg[1])
+    e = _host_system("etk", np.ascontiguousarray(etk[0], dtype=np.int32), etk[1])
+    ck = _checks_struct(checks, np.ascontiguousarray(num_impropers, dtype=np.int32))
+    pr = _embed_params(params)
+    pos4 = np.ascontiguousarray(pos4, dtype=np.float64)
+    L.oracle_etkdg_check.restype = C.c_uint
+    L.oracle_etkdg_check.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    return int(L.oracle_etkdg_check(C.addressof(d), C.addressof(e), C.addressof(ck), C.addressof(pr), mol, pos4.ctypes.data))
+
+
+def etkdg_embed(dg, etk, checks, num_impropers, params: dict, slot_mol):
+    """CPU pipeline over slots (serial). Returns (list of coords3 | None, attempts, energies, stage failure counts[11])."""
+    L = _ensure_ff()
+    counts = np.ascontiguousarray(dg[0], dtype=np.int32)
+    d = _host_system("dg", counts, dg[1])
+    e = _host_system("etk", np.ascontiguousarray(etk[0], dtype=np.int32), etk[1])
+    nimp = np.ascontiguousarray(num_impropers, dtype=np.int32)
+    ck = _checks_struct(checks, nimp)
+    pr = _embed_params(params)
+    L.oracle_etkdg_embed_one.restype = C.c_int
+    L.oracle_etkdg_embed_one.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    fails = np.zeros(11, dtype=np.int64)
+    out, attempts, energies = [], [], []
+    for slot, mol in enumerate(slot_mol):
+        xyz = np.zeros((counts[mol], 3))
+        att = C.c_int32(0)
+        en = C.c_double(0.0)
+        ok = L.oracle_etkdg_embed_one(C.addressof(d), C.addressof(e), C.addressof(ck), C.addressof(pr), slot, int(mol),
+                                      xyz.ctypes.data, C.addressof(att), C.addressof(en), fails.ctypes.data)
+        out.append(xyz if ok else None)
+        attempts.append(att.value)
+        energies.append(en.value)
+    return out, np.array(attempts), np.array(energies), fails
+
+
+def uniform01(seed: int, slot: int, attempt: int, element: int) -> float:
+    L = lib()
+    L.oracle_uniform01.restype = C.c_double
+    L.oracle_uniform01.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+    return float(L.oracle_uniform01(seed, slot, attempt, element))

@@ -387,7 +387,10 @@ static double etk_cos_phi(const double* p1, const double* p2, const double* p3, 
   return clampd(dot3(t1, t2) / sqrt(comb), -1.0, 1.0);
 }
 
-double oracle_etk_energy_grad(const EtkSystem* s, int mol, const double* pos, double* grad, int plain) {
+/* refPos (optional): reference geometry; the 1-2 / 1-3 windows whose `fixed` flag is 0 are re-centred on the reference
+ * distance keeping their half-width (src/etkdg_stage_etk_minimization.cu:32-64). */
+double oracle_etk_energy_grad_ref(const EtkSystem* s, int mol, const double* pos, double* grad, int plain,
+                                  const double* refPos) {
   double e = 0.0;
   for (int t = s->torsion.starts[mol]; t < s->torsion.starts[mol + 1]; ++t) {
     const int16_t* ix = s->torsion.idx + 4 * t;
@@ -507,9 +510,18 @@ double oracle_etk_energy_grad(const EtkSystem* s, int mol, const double* pos, do
   const TermTable* dts[3] = {&s->dist12, &s->dist13, &s->longrange};
   for (int q = 0; q < 3; ++q) {
     const TermTable* T = dts[q];
+    const int        P = q < 2 ? 4 : 3;
     for (int t = T->starts[mol]; t < T->starts[mol + 1]; ++t) {
       const int    i = T->idx[2 * t], j = T->idx[2 * t + 1];
-      const double mn = T->par[3 * t], mx = T->par[3 * t + 1], fk = T->par[3 * t + 2];
+      double       mn = T->par[P * t], mx = T->par[P * t + 1];
+      const double fk = T->par[P * t + 2];
+      if (P == 4 && refPos && T->par[P * t + 3] == 0.0) {
+        double r2 = 0.0;
+        for (int c = 0; c < 3; ++c) r2 += (refPos[4 * i + c] - refPos[4 * j + c]) * (refPos[4 * i + c] - refPos[4 * j + c]);
+        const double dref = sqrt(r2), half = (mx - mn) / 2.0;
+        mn = dref - half;
+        mx = dref + half;
+      }
       double       d2 = 0.0;
       for (int c = 0; c < 3; ++c) d2 += (pos[4 * i + c] - pos[4 * j + c]) * (pos[4 * i + c] - pos[4 * j + c]);
       double diff, pre;
@@ -568,6 +580,10 @@ double oracle_etk_energy_grad(const EtkSystem* s, int mol, const double* pos, do
     }
   }
   return e;
+}
+
+double oracle_etk_energy_grad(const EtkSystem* s, int mol, const double* pos, double* grad, int plain) {
+  return oracle_etk_energy_grad_ref(s, mol, pos, grad, plain, NULL);
 }
 
 /* =========================================================================================== test potential
@@ -759,10 +775,11 @@ static double dg_fn(const void* c, const double* x, double* g) {
 typedef struct {
   const EtkSystem* s;
   int              mol, plain;
+  const double*    ref;
 } EtkCtx;
 static double etk_fn(const void* c, const double* x, double* g) {
   const EtkCtx* m = (const EtkCtx*)c;
-  return oracle_etk_energy_grad(m->s, m->mol, x, g, m->plain);
+  return oracle_etk_energy_grad_ref(m->s, m->mol, x, g, m->plain, m->ref);
 }
 static double poly_fn(const void* c, const double* x, double* g) { return poly_energy_grad((const PolySystem*)c, x, g); }
 
@@ -793,15 +810,21 @@ void oracle_dg_minimize(const DgSystem* s, int dim, double chiralWeight, double 
     if (iters) iters[c] = it;
   }
 }
-void oracle_etk_minimize(const EtkSystem* s, int plain, int nConf, const int32_t* confMol,
+void oracle_etk_minimize(const EtkSystem* s, int plain, int recentre, int nConf, const int32_t* confMol,
                          const int32_t* confAtomStart, double* pos, int maxIters, double gradTol, double* energies,
                          int8_t* converged, int32_t* iters) {
 #pragma omp parallel for schedule(dynamic, 1)
   for (int c = 0; c < nConf; ++c) {
-    EtkCtx ctx = {s, confMol[c], plain};
+    const int nn  = 4 * s->atomCounts[confMol[c]];
+    double*   ref = NULL;
+    if (recentre) {
+      ref = (double*)malloc(sizeof(double) * nn);
+      memcpy(ref, pos + 4 * (size_t)confAtomStart[c], sizeof(double) * nn);
+    }
+    EtkCtx ctx = {s, confMol[c], plain, ref};
     int    it  = 0;
-    const int st = bfgs_minimize(4 * s->atomCounts[confMol[c]], pos + 4 * (size_t)confAtomStart[c], etk_fn, &ctx,
-                                 maxIters, gradTol, 1, &energies[c], &it);
+    const int st = bfgs_minimize(nn, pos + 4 * (size_t)confAtomStart[c], etk_fn, &ctx, maxIters, gradTol, 1, &energies[c], &it);
+    free(ref);
     if (converged) converged[c] = st == 0;
     if (iters) iters[c] = it;
   }
@@ -817,4 +840,21 @@ int oracle_poly_minimize(int n, int power, const double* w, const double* c, dou
 double oracle_poly_energy_grad(int n, int power, const double* w, const double* c, const double* x, double* grad) {
   PolySystem s = {n, power, w, c};
   return poly_energy_grad(&s, x, grad);
+}
+
+/* Single-conformer entry points used by oracle_etkdg.c. maxRestarts > 0: re-run while unconverged (repeatUntilConverged). */
+int oracle_dg_minimize_one(const DgSystem* s, int mol, int dim, double cw, double fw, double* pos, int maxIters,
+                           double gradTol, int maxRestarts, double* energy) {
+  DgCtx ctx = {s, mol, dim, cw, fw};
+  int   st  = 1;
+  for (int r = 0;; ++r) {
+    st = bfgs_minimize(dim * s->atomCounts[mol], pos, dg_fn, &ctx, maxIters, gradTol, 1, energy, NULL);
+    if (st == 0 || r >= maxRestarts) break;
+  }
+  return st;
+}
+int oracle_etk_minimize_one(const EtkSystem* s, int mol, int plain, const double* ref, double* pos, int maxIters,
+                            double gradTol, double* energy) {
+  EtkCtx ctx = {s, mol, plain, ref};
+  return bfgs_minimize(4 * s->atomCounts[mol], pos, etk_fn, &ctx, maxIters, gradTol, 1, energy, NULL);
 }
