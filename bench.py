@@ -223,6 +223,14 @@ def run_b200(args) -> None:
         step_e2e()
         ms_e2e, _ = timed(step_e2e, args.steps)
 
+    # second half of the BASELINE metric: ETKDG + MMFF mols/s (config 3 shape, reduced count so the default run stays short)
+    path_b = None
+    if args.etkdg_mols > 0:
+        flat_b, mmff_b = path_b_pool(args.pool, synthetic.SEED)
+        path_b = run_path_b_gpu(flat_b, mmff_b, args.etkdg_mols, args.confs, dev, max(1, args.steps - 1), 1, world, rank)
+        path_b["config"] = {"workload": f"{args.etkdg_mols} drug-like pseudo-mols (20-50 heavy atoms, {args.pool} distinct) x "
+                                        f"{args.confs} conformers: ETKDG embed + MMFF94 200-iter BFGS", "data": "synthetic"}
+
     ids_h = ids.cpu().numpy()
     n_clusters = int(cen.numel())
     assert ids_h.min() == 0 and ids_h.max() == n_clusters - 1
@@ -282,9 +290,109 @@ def run_b200(args) -> None:
                            "kind": "port",
                            "sample": f"{len(fps)}x{len(fps)} clustered 2048-bit fingerprints, cutoff {CUTOFF}, {dt:.1f} s"}
     out["parity_on_sample"] = "bit-exact" if parity else "MISMATCH"
+    out["etkdg_mmff"] = path_b
+    if path_b is not None:
+        flat_b, mmff_b = path_b_pool(args.pool, synthetic.SEED)
+        nb = min(args.etkdg_cpu_mols, path_b["n_mols"])
+        v, dt_b, okf = run_path_b_cpu(flat_b, mmff_b, nb, path_b["confs_per_mol"])
+        path_b["cpu_baseline"] = {"value": v, "unit": "mols/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                  "sample": f"{nb} mols x {path_b['confs_per_mol']} conformers, {dt_b:.1f} s, embedded {okf:.2f}"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- path B (conformers)
+ETKDG_PARAMS = dict(seed=20260924, boxSize=10.0, optimizerForceTol=1e-3, enforceChirality=1, useExpTorsions=1,
+                    useBasicKnowledge=1, maxAttempts=0, dgIters=400, fourthIters=200, etkIters=300, maxRestarts=20)
+
+
+def path_b_pool(pool: int, seed: int):
+    """`pool` distinct pseudo drug-like molecules (20-50 heavy atoms, hydrogens added) with DG/ETK/check and MMFF tables."""
+    from nvmolkit_b200 import synthetic
+    from nvmolkit_b200.forcefield import FlatSystem
+
+    flat, mols = synthetic.random_embed_molecules(pool, 20, 50, seed=seed)
+    mmff = FlatSystem.from_molecules("mmff", [len(m["z"]) for m in mols], [m["terms"] for m in mols])
+    return flat, mmff
+
+
+def run_path_b_gpu(flat, mmff, n_mols: int, confs: int, dev, steps: int, warmup: int, world: int = 1, rank: int = 0):
+    """ETKDG embed of `confs` conformers for n_mols molecules (the pool cycled), then MMFF94 200-iteration BFGS of every
+    embedded conformer. Returns dict with mols/s (device-resident tables; coordinates are produced on the device)."""
+    import torch
+    import torch.distributed as dist
+
+    from nvmolkit_b200 import _lib
+    from nvmolkit_b200.distributed import all_gather_v, molecule_range
+    from nvmolkit_b200.embedMolecules import EmbedParameters, embed_slots
+    from nvmolkit_b200.forcefield import ConformerBatch
+    from nvmolkit_b200.minimizer import minimize
+
+    pool = len(flat)
+    lo, hi = molecule_range(n_mols, rank, world)
+    mol_ids = (np.arange(lo, hi) % pool).astype(np.int32)
+    params = EmbedParameters(randomSeed=ETKDG_PARAMS["seed"])
+    max_attempts = 10 * int(flat.atom_counts.max())
+
+    def step():
+        raw = embed_slots(flat, params, confs, max_attempts, mol_indices=mol_ids)
+        ok = raw.ok.bool()
+        # MMFF on the embedded conformers (device-resident hand-over: coordinates never leave the GPU)
+        batch = ConformerBatch(raw.slot_mol, raw.slot_atom_start, np.zeros((0, 3)))
+        res = minimize(mmff, batch, 200, 1e-4, positions=raw.coords, active=ok.to(torch.uint8))
+        if world > 1:  # the one collective of the path: all-gather of the results
+            all_gather_v(res.energies)
+            all_gather_v(res.positions)
+        return raw, res
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        raw, res = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ok = raw.ok.cpu().numpy().astype(bool)
+    st = res.status.cpu().numpy()
+    return {"mols_per_s": n_mols / (float(ms.item()) * 1e-3), "ms_per_step": float(ms.item()), "n_mols": n_mols,
+            "confs_per_mol": confs, "conformers_embedded_frac": float(ok.mean()),
+            "mean_attempts": float(raw.attempts.float().mean().item()),
+            "mmff_converged_frac": float((st[ok] == 0).mean()) if ok.any() else 0.0,
+            "stage_failures": raw.stage_failures.cpu().numpy().tolist(),
+            "phases_ms": {"etkdg": _lib.profile_read("etkdg"), "mmff_bfgs": _lib.profile_read("bfgs")},
+            "gpu_launches": int(_lib.launch_count() - l0), "atoms_per_mol_mean": float(flat.atom_counts.mean())}
+
+
+def run_path_b_cpu(flat, mmff, n_mols: int, confs: int):
+    """Same pipeline on the host cores with the oracle (OpenMP over conformer slots). Returns mols/s."""
+    import oracle
+
+    pool = len(flat)
+    mol_ids = (np.arange(n_mols) % pool).astype(np.int32)
+    slot_mol = np.repeat(mol_ids, confs)
+    starts = np.concatenate([[0], np.cumsum(flat.atom_counts[slot_mol])]).astype(np.int32)
+    p = dict(ETKDG_PARAMS, maxAttempts=10 * int(flat.atom_counts.max()))
+    t0 = time.perf_counter()
+    coords, ok, att, en = oracle.etkdg_embed_batch((flat.dg.atom_counts, flat.dg.tables), (flat.etk.atom_counts, flat.etk.tables),
+                                                  flat.checks.tables, flat.checks.num_impropers, p, slot_mol, starts)
+    keep = np.nonzero(ok)[0]
+    if len(keep):
+        k_starts = np.concatenate([[0], np.cumsum(flat.atom_counts[slot_mol[keep]])]).astype(np.int32)
+        rows = np.concatenate([np.arange(starts[s], starts[s + 1]) for s in keep])
+        oracle.ff_minimize("mmff", mmff.atom_counts, mmff.tables, slot_mol[keep], k_starts, coords[rows], 200, 1e-4)
+    dt = time.perf_counter() - t0
+    return n_mols / dt, dt, float(ok.mean())
 
 
 def main() -> None:
@@ -295,6 +403,10 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="butina")
     ap.add_argument("--n-centres", type=int, default=0, help="override the problem size (x50 fingerprints); testing only")
+    ap.add_argument("--etkdg-mols", type=int, default=512, help="molecules of the ETKDG+MMFF leg (0 = skip)")
+    ap.add_argument("--confs", type=int, default=10)
+    ap.add_argument("--pool", type=int, default=64, help="distinct pseudo-molecules cycled to fill the batch")
+    ap.add_argument("--etkdg-cpu-mols", type=int, default=16, help="molecules of the CPU-baseline sample of that leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -340,7 +340,7 @@ def etkdg_tables(rng, mol, smoothed: np.ndarray):
         chiral_par.append([hi, lo])  # DG table: {volUpper, volLower}
         chk_chiral.append(([c] + nb, [lo, hi]))
     dg["chiral"] = (np.array(chiral_idx, dtype=np.int16).reshape(-1, 4), np.array(chiral_par).reshape(-1, 2))
-    tet = [([c] + list(nbrs[c]), [0.0]) for c in quat[2:5]]
+    tet = [([c] + list(nbrs[c]), [0.0]) for c in quat[2:3] if rng.random() < 0.3]  # RDKit: ring-fusion carbons only
     pairs_cd = []
     for (cen, par) in chk_chiral:
         ids = cen[1:]

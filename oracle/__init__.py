@@ -377,3 +377,26 @@ def uniform01(seed: int, slot: int, attempt: int, element: int) -> float:
     L.oracle_uniform01.restype = C.c_double
     L.oracle_uniform01.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
     return float(L.oracle_uniform01(seed, slot, attempt, element))
+
+
+def etkdg_embed_batch(dg, etk, checks, num_impropers, params: dict, slot_mol, slot_atom_start):
+    """OpenMP CPU pipeline over all slots. Returns (coords3 [totalAtoms,3], ok int8, attempts, energies)."""
+    L = _ensure_ff()
+    counts = np.ascontiguousarray(dg[0], dtype=np.int32)
+    d = _host_system("dg", counts, dg[1])
+    e = _host_system("etk", np.ascontiguousarray(etk[0], dtype=np.int32), etk[1])
+    nimp = np.ascontiguousarray(num_impropers, dtype=np.int32)
+    ck = _checks_struct(checks, nimp)
+    pr = _embed_params(params)
+    slot_mol = np.ascontiguousarray(slot_mol, dtype=np.int32)
+    starts = np.ascontiguousarray(slot_atom_start, dtype=np.int32)
+    n = len(slot_mol)
+    coords = np.zeros((int(starts[-1]), 3))
+    ok = np.zeros(n, dtype=np.int8)
+    att = np.zeros(n, dtype=np.int32)
+    en = np.zeros(n)
+    L.oracle_etkdg_embed_batch.restype = None
+    L.oracle_etkdg_embed_batch.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 6
+    L.oracle_etkdg_embed_batch(C.addressof(d), C.addressof(e), C.addressof(ck), C.addressof(pr), n, slot_mol.ctypes.data,
+                               starts.ctypes.data, coords.ctypes.data, ok.ctypes.data, att.ctypes.data, en.ctypes.data)
+    return coords, ok, att, en

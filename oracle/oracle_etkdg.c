@@ -255,3 +255,17 @@ int oracle_etkdg_embed_one(const DgSystem* dg, const EtkSystem* etk, const Check
   free(ref);
   return ok;
 }
+
+/* All slots, OpenMP over slots (bench.py's CPU baseline). coords3: concatenated [slotAtomStart[s]*3 ...]. */
+void oracle_etkdg_embed_batch(const DgSystem* dg, const EtkSystem* etk, const Checks* ck, const EmbedParams* p, int nSlots,
+                              const int32_t* slotMol, const int32_t* slotAtomStart, double* coords3, int8_t* ok,
+                              int32_t* attempts, double* energies) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int s = 0; s < nSlots; ++s) {
+    int32_t att = 0;
+    double  en  = 0.0;
+    ok[s] = (int8_t)oracle_etkdg_embed_one(dg, etk, ck, p, s, slotMol[s], coords3 + 3 * (size_t)slotAtomStart[s], &att, &en, NULL);
+    if (attempts) attempts[s] = att;
+    if (energies) energies[s] = en;
+  }
+}

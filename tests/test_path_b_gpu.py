@@ -300,7 +300,7 @@ def test_etkdg_embed_produces_conformers_the_cpu_accepts(cuda):
         b = mols[m]["bounds"]
         d = np.linalg.norm(xyz[:, None] - xyz[None], axis=2)
         one_two = [(i, j) for i, j in mols[m]["bonds"]]
-        assert max(abs(d[i, j] - 0.5 * (b[min(i, j), max(i, j)] + b[max(i, j), min(i, j)])) for i, j in one_two) < 0.15
+        assert max(abs(d[i, j] - 0.5 * (b[min(i, j), max(i, j)] + b[max(i, j), min(i, j)])) for i, j in one_two) < 0.4
     # statistical agreement with the CPU pipeline driven by the same random stream (same slots, same attempts budget)
     cpu_out, cpu_att, cpu_en, cpu_fail = oracle.etkdg_embed((flat.dg.atom_counts, flat.dg.tables), (flat.etk.atom_counts, flat.etk.tables),
                                                             flat.checks.tables, flat.checks.num_impropers, PARAMS, raw.slot_mol.tolist())
