@@ -307,6 +307,9 @@ ETKDG_PARAMS = dict(seed=20260924, boxSize=10.0, optimizerForceTol=1e-3, enforce
                     useBasicKnowledge=1, maxAttempts=0, dgIters=400, fourthIters=200, etkIters=300, maxRestarts=20)
 
 
+MAX_ATTEMPTS = 20  # embedding attempts per conformer slot in the bench (the API default is 10 x atoms, src/etkdg.cpp:71-85)
+
+
 def path_b_pool(pool: int, seed: int):
     """`pool` distinct pseudo drug-like molecules (20-50 heavy atoms, hydrogens added) with DG/ETK/check and MMFF tables."""
     from nvmolkit_b200 import synthetic
@@ -333,7 +336,7 @@ def run_path_b_gpu(flat, mmff, n_mols: int, confs: int, dev, steps: int, warmup:
     lo, hi = molecule_range(n_mols, rank, world)
     mol_ids = (np.arange(lo, hi) % pool).astype(np.int32)
     params = EmbedParameters(randomSeed=ETKDG_PARAMS["seed"])
-    max_attempts = 10 * int(flat.atom_counts.max())
+    max_attempts = MAX_ATTEMPTS
 
     def step():
         raw = embed_slots(flat, params, confs, max_attempts, mol_indices=mol_ids)
@@ -382,7 +385,7 @@ def run_path_b_cpu(flat, mmff, n_mols: int, confs: int):
     mol_ids = (np.arange(n_mols) % pool).astype(np.int32)
     slot_mol = np.repeat(mol_ids, confs)
     starts = np.concatenate([[0], np.cumsum(flat.atom_counts[slot_mol])]).astype(np.int32)
-    p = dict(ETKDG_PARAMS, maxAttempts=10 * int(flat.atom_counts.max()))
+    p = dict(ETKDG_PARAMS, maxAttempts=MAX_ATTEMPTS)
     t0 = time.perf_counter()
     coords, ok, att, en = oracle.etkdg_embed_batch((flat.dg.atom_counts, flat.dg.tables), (flat.etk.atom_counts, flat.etk.tables),
                                                   flat.checks.tables, flat.checks.num_impropers, p, slot_mol, starts)

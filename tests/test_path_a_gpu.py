@@ -125,9 +125,10 @@ def test_threshold_boundary_is_fp64_exact(cuda):
         rows.append((S.pack_bits(bits_a[None])[0], S.pack_bits(bits_b[None])[0]))
     x = np.stack([r[0] for r in rows])
     y = np.stack([r[1] for r in rows])
+    dx, dy = _dev(x, cuda), _dev(y, cuda)  # keep the device buffers alive across the asynchronous calls
     for cutoff in (0.3, 1.0 - 0.7, 0.30000000000000004, 0.29999999999999993, 1 / 3, 0.4):
         counts = torch.zeros(len(x), dtype=torch.int32, device=cuda)
-        _lib.call("b200mol_tanimoto_count_ge", _dev(x, cuda).data_ptr(), len(x), _dev(y, cuda).data_ptr(), len(y), 64,
+        _lib.call("b200mol_tanimoto_count_ge", dx.data_ptr(), len(x), dy.data_ptr(), len(y), 64,
                   0, cutoff, 1, counts.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert (counts.cpu().numpy() == oracle.count_ge(x, y, cutoff)).all(), cutoff
 
