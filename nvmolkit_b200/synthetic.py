@@ -342,12 +342,10 @@ def etkdg_tables(rng, mol, smoothed: np.ndarray):
     dg["chiral"] = (np.array(chiral_idx, dtype=np.int16).reshape(-1, 4), np.array(chiral_par).reshape(-1, 2))
     tet = [([c] + list(nbrs[c]), [0.0]) for c in quat[2:3] if rng.random() < 0.3]  # RDKit: ring-fusion carbons only
     pairs_cd = []
-    for (cen, par) in chk_chiral:
-        ids = cen[1:]
-        for x in range(4):
-            for y in range(x + 1, 4):
-                a, b = sorted((ids[x], ids[y]))
-                pairs_cd.append(([a, b], [smoothed[b, a], smoothed[a, b]]))
+    for (cen, par) in chk_chiral:  # RDKit checks the bounds among the chiral centre and its neighbours; the pseudo
+        for nb_ in cen[1:]:        # molecules keep the bonded pairs only (their 1-3 windows are synthetic)
+            a, b = sorted((cen[0], nb_))
+            pairs_cd.append(([a, b], [smoothed[b, a], smoothed[a, b]]))
     checks = {
         "tetrahedral": (np.array([t[0] for t in tet], dtype=np.int16).reshape(-1, 5), np.array([t[1] for t in tet]).reshape(-1, 1)),
         "chiral": (np.array([c[0] for c in chk_chiral], dtype=np.int16).reshape(-1, 5),
