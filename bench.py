@@ -315,7 +315,7 @@ def path_b_pool(pool: int, seed: int):
     from nvmolkit_b200 import synthetic
     from nvmolkit_b200.forcefield import FlatSystem
 
-    flat, mols = synthetic.random_embed_molecules(pool, 20, 50, seed=seed)
+    flat, mols = synthetic.random_embed_molecules(pool, 20, 50, seed=seed, strict_checks=False)
     mmff = FlatSystem.from_molecules("mmff", [len(m["z"]) for m in mols], [m["terms"] for m in mols])
     return flat, mmff
 

@@ -318,7 +318,7 @@ def bounds_matrix(mol) -> np.ndarray:
     return m
 
 
-def etkdg_tables(rng, mol, smoothed: np.ndarray):
+def etkdg_tables(rng, mol, smoothed: np.ndarray, strict_checks: bool = True):
     """DG / ETK / check term tables of one pseudo molecule from its SMOOTHED bounds matrix."""
     z, nbrs, topo = mol["z"], mol["nbrs"], mol["topo"]
     n = len(z)
@@ -393,13 +393,17 @@ def etkdg_tables(rng, mol, smoothed: np.ndarray):
         "angle13": (np.array(ang, dtype=np.int16).reshape(-1, 3), np.tile([115.0, 125.0], (len(ang), 1)).reshape(-1, 2)),
         "longrange": (np.stack([ilr, jlr], 1), np.stack([smoothed[jlr, ilr], smoothed[ilr, jlr], np.full(len(ilr), 10.0)], 1)),
     }
+    if not strict_checks:  # bench workloads: the synthetic 1-2 / stereo windows are not chemically consistent, so these
+        pairs_cd, db_stereo = [], []  # two checks would only burn attempts; tests keep them to exercise every kernel
+        checks["chiralDist"] = (np.zeros((0, 2), np.int16), np.zeros((0, 2)))
     checks["dbStereo"] = (np.array([d[0] for d in db_stereo], dtype=np.int16).reshape(-1, 4),
                           np.array([d[1] for d in db_stereo]).reshape(-1, 1))
     checks["dbGeom"] = (np.array(db_geom, dtype=np.int16).reshape(-1, 3), np.zeros((len(db_geom), 0)))
     return dg, etk, checks, len(planar)
 
 
-def random_embed_molecules(n_mols: int, min_heavy: int = 6, max_heavy: int = 25, seed: int = SEED):
+def random_embed_molecules(n_mols: int, min_heavy: int = 6, max_heavy: int = 25, seed: int = SEED,
+                           strict_checks: bool = True):
     """Pseudo molecules with everything ETKDG needs. Returns (FlatEmbedMolecules, raw molecule dicts)."""
     from nvmolkit_b200.embedMolecules import FlatEmbedMolecules
     from nvmolkit_b200.forcefield import CheckTables, FlatSystem
@@ -423,7 +427,7 @@ def random_embed_molecules(n_mols: int, min_heavy: int = 6, max_heavy: int = 25,
         sm[iu] = ub[iu]
         sm.T[iu] = lb[iu]
         m["bounds_raw"], m["bounds"] = b, sm
-        dg, etk, chk, np_ = etkdg_tables(rng, m, sm)
+        dg, etk, chk, np_ = etkdg_tables(rng, m, sm, strict_checks)
         mols.append(m)
         dgs.append(dg)
         etks.append(etk)
