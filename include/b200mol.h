@@ -166,12 +166,24 @@ typedef struct b200mol_etk_system {
   b200mol_term_table torsion, improper, dist12, dist13, angle13, longrange;
 } b200mol_etk_system;
 
+/* UFF (src/forcefields/uff_kernels_device.cuh:37-590; layout source src/forcefields/uff.h:33-97)
+ *   bond K2 P2 {restLen, k}    angle K3 P6 {theta0 (rad), k, order, C0, C1, C2}    torsion K4 P3 {k, order, cosTerm}
+ *   inversion K4 P4 {k, C0, C1, C2} (idx[1] = centre)    vdw K2 P3 {x_ij, wellDepth, threshold} */
+typedef struct b200mol_uff_system {
+  int32_t            nMols;
+  const int32_t*     atomCounts;
+  b200mol_term_table bond, angle, torsion, inversion, vdw;
+} b200mol_uff_system;
+
 /* Energies (d_energy[nConf]) and, when d_grad != NULL, gradients (d_grad[totalAtoms*dim], overwritten) of a
  * conformer batch. Replaces launch*EnergyKernel / launch*GradientKernel + combinedEnergies/GradKernel
  * (src/forcefields/mmff_kernels.h, mmff_kernels.cu:1067-1125; dist_geom_kernels.cu). */
 int b200mol_mmff_energy_grad(const b200mol_mmff_system* sys, int32_t nConf, const int32_t* d_conf_mol,
                              const int32_t* d_conf_atom_start, const double* d_pos, double* d_energy, double* d_grad,
                              void* stream);
+int b200mol_uff_energy_grad(const b200mol_uff_system* sys, int32_t nConf, const int32_t* d_conf_mol,
+                            const int32_t* d_conf_atom_start, const double* d_pos, double* d_energy, double* d_grad,
+                            void* stream);
 int b200mol_dg_energy_grad(const b200mol_dg_system* sys, int dim, double chiralWeight, double fourthDimWeight,
                            int32_t nConf, const int32_t* d_conf_mol, const int32_t* d_conf_atom_start,
                            const double* d_pos, double* d_energy, double* d_grad, void* stream);
@@ -193,6 +205,11 @@ int b200mol_mmff_minimize(const b200mol_mmff_system* sys, int32_t nConf, const i
                           const int32_t* d_conf_atom_start, int max_atoms, double* d_pos, int max_iters,
                           double grad_tol, const uint8_t* d_active, double* d_energy, int8_t* d_status,
                           int32_t* d_iters, void* stream);
+/* UFF twin (reference: UFFMinimizeMoleculesConfs, src/minimizer/bfgs_uff.cpp; Python default maxIters 1000). */
+int b200mol_uff_minimize(const b200mol_uff_system* sys, int32_t nConf, const int32_t* d_conf_mol,
+                         const int32_t* d_conf_atom_start, int max_atoms, double* d_pos, int max_iters,
+                         double grad_tol, const uint8_t* d_active, double* d_energy, int8_t* d_status,
+                         int32_t* d_iters, void* stream);
 int b200mol_dg_minimize(const b200mol_dg_system* sys, int dim, double chiralWeight, double fourthDimWeight,
                         int32_t nConf, const int32_t* d_conf_mol, const int32_t* d_conf_atom_start, int max_atoms,
                         double* d_pos, int max_iters, double grad_tol, const uint8_t* d_active, double* d_energy,

@@ -37,6 +37,9 @@ SIGNATURES = {
     "b200mol_butina_from_edges": (C.c_int, [C.c_size_t, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "b200mol_butina_dense": (C.c_int, [_vp, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "b200mol_mmff_energy_grad": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_uff_energy_grad": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_uff_minimize": (C.c_int, [_vp, C.c_int32, _vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp,
+                                       _vp]),
     "b200mol_dg_energy_grad": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mol_etk_energy_grad": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mol_mmff_minimize": (C.c_int, [_vp, C.c_int32, _vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp,

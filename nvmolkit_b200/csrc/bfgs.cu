@@ -190,6 +190,26 @@ extern "C" int b200mol_mmff_energy_grad(const b200mol_mmff_system* sys, int32_t 
     runEnergyGrad<ff::Mmff>(*sys, {}, nConf, d_conf_mol, d_conf_atom_start, maxAtoms, d_pos, d_energy, d_grad, asStream(stream));
   });
 }
+extern "C" int b200mol_uff_energy_grad(const b200mol_uff_system* sys, int32_t nConf, const int32_t* d_conf_mol,
+                                       const int32_t* d_conf_atom_start, const double* d_pos, double* d_energy,
+                                       double* d_grad, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(sys, "null system");
+    if (nConf <= 0) return;
+    const int maxAtoms = maxSpan(d_conf_atom_start, nConf, asStream(stream));
+    runEnergyGrad<ff::Uff>(*sys, {}, nConf, d_conf_mol, d_conf_atom_start, maxAtoms, d_pos, d_energy, d_grad, asStream(stream));
+  });
+}
+extern "C" int b200mol_uff_minimize(const b200mol_uff_system* sys, int32_t nConf, const int32_t* d_conf_mol,
+                                    const int32_t* d_conf_atom_start, int max_atoms, double* d_pos, int max_iters,
+                                    double grad_tol, const uint8_t* d_active, double* d_energy, int8_t* d_status,
+                                    int32_t* d_iters, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(sys, "null system");
+    runMinimize<ff::Uff>(*sys, {}, nConf, d_conf_mol, d_conf_atom_start, max_atoms, d_pos, max_iters, grad_tol, 1, d_active,
+                         d_energy, d_status, d_iters, asStream(stream));
+  });
+}
 extern "C" int b200mol_dg_energy_grad(const b200mol_dg_system* sys, int dim, double chiralWeight, double fourthDimWeight,
                                       int32_t nConf, const int32_t* d_conf_mol, const int32_t* d_conf_atom_start,
                                       const double* d_pos, double* d_energy, double* d_grad, void* stream) {

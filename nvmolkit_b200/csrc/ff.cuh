@@ -497,6 +497,193 @@ struct Etk {
   }
 };
 
+// ============================================================================================ UFF
+// Term math: src/forcefields/uff_kernels_device.cuh:37-590 (RDKit ForceFields::UFF contribs).
+struct Uff {
+  static constexpr int  kDim    = 3;
+  static constexpr bool kHasRef = false;
+  using System                  = b200mol_uff_system;
+  struct Params {};
+  struct View {
+    const System* s;
+    Range         bond, angle, torsion, inversion, vdw;
+  };
+  __device__ static View view(const System& s, int mol, const Params&) {
+    return {&s, range(s.bond, mol), range(s.angle, mol), range(s.torsion, mol), range(s.inversion, mol), range(s.vdw, mol)};
+  }
+  template <bool GRAD>
+  __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
+    const System& s = *v.s;
+    double        e = 0.0;
+    for (int t = v.bond.beg + tid; t < v.bond.end; t += nT) {
+      const int    i = s.bond.idx[2 * t], j = s.bond.idx[2 * t + 1];
+      const double r0 = s.bond.par[2 * t], k = s.bond.par[2 * t + 1];
+      const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
+      const double dist = sqrt(dot(d, d));
+      if (!GRAD) {
+        e += 0.5 * k * (dist - r0) * (dist - r0);
+      } else {
+        const V3 g = dist > 0.0 ? d * (k * (dist - r0) / dist) : V3{k * 0.01, k * 0.01, k * 0.01};
+        acc<3>(grad, i, g);
+        acc<3>(grad, j, -g);
+      }
+    }
+    for (int t = v.angle.beg + tid; t < v.angle.end; t += nT) {
+      const int     i = s.angle.idx[3 * t], j = s.angle.idx[3 * t + 1], k = s.angle.idx[3 * t + 2];
+      const double* q = s.angle.par + 6 * t;  // theta0, k, order, C0, C1, C2
+      const int     order = static_cast<int>(q[2]);
+      const V3      d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
+      const double  l1sq = dot(d1, d1), l2sq = dot(d2, d2);
+      if (l1sq <= 0.0 || l2sq <= 0.0) continue;
+      const double l1 = sqrt(l1sq), l2 = sqrt(l2sq);
+      const double c  = clampd(dot(d1, d2) / (l1 * l2), -1.0, 1.0);
+      const double sSq = 1.0 - c * c;
+      const bool   corr = order > 0 && order < 5 && c > 0.8660;
+      if (!GRAD) {
+        const double c2t = c * c - sSq;
+        double       term;
+        if (order == 0) {
+          term = q[3] + q[4] * c + q[5] * c2t;
+        } else {
+          double r = 0.0;
+          if (order == 1) r = -c;
+          else if (order == 2) r = c2t;
+          else if (order == 3) r = c * (c * c - 3.0 * sSq);
+          else if (order == 4) r = c * c * c * c - 6.0 * c * c * sSq + sSq * sSq;
+          term = (1.0 - r) / static_cast<double>(order * order);
+        }
+        double en = q[1] * term;
+        if (corr) en += exp(-20.0 * (acos(c) - q[0] + 0.25));
+        e += en;
+      } else {
+        if (isZero(sSq)) continue;
+        const double sn = fmax(sqrt(sSq), 1.0e-8), s2t = 2.0 * sn * c;
+        double       dE;
+        if (order == 0) {
+          dE = -q[1] * (q[4] * sn + 2.0 * q[5] * s2t);
+        } else {
+          double r = 0.0;
+          if (order == 1) r = -sn;
+          else if (order == 2) r = s2t;
+          else if (order == 3) r = sn * (3.0 - 4.0 * sn * sn);
+          else if (order == 4) r = c * sn * (4.0 - 8.0 * sn * sn);
+          dE = (order >= 1 && order <= 4) ? r * q[1] / static_cast<double>(order) : 0.0;
+        }
+        if (corr) dE += -20.0 * exp(-20.0 * (acos(c) - q[0] + 0.25));
+        const double cf = dE / (-sn);
+        const V3     n1 = d1 * (1.0 / l1), n2 = d2 * (1.0 / l2);
+        const V3     a = (n2 - n1 * c) * (cf / l1), b = (n1 - n2 * c) * (cf / l2);
+        acc<3>(grad, i, a);
+        acc<3>(grad, j, -(a + b));
+        acc<3>(grad, k, b);
+      }
+    }
+    for (int t = v.torsion.beg + tid; t < v.torsion.end; t += nT) {
+      const int16_t* ix = s.torsion.idx + 4 * t;
+      const double   fk = s.torsion.par[3 * t], cosTerm = s.torsion.par[3 * t + 2];
+      const int      order = static_cast<int>(s.torsion.par[3 * t + 1]);
+      const V3       r0 = ld<3>(pos, ix[0]) - ld<3>(pos, ix[1]), r1 = ld<3>(pos, ix[2]) - ld<3>(pos, ix[1]), r2 = -r1,
+               r3 = ld<3>(pos, ix[3]) - ld<3>(pos, ix[2]);
+      V3           t0 = cross(r0, r1), t1 = cross(r2, r3);
+      const double d0 = sqrt(dot(t0, t0)), d1 = sqrt(dot(t1, t1));
+      if (!GRAD) {
+        const double c = (isZero(d0) || isZero(d1)) ? 0.0 : clampd(dot(t0, t1) / (d0 * d1), -1.0, 1.0);
+        const double sSq = 1.0 - c * c;
+        double       cn;
+        if (order == 2) cn = 1.0 - 2.0 * sSq;
+        else if (order == 3) cn = c * (c * c - 3.0 * sSq);
+        else if (order == 6) cn = 1.0 + sSq * (-32.0 * sSq * sSq + 48.0 * sSq - 18.0);
+        else continue;
+        e += fk / 2.0 * (1.0 - cosTerm * cn);
+      } else {
+        if (isZero(d0) || isZero(d1)) continue;
+        t0 = t0 * (1.0 / d0);
+        t1 = t1 * (1.0 / d1);
+        const double c = clampd(dot(t0, t1), -1.0, 1.0), sSq = 1.0 - c * c, sn = sSq > 0.0 ? sqrt(sSq) : 0.0;
+        double       r;
+        if (order == 2) r = 2.0 * sn * c;
+        else if (order == 3) r = sn * (3.0 - 4.0 * sSq);
+        else if (order == 6) r = c * sn * (32.0 * sSq * (sSq - 1.0) + 6.0);
+        else continue;
+        const double dE = r * fk / 2.0 * cosTerm * -1.0 * static_cast<double>(order);
+        const double sinTerm = dE * (isZero(sn) ? (1.0 / fmax(fabs(c), 1.0e-8)) : (1.0 / sn));
+        const V3     a = (t1 - t0 * c) * (1.0 / d0), b = (t0 - t1 * c) * (1.0 / d1);
+        acc<3>(grad, ix[0], V3{a.z * r1.y - a.y * r1.z, a.x * r1.z - a.z * r1.x, a.y * r1.x - a.x * r1.y} * sinTerm);
+        acc<3>(grad, ix[1],
+               V3{a.y * (r1.z - r0.z) + a.z * (r0.y - r1.y) + b.y * (-r3.z) + b.z * (r3.y),
+                  a.x * (r0.z - r1.z) + a.z * (r1.x - r0.x) + b.x * (r3.z) + b.z * (-r3.x),
+                  a.x * (r1.y - r0.y) + a.y * (r0.x - r1.x) + b.x * (-r3.y) + b.y * (r3.x)} * sinTerm);
+        acc<3>(grad, ix[2],
+               V3{a.y * r0.z + a.z * (-r0.y) + b.y * (r3.z - r2.z) + b.z * (r2.y - r3.y),
+                  a.x * (-r0.z) + a.z * r0.x + b.x * (r2.z - r3.z) + b.z * (r3.x - r2.x),
+                  a.x * r0.y + a.y * (-r0.x) + b.x * (r3.y - r2.y) + b.y * (r2.x - r3.x)} * sinTerm);
+        acc<3>(grad, ix[3], V3{b.y * r2.z - b.z * r2.y, b.z * r2.x - b.x * r2.z, b.x * r2.y - b.y * r2.x} * sinTerm);
+      }
+    }
+    for (int t = v.inversion.beg + tid; t < v.inversion.end; t += nT) {
+      const int16_t* ix = s.inversion.idx + 4 * t;
+      const double   fk = s.inversion.par[4 * t], C0 = s.inversion.par[4 * t + 1], C1 = s.inversion.par[4 * t + 2],
+                   C2 = s.inversion.par[4 * t + 3];
+      const V3     ji = ld<3>(pos, ix[0]) - ld<3>(pos, ix[1]), jk = ld<3>(pos, ix[2]) - ld<3>(pos, ix[1]),
+               jl = ld<3>(pos, ix[3]) - ld<3>(pos, ix[1]);
+      const double l2i = dot(ji, ji), l2k = dot(jk, jk), l2l = dot(jl, jl);
+      if (!GRAD) {
+        double cosY = 0.0;
+        if (!(l2i < 1.0e-16 || l2k < 1.0e-16 || l2l < 1.0e-16)) {
+          const V3     n   = cross(ji, jk) * (1.0 / (sqrt(l2i) * sqrt(l2k)));
+          const double l2n = dot(n, n);
+          if (!(l2n < 1.0e-16)) cosY = dot(n, jl) / (sqrt(l2l) * sqrt(l2n));
+        }
+        const double sSq = 1.0 - cosY * cosY, sinY = sSq > 0.0 ? sqrt(sSq) : 0.0;
+        e += fk * (C0 + C1 * sinY + C2 * (2.0 * sinY * sinY - 1.0));
+      } else {
+        const double dI = sqrt(l2i), dK = sqrt(l2k), dL = sqrt(l2l);
+        if (isZero(dI) || isZero(dK) || isZero(dL)) continue;
+        const V3 a = ji * (1.0 / dI), b = jk * (1.0 / dK), c = jl * (1.0 / dL);
+        V3       n = cross(-a, b);
+        const double nn = sqrt(dot(n, n));
+        if (nn <= 0.0) continue;
+        n = n * (1.0 / nn);
+        const double cY = clampd(dot(n, c), -1.0, 1.0), sY = fmax(sqrt(1.0 - cY * cY), 1.0e-8);
+        const double cT = clampd(dot(a, b), -1.0, 1.0), sTsq = 1.0 - cT * cT, sT = fmax(sqrt(sTsq), 1.0e-8);
+        const double dE = -fk * (C1 * cY - 4.0 * C2 * cY * sY);
+        const V3     t1 = cross(c, b), t2 = cross(a, c), t3 = cross(b, a);
+        const double term1 = sY * sT, term2 = cY / (sY * sTsq);
+        const V3     g1 = (t1 * (1.0 / term1) - (a - b * cT) * term2) * (1.0 / dI);
+        const V3     g3 = (t2 * (1.0 / term1) - (b - a * cT) * term2) * (1.0 / dK);
+        const V3     g4 = (t3 * (1.0 / term1) - c * (cY / sY)) * (1.0 / dL);
+        acc<3>(grad, ix[0], g1 * dE);
+        acc<3>(grad, ix[1], (g1 + g3 + g4) * (-dE));
+        acc<3>(grad, ix[2], g3 * dE);
+        acc<3>(grad, ix[3], g4 * dE);
+      }
+    }
+    for (int t = v.vdw.beg + tid; t < v.vdw.end; t += nT) {
+      const int    i = s.vdw.idx[2 * t], j = s.vdw.idx[2 * t + 1];
+      const double x = s.vdw.par[3 * t], eps = s.vdw.par[3 * t + 1], thr = s.vdw.par[3 * t + 2];
+      const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
+      const double dist = sqrt(dot(d, d));
+      if (dist > thr) continue;
+      if (!GRAD) {
+        if (dist <= 0.0) continue;
+        const double r = x / dist, r2 = r * r, r6 = r2 * r2 * r2;
+        e += eps * (r6 * r6 - 2.0 * r6);
+      } else {
+        V3 g;
+        if (dist <= 0.0) {
+          g = V3{100.0, 100.0, 100.0};
+        } else {
+          const double r = x / dist, r2 = r * r, r7 = r * r2 * r2 * r2, r13 = r7 * r2 * r2 * r2;
+          g = d * (12.0 * eps / x * (r7 - r13) / dist);
+        }
+        acc<3>(grad, i, g);
+        acc<3>(grad, j, -g);
+      }
+    }
+    return e;
+  }
+};
+
 // ============================================================================================ analytic test potential
 struct Poly {
   static constexpr int  kDim    = 1;

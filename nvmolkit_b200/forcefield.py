@@ -18,11 +18,12 @@ import numpy as np
 LAYOUT: Dict[str, Tuple[Tuple[str, int, int], ...]] = {
     "mmff": (("bond", 2, 2), ("angle", 3, 3), ("strbend", 3, 5), ("oop", 4, 1), ("torsion", 4, 3), ("vdw", 2, 2),
              ("ele", 2, 3)),
+    "uff": (("bond", 2, 2), ("angle", 3, 6), ("torsion", 4, 3), ("inversion", 4, 4), ("vdw", 2, 3)),
     "dg": (("dist", 2, 3), ("chiral", 4, 2), ("fourth", 1, 0)),
     "etk": (("torsion", 4, 12), ("improper", 4, 4), ("dist12", 2, 4), ("dist13", 2, 4), ("angle13", 3, 2),
             ("longrange", 2, 3)),
 }
-DIM = {"mmff": 3, "dg": 4, "etk": 4}
+DIM = {"mmff": 3, "uff": 3, "dg": 4, "etk": 4}
 CHECK_LAYOUT = (("tetrahedral", 5, 1), ("chiral", 5, 2), ("chiralDist", 2, 2), ("dbStereo", 4, 1), ("dbGeom", 3, 0))
 
 

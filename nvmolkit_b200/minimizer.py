@@ -55,6 +55,8 @@ def minimize(system: FlatSystem, batch: ConformerBatch, max_iters: int = 200, gr
                   float(grad_tol), act, energies.data_ptr(), status.data_ptr(), iters.data_ptr(), sptr)
         if kind == "mmff":
             _lib.call("b200mol_mmff_minimize", C.byref(st), *common)
+        elif kind == "uff":
+            _lib.call("b200mol_uff_minimize", C.byref(st), *common)
         elif kind == "dg":
             _lib.call("b200mol_dg_minimize", C.byref(st), int(dim), float(chiral_weight), float(fourth_dim_weight), *common)
         elif kind == "etk":
@@ -80,8 +82,8 @@ def energy_and_grad(system: FlatSystem, batch: ConformerBatch, want_grad: bool =
         energies = torch.empty(n, dtype=torch.float64, device=dev)
         grad = torch.zeros_like(pos) if want_grad else None
         gptr = grad.data_ptr() if want_grad else None
-        if kind == "mmff":
-            _lib.call("b200mol_mmff_energy_grad", C.byref(st), n, conf_mol.data_ptr(), starts.data_ptr(), pos.data_ptr(),
+        if kind in ("mmff", "uff"):
+            _lib.call(f"b200mol_{kind}_energy_grad", C.byref(st), n, conf_mol.data_ptr(), starts.data_ptr(), pos.data_ptr(),
                       energies.data_ptr(), gptr, sptr)
         elif kind == "dg":
             _lib.call("b200mol_dg_energy_grad", C.byref(st), int(dim), float(chiral_weight), float(fourth_dim_weight), n,

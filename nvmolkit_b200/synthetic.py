@@ -437,3 +437,35 @@ def random_embed_molecules(n_mols: int, min_heavy: int = 6, max_heavy: int = 25,
     flat = FlatEmbedMolecules(FlatSystem.from_molecules("dg", counts, dgs), FlatSystem.from_molecules("etk", counts, etks),
                               CheckTables.from_molecules(counts, chks, nimp))
     return flat, mols
+
+
+def random_uff_system(n_mols: int, min_heavy: int = 10, max_heavy: int = 50, seed: int = SEED):
+    """UFF-shaped term tables for the same pseudo molecules (every angle order 0..4 and torsion order 2/3/6 occurs)."""
+    from nvmolkit_b200.forcefield import FlatSystem
+
+    rng = np.random.default_rng(seed)
+    mols = [random_mmff_molecule(rng, int(rng.integers(min_heavy, max_heavy + 1))) for _ in range(n_mols)]
+    tabs = []
+    for m in mols:
+        t = m["terms"]
+        b_idx, b_par = t["bond"]
+        ang = t["angle"][0]
+        theta0 = np.deg2rad(t["angle"][1][:, 0])
+        order = rng.choice([0, 0, 0, 1, 2, 3, 4], size=len(ang)).astype(np.float64)
+        ka = rng.uniform(50, 150, len(ang))
+        c2 = 1.0 / (4.0 * np.maximum(np.sin(theta0) ** 2, 1e-3))
+        c1 = -4.0 * c2 * np.cos(theta0)
+        c0 = c2 * (2.0 * np.cos(theta0) ** 2 + 1.0)
+        tor = t["torsion"][0]
+        t_order = rng.choice([2.0, 3.0, 3.0, 6.0], size=len(tor))
+        inv = t["oop"][0]
+        pairs = t["vdw"][0]
+        tabs.append({
+            "bond": (b_idx, np.stack([b_par[:, 0], rng.uniform(500, 900, len(b_idx))], 1)),
+            "angle": (ang, np.stack([theta0, ka, order, c0, c1, c2], 1)),
+            "torsion": (tor, np.stack([rng.uniform(0.2, 2.5, len(tor)), t_order, rng.choice([-1.0, 1.0], len(tor))], 1)),
+            "inversion": (inv, np.tile([6.0 / 3.0, 1.0, -1.0, 0.0], (len(inv), 1))),
+            "vdw": (pairs, np.stack([t["vdw"][1][:, 0], t["vdw"][1][:, 1], np.full(len(pairs), 10.0)], 1)),
+        })
+    system = FlatSystem.from_molecules("uff", [len(m["z"]) for m in mols], tabs)
+    return system, [m["xyz"] for m in mols], mols

@@ -151,6 +151,7 @@ class _TermTableC(C.Structure):
 
 _FF_LAYOUT = {
     "mmff": ("bond", "angle", "strbend", "oop", "torsion", "vdw", "ele"),
+    "uff": ("bond", "angle", "torsion", "inversion", "vdw"),
     "dg": ("dist", "chiral", "fourth"),
     "etk": ("torsion", "improper", "dist12", "dist13", "angle13", "longrange"),
 }
@@ -179,6 +180,10 @@ def _declare_ff(L):
     vp, f64p, i32p, i8p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int8)
     L.oracle_mmff_energy_grad.argtypes = [vp, C.c_int, f64p, f64p, f64p]
     L.oracle_mmff_energy_grad.restype = C.c_double
+    L.oracle_uff_energy_grad.argtypes = [vp, C.c_int, f64p, f64p]
+    L.oracle_uff_energy_grad.restype = C.c_double
+    L.oracle_uff_minimize.argtypes = [vp, C.c_int, i32p, i32p, f64p, C.c_int, C.c_double, f64p, i8p, i32p]
+    L.oracle_uff_minimize.restype = None
     L.oracle_dg_energy_grad.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, f64p, f64p]
     L.oracle_dg_energy_grad.restype = C.c_double
     L.oracle_etk_energy_grad.argtypes = [vp, C.c_int, f64p, f64p, C.c_int]
@@ -222,6 +227,8 @@ def ff_energy_grad(kind: str, atom_counts, tables, mol: int, pos, want_grad=True
         per = np.zeros(7)
         e = L.oracle_mmff_energy_grad(C.addressof(st), mol, _p(pos, C.c_double), gp, _p(per, C.c_double))
         return e, grad, per
+    if kind == "uff":
+        return L.oracle_uff_energy_grad(C.addressof(st), mol, _p(pos, C.c_double), gp), grad, None
     if kind == "dg":
         e = L.oracle_dg_energy_grad(C.addressof(st), mol, dim or 4, chiral_weight, fourth_dim_weight, _p(pos, C.c_double), gp)
         return e, grad, None
@@ -250,6 +257,8 @@ def ff_minimize(kind: str, atom_counts, tables, conf_mol, conf_atom_start, posit
          _p(e, C.c_double), _p(conv, C.c_int8), _p(iters, C.c_int32))
     if kind == "mmff":
         L.oracle_mmff_minimize(C.addressof(st), *a)
+    elif kind == "uff":
+        L.oracle_uff_minimize(C.addressof(st), *a)
     elif kind == "dg":
         L.oracle_dg_minimize(C.addressof(st), dim or 4, chiral_weight, fourth_dim_weight, *a)
     else:

@@ -858,3 +858,235 @@ int oracle_etk_minimize_one(const EtkSystem* s, int mol, int plain, const double
   EtkCtx ctx = {s, mol, plain, ref};
   return bfgs_minimize(4 * s->atomCounts[mol], pos, etk_fn, &ctx, maxIters, gradTol, 1, energy, NULL);
 }
+
+/* =========================================================================================== UFF
+ * src/forcefields/uff_kernels_device.cuh:37-590 (RDKit ForceFields::UFF contribs), fp64. */
+typedef struct {
+  int32_t        nMols;
+  const int32_t* atomCounts;
+  TermTable      bond, angle, torsion, inversion, vdw;
+} UffSystem;
+
+double oracle_uff_energy_grad(const UffSystem* s, int mol, const double* p, double* g) {
+  double e = 0.0;
+  for (int t = s->bond.starts[mol]; t < s->bond.starts[mol + 1]; ++t) {
+    const int    i = s->bond.idx[2 * t], j = s->bond.idx[2 * t + 1];
+    const double r0 = s->bond.par[2 * t], k = s->bond.par[2 * t + 1];
+    double       d[3] = {p[3 * i] - p[3 * j], p[3 * i + 1] - p[3 * j + 1], p[3 * i + 2] - p[3 * j + 2]};
+    const double dist = sqrt(dot3(d, d));
+    e += 0.5 * k * (dist - r0) * (dist - r0);
+    if (g)
+      for (int c = 0; c < 3; ++c) {
+        const double v = dist > 0.0 ? k * (dist - r0) * d[c] / dist : k * 0.01;
+        g[3 * i + c] += v;
+        g[3 * j + c] -= v;
+      }
+  }
+  for (int t = s->angle.starts[mol]; t < s->angle.starts[mol + 1]; ++t) {
+    const int     i = s->angle.idx[3 * t], j = s->angle.idx[3 * t + 1], k = s->angle.idx[3 * t + 2];
+    const double* q = s->angle.par + 6 * t;
+    const int     order = (int)q[2];
+    double        d1[3], d2[3];
+    for (int c = 0; c < 3; ++c) {
+      d1[c] = p[3 * i + c] - p[3 * j + c];
+      d2[c] = p[3 * k + c] - p[3 * j + c];
+    }
+    const double l1sq = dot3(d1, d1), l2sq = dot3(d2, d2);
+    if (l1sq <= 0.0 || l2sq <= 0.0) continue;
+    const double l1 = sqrt(l1sq), l2 = sqrt(l2sq);
+    const double c = clampd(dot3(d1, d2) / (l1 * l2), -1.0, 1.0), sSq = 1.0 - c * c, c2t = c * c - sSq;
+    const int    corr = order > 0 && order < 5 && c > 0.8660;
+    double       term;
+    if (order == 0) {
+      term = q[3] + q[4] * c + q[5] * c2t;
+    } else {
+      double r = 0.0;
+      if (order == 1) r = -c;
+      else if (order == 2) r = c2t;
+      else if (order == 3) r = c * (c * c - 3.0 * sSq);
+      else if (order == 4) r = c * c * c * c - 6.0 * c * c * sSq + sSq * sSq;
+      term = (1.0 - r) / (double)(order * order);
+    }
+    e += q[1] * term;
+    if (corr) e += exp(-20.0 * (acos(c) - q[0] + 0.25));
+    if (g && !is_zero(sSq)) {
+      const double sn = fmax(sqrt(sSq), 1.0e-8), s2t = 2.0 * sn * c;
+      double       dE;
+      if (order == 0) {
+        dE = -q[1] * (q[4] * sn + 2.0 * q[5] * s2t);
+      } else {
+        double r = 0.0;
+        if (order == 1) r = -sn;
+        else if (order == 2) r = s2t;
+        else if (order == 3) r = sn * (3.0 - 4.0 * sn * sn);
+        else if (order == 4) r = c * sn * (4.0 - 8.0 * sn * sn);
+        dE = (order >= 1 && order <= 4) ? r * q[1] / (double)order : 0.0;
+      }
+      if (corr) dE += -20.0 * exp(-20.0 * (acos(c) - q[0] + 0.25));
+      const double cf = dE / (-sn);
+      for (int x = 0; x < 3; ++x) {
+        const double n1 = d1[x] / l1, n2 = d2[x] / l2;
+        const double a = (n2 - c * n1) / l1, b = (n1 - c * n2) / l2;
+        g[3 * i + x] += cf * a;
+        g[3 * j + x] += cf * (-a - b);
+        g[3 * k + x] += cf * b;
+      }
+    }
+  }
+  for (int t = s->torsion.starts[mol]; t < s->torsion.starts[mol + 1]; ++t) {
+    const int16_t* ix = s->torsion.idx + 4 * t;
+    const double   fk = s->torsion.par[3 * t], cosTerm = s->torsion.par[3 * t + 2];
+    const int      order = (int)s->torsion.par[3 * t + 1];
+    double         r0[3], r1[3], r2[3], r3[3], t0[3], t1[3];
+    for (int c = 0; c < 3; ++c) {
+      r0[c] = p[3 * ix[0] + c] - p[3 * ix[1] + c];
+      r1[c] = p[3 * ix[2] + c] - p[3 * ix[1] + c];
+      r2[c] = -r1[c];
+      r3[c] = p[3 * ix[3] + c] - p[3 * ix[2] + c];
+    }
+    cross(r0, r1, t0);
+    cross(r2, r3, t1);
+    const double d0 = sqrt(dot3(t0, t0)), d1 = sqrt(dot3(t1, t1));
+    if (order != 2 && order != 3 && order != 6) continue;
+    {
+      const double c = (is_zero(d0) || is_zero(d1)) ? 0.0 : clampd(dot3(t0, t1) / (d0 * d1), -1.0, 1.0);
+      const double sSq = 1.0 - c * c;
+      double       cn;
+      if (order == 2) cn = 1.0 - 2.0 * sSq;
+      else if (order == 3) cn = c * (c * c - 3.0 * sSq);
+      else cn = 1.0 + sSq * (-32.0 * sSq * sSq + 48.0 * sSq - 18.0);
+      e += fk / 2.0 * (1.0 - cosTerm * cn);
+    }
+    if (g && !(is_zero(d0) || is_zero(d1))) {
+      for (int c = 0; c < 3; ++c) {
+        t0[c] /= d0;
+        t1[c] /= d1;
+      }
+      const double c = clampd(dot3(t0, t1), -1.0, 1.0), sSq = 1.0 - c * c, sn = sSq > 0.0 ? sqrt(sSq) : 0.0;
+      double       r;
+      if (order == 2) r = 2.0 * sn * c;
+      else if (order == 3) r = sn * (3.0 - 4.0 * sSq);
+      else r = c * sn * (32.0 * sSq * (sSq - 1.0) + 6.0);
+      const double dE = r * fk / 2.0 * cosTerm * -1.0 * (double)order;
+      const double sinTerm = dE * (is_zero(sn) ? (1.0 / fmax(fabs(c), 1.0e-8)) : (1.0 / sn));
+      double       a[3], b[3];
+      for (int x = 0; x < 3; ++x) {
+        a[x] = (t1[x] - c * t0[x]) / d0;
+        b[x] = (t0[x] - c * t1[x]) / d1;
+      }
+      double *g1 = g + 3 * ix[0], *g2 = g + 3 * ix[1], *g3 = g + 3 * ix[2], *g4 = g + 3 * ix[3];
+      g1[0] += sinTerm * (a[2] * r1[1] - a[1] * r1[2]);
+      g1[1] += sinTerm * (a[0] * r1[2] - a[2] * r1[0]);
+      g1[2] += sinTerm * (a[1] * r1[0] - a[0] * r1[1]);
+      g2[0] += sinTerm * (a[1] * (r1[2] - r0[2]) + a[2] * (r0[1] - r1[1]) + b[1] * (-r3[2]) + b[2] * (r3[1]));
+      g2[1] += sinTerm * (a[0] * (r0[2] - r1[2]) + a[2] * (r1[0] - r0[0]) + b[0] * (r3[2]) + b[2] * (-r3[0]));
+      g2[2] += sinTerm * (a[0] * (r1[1] - r0[1]) + a[1] * (r0[0] - r1[0]) + b[0] * (-r3[1]) + b[1] * (r3[0]));
+      g3[0] += sinTerm * (a[1] * r0[2] + a[2] * (-r0[1]) + b[1] * (r3[2] - r2[2]) + b[2] * (r2[1] - r3[1]));
+      g3[1] += sinTerm * (a[0] * (-r0[2]) + a[2] * r0[0] + b[0] * (r2[2] - r3[2]) + b[2] * (r3[0] - r2[0]));
+      g3[2] += sinTerm * (a[0] * r0[1] + a[1] * (-r0[0]) + b[0] * (r3[1] - r2[1]) + b[1] * (r2[0] - r3[0]));
+      g4[0] += sinTerm * (b[1] * r2[2] - b[2] * r2[1]);
+      g4[1] += sinTerm * (b[2] * r2[0] - b[0] * r2[2]);
+      g4[2] += sinTerm * (b[0] * r2[1] - b[1] * r2[0]);
+    }
+  }
+  for (int t = s->inversion.starts[mol]; t < s->inversion.starts[mol + 1]; ++t) {
+    const int16_t* ix = s->inversion.idx + 4 * t;
+    const double   fk = s->inversion.par[4 * t], C0 = s->inversion.par[4 * t + 1], C1 = s->inversion.par[4 * t + 2],
+                 C2 = s->inversion.par[4 * t + 3];
+    double ji[3], jk[3], jl[3];
+    for (int c = 0; c < 3; ++c) {
+      ji[c] = p[3 * ix[0] + c] - p[3 * ix[1] + c];
+      jk[c] = p[3 * ix[2] + c] - p[3 * ix[1] + c];
+      jl[c] = p[3 * ix[3] + c] - p[3 * ix[1] + c];
+    }
+    const double l2i = dot3(ji, ji), l2k = dot3(jk, jk), l2l = dot3(jl, jl);
+    double       cosY = 0.0;
+    if (!(l2i < 1.0e-16 || l2k < 1.0e-16 || l2l < 1.0e-16)) {
+      double n[3];
+      cross(ji, jk, n);
+      const double sc = sqrt(l2i) * sqrt(l2k);
+      for (int c = 0; c < 3; ++c) n[c] /= sc;
+      const double l2n = dot3(n, n);
+      if (!(l2n < 1.0e-16)) cosY = dot3(n, jl) / (sqrt(l2l) * sqrt(l2n));
+    }
+    const double sSq = 1.0 - cosY * cosY, sinY = sSq > 0.0 ? sqrt(sSq) : 0.0;
+    e += fk * (C0 + C1 * sinY + C2 * (2.0 * sinY * sinY - 1.0));
+    if (g) {
+      const double dI = sqrt(l2i), dK = sqrt(l2k), dL = sqrt(l2l);
+      if (is_zero(dI) || is_zero(dK) || is_zero(dL)) continue;
+      double a[3], b[3], c[3], na[3], n[3];
+      for (int x = 0; x < 3; ++x) {
+        a[x]  = ji[x] / dI;
+        b[x]  = jk[x] / dK;
+        c[x]  = jl[x] / dL;
+        na[x] = -a[x];
+      }
+      cross(na, b, n);
+      const double nn = sqrt(dot3(n, n));
+      if (nn <= 0.0) continue;
+      for (int x = 0; x < 3; ++x) n[x] /= nn;
+      const double cY = clampd(dot3(n, c), -1.0, 1.0), sY = fmax(sqrt(1.0 - cY * cY), 1.0e-8);
+      const double cT = clampd(dot3(a, b), -1.0, 1.0), sTsq = 1.0 - cT * cT, sT = fmax(sqrt(sTsq), 1.0e-8);
+      const double dE = -fk * (C1 * cY - 4.0 * C2 * cY * sY);
+      double       t1[3], t2[3], t3[3];
+      cross(c, b, t1);
+      cross(a, c, t2);
+      cross(b, a, t3);
+      const double term1 = sY * sT, term2 = cY / (sY * sTsq);
+      for (int x = 0; x < 3; ++x) {
+        const double g1 = (t1[x] / term1 - (a[x] - b[x] * cT) * term2) / dI;
+        const double g3 = (t2[x] / term1 - (b[x] - a[x] * cT) * term2) / dK;
+        const double g4 = (t3[x] / term1 - c[x] * cY / sY) / dL;
+        g[3 * ix[0] + x] += dE * g1;
+        g[3 * ix[1] + x] += -dE * (g1 + g3 + g4);
+        g[3 * ix[2] + x] += dE * g3;
+        g[3 * ix[3] + x] += dE * g4;
+      }
+    }
+  }
+  for (int t = s->vdw.starts[mol]; t < s->vdw.starts[mol + 1]; ++t) {
+    const int    i = s->vdw.idx[2 * t], j = s->vdw.idx[2 * t + 1];
+    const double x = s->vdw.par[3 * t], eps = s->vdw.par[3 * t + 1], thr = s->vdw.par[3 * t + 2];
+    double       d[3] = {p[3 * i] - p[3 * j], p[3 * i + 1] - p[3 * j + 1], p[3 * i + 2] - p[3 * j + 2]};
+    const double dist = sqrt(dot3(d, d));
+    if (dist > thr) continue;
+    if (dist > 0.0) {
+      const double r = x / dist, r2 = r * r, r6 = r2 * r2 * r2;
+      e += eps * (r6 * r6 - 2.0 * r6);
+    }
+    if (g) {
+      for (int c = 0; c < 3; ++c) {
+        double v = 100.0;
+        if (dist > 0.0) {
+          const double r = x / dist, r2 = r * r, r7 = r * r2 * r2 * r2, r13 = r7 * r2 * r2 * r2;
+          v = 12.0 * eps / x * (r7 - r13) * d[c] / dist;
+        }
+        g[3 * i + c] += v;
+        g[3 * j + c] -= v;
+      }
+    }
+  }
+  return e;
+}
+
+typedef struct {
+  const UffSystem* s;
+  int              mol;
+} UffCtx;
+static double uff_fn(const void* c, const double* x, double* g) {
+  const UffCtx* m = (const UffCtx*)c;
+  return oracle_uff_energy_grad(m->s, m->mol, x, g);
+}
+void oracle_uff_minimize(const UffSystem* s, int nConf, const int32_t* confMol, const int32_t* confAtomStart,
+                         double* pos, int maxIters, double gradTol, double* energies, int8_t* converged,
+                         int32_t* iters) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int c = 0; c < nConf; ++c) {
+    UffCtx ctx = {s, confMol[c]};
+    int    it  = 0;
+    const int st = bfgs_minimize(3 * s->atomCounts[confMol[c]], pos + 3 * (size_t)confAtomStart[c], uff_fn, &ctx,
+                                 maxIters, gradTol, 1, &energies[c], &it);
+    if (converged) converged[c] = st == 0;
+    if (iters) iters[c] = it;
+  }
+}

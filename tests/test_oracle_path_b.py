@@ -173,3 +173,17 @@ def test_uniform01_is_a_pure_function():
     assert oracle.uniform01(7, 1, 2, 3) == oracle.uniform01(7, 1, 2, 3)
     u = np.array([oracle.uniform01(7, 0, 0, i) for i in range(2000)])
     assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.03
+
+
+def test_uff_gradient_matches_finite_differences_and_hand_values():
+    system, xyz, _ = S.random_uff_system(2, 6, 9, seed=5)
+    for m in range(2):
+        pos = xyz[m] + np.random.default_rng(m).normal(0, 0.05, xyz[m].shape)
+        e, g, _ = oracle.ff_energy_grad("uff", system.atom_counts, system.tables, m, pos)
+        num = _fd(lambda p: oracle.ff_energy_grad("uff", system.atom_counts, system.tables, m, p, False)[0], pos)
+        assert np.abs(num - g).max() < 1e-6 * max(1.0, np.abs(g).max())
+    # harmonic bond and 12-6 at the minimum: E = -wellDepth, zero force
+    one = FlatSystem.from_molecules("uff", [2], [{"bond": ([[0, 1]], [[1.5, 700.0]]), "vdw": ([[0, 1]], [[1.7, 0.1, 10.0]])}])
+    e, g, _ = oracle.ff_energy_grad("uff", one.atom_counts, one.tables, 0, np.array([[0, 0, 0], [1.7, 0, 0.0]]))
+    assert abs(e - (0.5 * 700.0 * 0.04 - 0.1)) < 1e-12
+    assert np.allclose(g, [[-700.0 * 0.2, 0, 0], [700.0 * 0.2, 0, 0]], atol=1e-9)

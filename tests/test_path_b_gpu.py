@@ -319,3 +319,35 @@ def test_etkdg_embed_produces_conformers_the_cpu_accepts(cuda):
     assert sum(len(c) for c in per) == int(ok.sum())
     with pytest.raises(ValueError):
         EmbedMolecules(flat, EmbedParameters(useRandomCoords=False))
+
+
+# ------------------------------------------------------------------ UFF
+def test_uff_energy_gradient_and_minimize_parity(cuda):
+    from nvmolkit_b200.minimizer import energy_and_grad, minimize
+    from nvmolkit_b200.uffOptimization import FlatUFFMolecules, UFFOptimizeMoleculesConfs
+
+    system, xyz, _ = S.random_uff_system(8, 4, 30, seed=31)
+    rng = np.random.default_rng(2)
+    batch = ConformerBatch.from_coords(system, [[x + rng.normal(0, 0.05, x.shape), x + rng.normal(0, 0.15, x.shape)] for x in xyz])
+    e, g = energy_and_grad(system, batch)
+    e, g = e.cpu().numpy(), g.cpu().numpy()
+    for c in range(batch.n_conf):
+        a0, a1 = batch.atom_starts[c], batch.atom_starts[c + 1]
+        eo, go, _ = oracle.ff_energy_grad("uff", system.atom_counts, system.tables, batch.conf_mol[c], batch.positions[a0:a1])
+        assert _rel(e[c], eo) < 1e-11
+        assert np.abs(g[a0:a1] - go).max() < 1e-9 * max(1.0, np.abs(go).max())
+    # minimise from a CPU-relaxed geometry + perturbation, compare minima
+    pos0, _, _, _ = oracle.ff_minimize("uff", system.atom_counts, system.tables, np.arange(8, dtype=np.int32),
+                                       np.concatenate([[0], np.cumsum(system.atom_counts)]).astype(np.int32),
+                                       np.concatenate(xyz), 2000, 1e-4)
+    st0 = np.concatenate([[0], np.cumsum(system.atom_counts)])
+    relaxed = [pos0[st0[m]:st0[m + 1]] for m in range(8)]
+    b2 = ConformerBatch.from_coords(system, [[r + rng.normal(0, 0.05, r.shape) for _ in range(2)] for r in relaxed])
+    res = minimize(system, b2, 1000, 1e-4)
+    pos_o, e_o, conv_o, _ = oracle.ff_minimize("uff", system.atom_counts, system.tables, b2.conf_mol, b2.atom_starts, b2.positions, 1000, 1e-4)
+    eg, st = res.energies.cpu().numpy(), res.status.cpu().numpy()
+    both = (st == 0) & (conv_o == 1)
+    assert both.mean() > 0.7
+    assert (_rel(eg[both], e_o[both]) < E_RTOL).all()
+    energies, coords = UFFOptimizeMoleculesConfs(FlatUFFMolecules(system, b2), maxIters=1000)
+    assert np.allclose(np.array(energies).ravel(), eg, rtol=1e-6, atol=1e-6)
