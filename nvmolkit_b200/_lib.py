@@ -24,6 +24,7 @@ SIGNATURES = {
     "b200mol_launch_count": (C.c_uint64, []),
     "b200mol_check_device": (C.c_int, [C.c_int]),
     "b200mol_free_async": (C.c_int, [_vp, _vp]),
+    "b200mol_set_option": (C.c_int, [C.c_char_p, C.c_longlong]),
     "b200mol_profile_enable": (C.c_int, [C.c_int]),
     "b200mol_profile_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_float)]),
     "b200mol_tanimoto_cross": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, _vp, _vp]),
@@ -109,3 +110,7 @@ def profile_read(phase: str) -> float:
     ms = C.c_float(0.0)
     check(load().b200mol_profile_read(phase.encode(), C.byref(ms)))
     return float(ms.value)
+
+
+def set_option(key: str, value: int) -> None:
+    check(load().b200mol_set_option(key.encode(), int(value)))

@@ -294,6 +294,14 @@ void launchTile(const CUtensorMap& tmX, const CUtensorMap& tmY, const TileParams
 
 }  // namespace
 
+bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s);
+long long g_tensorMinPairs = 1ll << 24;  // pair count from which the count mode runs on tcgen05 (< 0: never)
+
+void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s) {
+  threshTableKernel<<<(maxS + 1 + 127) / 128, 128, 0, s>>>(maxS, cutoff, thresh);
+  B200_LAUNCHED();
+}
+
 void launchRowPopcount(const uint32_t* fp, size_t n, int words, int32_t* pop, cudaStream_t s) {
   if (n == 0) return;
   const size_t threads = n * 32;
@@ -306,6 +314,11 @@ void launchSimilarity(SimMode mode, const SimLaunch& q, cudaStream_t s) {
                "fingerprint width must be a multiple of 128 bits and at most 4096 bits (got %d words)", q.words);
   if (q.nX == 0 || q.nY == 0) return;
   B200_REQUIRE(q.nX < (1ull << 31) && q.nY < (1ull << 31), "too many fingerprints");
+  if (mode == kCountTanimoto && g_tensorMinPairs >= 0 &&
+      static_cast<double>(q.nX) * static_cast<double>(q.nY) >= static_cast<double>(g_tensorMinPairs) &&
+      (reinterpret_cast<uintptr_t>(q.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.y) & 15) == 0) {
+    if (launchSimilarityTensor(q, s)) return;
+  }
   B200_REQUIRE((reinterpret_cast<uintptr_t>(q.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.y) & 15) == 0,
                "fingerprint buffers must be 16-byte aligned");
 
@@ -383,6 +396,15 @@ extern "C" int b200mol_profile_read(const char* phase, float* ms) {
     B200_REQUIRE(it != g_phases.end() && it->second.recorded, "phase '%s' was not recorded", phase);
     B200_CUDA(cudaEventSynchronize(it->second.stop));
     B200_CUDA(cudaEventElapsedTime(ms, it->second.start, it->second.stop));
+  });
+}
+
+extern "C" int b200mol_set_option(const char* key, long long value) {
+  return guarded([&] {
+    B200_REQUIRE(key, "null key");
+    const std::string k(key);
+    if (k == "similarity_tensor_min_pairs") g_tensorMinPairs = value;
+    else fail(B200MOL_ERR_INVALID, "unknown option '%s'", key);
   });
 }
 

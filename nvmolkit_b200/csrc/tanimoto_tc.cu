@@ -1,0 +1,370 @@
+// Thresholded popcount similarity on the 5th-generation tensor cores (tcgen05), sm_100a.
+//
+// |A & B| of two bit vectors is the dot product of their 0/1 expansions, so the N x M intersection-count matrix is an
+// unsigned-int8 GEMM with s32 accumulation (exact). The SIMT tile (tanimoto.cu) sits on the POPC issue roof
+// (64 POPC per 2048-bit pair, 16 lanes/clk/SM -> 7e10 pairs/s, profiles/r01_path_a_summary.md); the reference reaches
+// its tensor path through `mma.sync ... b1 ... and.popc`, which ptxas lowers on sm_100a to bit-slicing LOP3s plus
+// eight IMMA.16832.U8.U8 per 256-bit step — i.e. it already runs this contraction as an int8 MMA, through the legacy
+// warp-level path. Here it is issued natively:
+//
+//   pre-pass   bits -> bytes (0/1) once per fingerprint set, [n][bits] u8 in HBM (2 KB per 2048-bit row)
+//   tile       128 (rows of X) x 256 (rows of Y) pairs per step of a persistent CTA
+//   warp 0     TMA producer: [128|256 rows][128 B] K-chunks, SWIZZLE_128B, 4-stage mbarrier ring
+//   warp 1     one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (M128 N256 K32), accumulators in TMEM
+//              (2 x 256 columns: the next tile's MMAs overlap this tile's epilogue), tcgen05.commit -> mbarriers
+//   warps 2-5  epilogue: tcgen05.ld 32x32b, integer threshold test c >= thresh[|A|+|B|] (bit-exact with the fp64
+//              predicate, see tanimoto.cu), neighbour counts for both endpoints, warp-aggregated edge append
+//
+// Replaces crossSimilarityKernelTensorOp (src/similarity_kernels.cu:104-240) + the Triton count kernel
+// (nvmolkit/_fusedButina.py:99-179) for the fused Butina pass.
+#include "profile.cuh"
+#include "similarity.cuh"
+#include "tma.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kTM       = 128;
+constexpr int kTN       = 256;
+constexpr int kTK       = 128;  // bytes (= bits of the fingerprint) per K chunk
+constexpr int kStagesTC = 4;
+constexpr int kThreadsTC = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kABytes   = kTM * kTK;
+constexpr int kBBytes   = kTN * kTK;
+constexpr int kGroupTC  = 16;  // tile rows per L2 reuse group
+
+struct TcParams {
+  uint32_t        n;  // X == Y (symmetric) or nX/nY
+  uint32_t        nY;
+  int             kChunks;
+  uint32_t        tilesM, tilesN;
+  int             symmetric;
+  const int32_t*  popX;
+  const int32_t*  popY;
+  const uint16_t* thresh;
+  int             threshLen;
+  int             sign;
+  int32_t*        counts;
+  int32_t*        countsY;  // == counts in symmetric mode; nullptr in X-vs-Y mode (rows only)
+  int2*           edges;
+  unsigned long long* edgeCursor;
+  unsigned long long  edgeCap;
+};
+
+__global__ void expandBitsKernel(const uint32_t* __restrict__ fp, size_t nWords, uint4* __restrict__ out) {
+  const size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= nWords) return;
+  const uint32_t x = fp[w];
+  uint32_t       b[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {  // 4 bits -> 4 bytes of 0/1 (bit j of the nibble lands in byte j)
+    const uint32_t nib = (x >> (4 * q)) & 0xFu;
+    b[q]               = (nib * 0x00204081u) & 0x01010101u;
+  }
+  out[2 * w]     = make_uint4(b[0], b[1], b[2], b[3]);
+  out[2 * w + 1] = make_uint4(b[4], b[5], b[6], b[7]);
+}
+
+__device__ __forceinline__ uint64_t makeSmemDesc(uint32_t smemByteAddr) {
+  // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO unused, descriptor version 1 (sm_100), layout type 2
+  return static_cast<uint64_t>((smemByteAddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+         (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+}
+constexpr uint32_t kIdescI8 = (2u << 4)                 // D = S32
+                              | (0u << 7) | (0u << 10)  // A, B = unsigned 8-bit
+                              | (static_cast<uint32_t>(kTN >> 3) << 17) | (static_cast<uint32_t>(kTM >> 4) << 24);
+
+__device__ __forceinline__ void ummaI8(uint32_t tmemD, uint64_t aDesc, uint64_t bDesc, uint32_t accumulate) {
+  asm volatile(
+    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemD),
+    "l"(aDesc), "l"(bDesc), "r"(kIdescI8), "r"(accumulate)
+    : "memory");
+}
+__device__ __forceinline__ void ummaCommit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+    "[%32];"
+    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+      "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+      "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+    : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// linear tile index -> (tm, tn): groups of kGroupTC tile-rows sweep the tile-columns
+__device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32_t& tm, uint32_t& tn) {
+  const uint64_t perGroup = static_cast<uint64_t>(kGroupTC) * p.tilesN;
+  const uint32_t group    = static_cast<uint32_t>(t / perGroup);
+  const uint32_t inGroup  = static_cast<uint32_t>(t % perGroup);
+  if (group * kGroupTC >= p.tilesM) return false;
+  const uint32_t gRows = min(static_cast<uint32_t>(kGroupTC), p.tilesM - group * kGroupTC);
+  tm                   = group * kGroupTC + inGroup % gRows;
+  tn                   = inGroup / gRows;
+  if (tn >= p.tilesN) return false;
+  // symmetric: skip tiles whose every column index is <= every row index (no pair with row < col)
+  if (p.symmetric && (tn * kTN + kTN - 1) <= tm * kTM) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(kThreadsTC, 1)
+  simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+                  uint64_t totalTiles) {
+  extern __shared__ __align__(1024) uint8_t smemRaw[];
+  __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
+  __shared__ uint32_t tmemBase;
+  __shared__ int      popB[2][kTN];
+  __shared__ int      colAcc[2][kTN];
+
+  const uint32_t smemBase = (smemAddr(smemRaw) + 1023u) & ~1023u;
+  uint8_t*       smemGen  = smemRaw + (smemBase - smemAddr(smemRaw));
+  uint16_t*      threshS  = reinterpret_cast<uint16_t*>(smemGen + kStagesTC * (kABytes + kBBytes));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tmaPrefetchDesc(&tmA);
+    tmaPrefetchDesc(&tmB);
+    for (int s = 0; s < kStagesTC; ++s) {
+      mbarInit(&fullBar[s], 1);
+      mbarInit(&emptyBar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbarInit(&tmemFull[s], 1);
+      mbarInit(&tmemEmpty[s], 4);  // one arrival per epilogue warp
+    }
+    fenceBarrierInit();
+  }
+  if (warp == 1) {  // TMEM: 512 columns = two 128 x 256 s32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(&tmemBase)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < p.threshLen; i += kThreadsTC) threshS[i] = p.thresh[i];
+  tcFenceBefore();
+  __syncthreads();
+  tcFenceAfter();
+  const uint32_t tmem = tmemBase;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int      stage = 0;
+      uint32_t phase = 0;
+      for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
+        uint32_t tm, tn;
+        if (!tileCoords(p, t, tm, tn)) continue;
+        for (int kc = 0; kc < p.kChunks; ++kc) {
+          mbarWait(&emptyBar[stage], phase ^ 1);
+          uint8_t* dst = smemGen + stage * (kABytes + kBBytes);
+          mbarExpectTx(&fullBar[stage], kABytes + kBBytes);
+          tmaLoad2D(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
+          tmaLoad2D(dst + kABytes, &tmB, kc * kTK, tn * kTN, &fullBar[stage]);
+          if (++stage == kStagesTC) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int      stage = 0;
+      uint32_t phase = 0, local = 0;
+      for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
+        uint32_t tm, tn;
+        if (!tileCoords(p, t, tm, tn)) continue;
+        const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
+        mbarWait(&tmemEmpty[as], accPhase ^ 1);
+        tcFenceAfter();
+        const uint32_t dAddr = tmem + as * kTN;
+        for (int kc = 0; kc < p.kChunks; ++kc) {
+          mbarWait(&fullBar[stage], phase);
+          tcFenceAfter();
+          const uint32_t aAddr = smemBase + stage * (kABytes + kBBytes);
+          const uint64_t aDesc = makeSmemDesc(aAddr), bDesc = makeSmemDesc(aAddr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kTK / 32; ++k)  // K = 32 bytes per instruction: +32 B = +2 in the 16-byte address field
+            ummaI8(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u);
+          ummaCommit(&emptyBar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == kStagesTC) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ummaCommit(&tmemFull[as]);
+        ++local;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int      ew      = warp - 2;             // 0..3
+    const int      quarter = warp & 3;             // TMEM lane quarter this warp may read
+    const int      et      = ew * 32 + lane;       // 0..127 thread index among the epilogue warps
+    uint32_t       local   = 0;
+    for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
+      uint32_t tm, tn;
+      if (!tileCoords(p, t, tm, tn)) continue;
+      const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
+      // stage this tile's column popcounts
+      for (int c = et; c < kTN; c += 128) {
+        const uint32_t gc = tn * kTN + c;
+        popB[as][c]       = gc < p.nY ? __ldg(p.popY + gc) : 0;
+        colAcc[as][c]     = 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t gr = tm * kTM + quarter * 32 + lane;
+      const int      pa = gr < p.n ? __ldg(p.popX + gr) : 0;
+      mbarWait(&tmemFull[as], accPhase);
+      tcFenceAfter();
+      int rowHits = 0;
+      for (int cb = 0; cb < kTN / 32; ++cb) {
+        uint32_t r[32];
+        tmemLoad32(tmem + as * kTN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t gc = tn * kTN + cb * 32 + j;
+          bool           ok = gr < p.n && gc < p.nY;
+          if (p.symmetric) ok = ok && gr < gc;
+          const int th = threshS[pa + popB[as][cb * 32 + j]];
+          if (ok && static_cast<int>(r[j]) >= th) mask |= 1u << j;
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+        if (any) {
+          rowHits += __popc(mask);
+          if (p.countsY) {
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+              const unsigned col = __ballot_sync(0xffffffffu, (mask >> j) & 1u);
+              if (lane == 0 && col) atomicAdd(&colAcc[as][cb * 32 + j], __popc(col));
+            }
+          }
+          if (p.edges) {
+            const int mine = __popc(mask);
+            int       incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            const int          total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned long long base  = 0;
+            if (lane == 31) base = atomicAdd(p.edgeCursor, static_cast<unsigned long long>(total));
+            base                  = __shfl_sync(0xffffffffu, base, 31);
+            unsigned long long at = base + incl - mine;
+            uint32_t           m  = mask;
+            while (m) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1;
+              if (at < p.edgeCap) p.edges[at] = make_int2(static_cast<int>(gr), static_cast<int>(tn * kTN + cb * 32 + j));
+              ++at;
+            }
+          }
+        }
+      }
+      tcFenceBefore();
+      __syncwarp();
+      if (lane == 0) mbarArrive(&tmemEmpty[as]);  // accumulator may be overwritten
+      if (rowHits) atomicAdd(p.counts + gr, p.sign * rowHits);
+      if (p.countsY) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = et; c < kTN; c += 128) {
+          const int v = colAcc[as][c];
+          if (v) atomicAdd(p.countsY + tn * kTN + c, p.sign * v);
+        }
+      }
+      ++local;
+    }
+  }
+  tcFenceBefore();
+  __syncthreads();
+  if (warp == 1) {
+    tcFenceAfter();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+}  // namespace
+
+void launchRowPopcount(const uint32_t* fp, size_t n, int words, int32_t* pop, cudaStream_t s);
+void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s);
+
+// Tanimoto count mode on tensor cores. Returns false when the problem shape is not eligible (caller uses the SIMT tile).
+bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
+  const int bits = q.words * 32;
+  if (bits % kTK != 0 || bits > 4096) return false;
+  if (q.groupStride != 1 || q.groupOffset != 0) return false;  // multi-GPU row-group sharding stays on the SIMT tile
+  const bool same = (q.x == q.y && q.nX == q.nY);
+  if (q.symmetric && !same) return false;
+
+  TcParams p{};
+  p.n         = static_cast<uint32_t>(q.nX);
+  p.nY        = static_cast<uint32_t>(q.nY);
+  p.kChunks   = bits / kTK;
+  p.tilesM    = static_cast<uint32_t>((q.nX + kTM - 1) / kTM);
+  p.tilesN    = static_cast<uint32_t>((q.nY + kTN - 1) / kTN);
+  p.symmetric = q.symmetric ? 1 : 0;
+  p.sign      = q.sign;
+  p.counts    = q.rowCounts;
+  p.countsY   = q.symmetric ? q.rowCounts : nullptr;
+  p.edges     = q.edges;
+  p.edgeCursor = q.edgeCursor;
+  p.edgeCap   = q.edgeCap;
+
+  // 0/1 byte expansion of the fingerprints (2 KB per 2048-bit row)
+  Scratch<uint8_t> expX(q.nX * static_cast<size_t>(bits), s);
+  Scratch<uint8_t> expYown(same ? 0 : q.nY * static_cast<size_t>(bits), s);
+  {
+    const size_t nw = q.nX * static_cast<size_t>(q.words);
+    expandBitsKernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(q.x, nw, reinterpret_cast<uint4*>(expX.get()));
+    B200_LAUNCHED();
+    if (!same) {
+      const size_t nwy = q.nY * static_cast<size_t>(q.words);
+      expandBitsKernel<<<static_cast<unsigned>((nwy + 255) / 256), 256, 0, s>>>(q.y, nwy, reinterpret_cast<uint4*>(expYown.get()));
+      B200_LAUNCHED();
+    }
+  }
+  const uint8_t* expY = same ? expX.get() : expYown.get();
+
+  Scratch<int32_t> popX(q.nX, s), popYown(same ? 0 : q.nY, s);
+  launchRowPopcount(q.x, q.nX, q.words, popX.get(), s);
+  if (!same) launchRowPopcount(q.y, q.nY, q.words, popYown.get(), s);
+  p.popX = popX.get();
+  p.popY = same ? popX.get() : popYown.get();
+  const int         maxS = 2 * bits;
+  Scratch<uint16_t> thresh(maxS + 1, s);
+  launchThreshTable(maxS, q.cutoff, thresh.get(), s);
+  p.thresh    = thresh.get();
+  p.threshLen = maxS + 1;
+
+  CUtensorMap tmA, tmB;
+  makeTensorMap2D(&tmA, expX.get(), q.nX, bits, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  makeTensorMap2D(&tmB, expY, q.nY, bits, kTN, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+
+  const size_t smemBytes = static_cast<size_t>(kStagesTC) * (kABytes + kBBytes) + static_cast<size_t>(maxS + 1) * 2 + 1024 + 64;
+  static bool  configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    configured = true;
+  }
+  B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
+  const uint64_t groupsM = (p.tilesM + kGroupTC - 1) / kGroupTC;
+  const uint64_t total   = groupsM * kGroupTC * p.tilesN;
+  int            blocks  = smCount();
+  if (static_cast<uint64_t>(blocks) > total) blocks = static_cast<int>(total);
+  PhaseTimer t("neighbor_pass_tc", s);
+  simTensorKernel<<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+  B200_LAUNCHED();
+  return true;
+}
+
+}  // namespace b200

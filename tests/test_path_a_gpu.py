@@ -256,3 +256,47 @@ def test_pack_unpack_roundtrip(cuda):
 
     fp = torch.from_numpy(S.random_fingerprints(9, bits=256).view(np.int32)).to(cuda)
     assert (pack_fingerprint(unpack_fingerprint(fp)) == fp).all()
+
+
+# ------------------------------------------------------------------ tensor-core (tcgen05 int8) path of the count pass
+@pytest.fixture
+def force_tensor_path(cuda):
+    from nvmolkit_b200 import _lib
+
+    _lib.set_option("similarity_tensor_min_pairs", 0)
+    yield
+    _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
+
+
+@pytest.mark.parametrize("bits", [128, 512, 2048])
+@pytest.mark.parametrize("nx,ny", [(1, 1), (127, 255), (128, 256), (129, 257), (700, 333)])
+def test_tensor_count_ge_exact(cuda, force_tensor_path, bits, nx, ny):
+    from nvmolkit_b200 import _lib
+
+    x = S.clustered_fingerprints(max(1, nx // 25 + 1), 25, bits=bits, seed=41)[:nx]
+    y = S.clustered_fingerprints(max(1, ny // 11 + 1), 11, bits=bits, seed=41)[:ny]
+    dx, dy = _dev(x, cuda), _dev(y, cuda)
+    for cutoff in (0.3, 0.65):
+        counts = torch.full((nx,), 7, dtype=torch.int32, device=cuda)
+        _lib.call("b200mol_tanimoto_count_ge", dx.data_ptr(), nx, dy.data_ptr(), ny, bits // 32, 0, cutoff, 1,
+                  counts.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        want = oracle.count_ge(x, y, cutoff, counts=np.full(nx, 7, dtype=np.int32))
+        assert (counts.cpu().numpy() == want).all(), (bits, nx, ny, cutoff)
+
+
+@pytest.mark.parametrize("centres,members,cutoff", [(1, 1, 0.3), (7, 40, 0.3), (40, 25, 0.3), (60, 17, 0.5), (100, 50, 0.3)])
+def test_tensor_fused_butina_equals_rdkit_definition(cuda, force_tensor_path, centres, members, cutoff):
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    fp = S.clustered_fingerprints(centres, members, seed=centres * 100 + members)
+    ids, cen = fused_butina_device(_dev(fp, cuda), cutoff)
+    ids_cpu, cen_cpu = oracle.butina_fp(fp, cutoff)
+    assert (ids.cpu().numpy() == ids_cpu).all() and (cen.cpu().numpy() == cen_cpu).all()
+
+
+def test_tensor_and_simt_paths_agree_on_identical_rows(cuda, force_tensor_path):
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    one = np.repeat(S.random_fingerprints(1, seed=1), 600, axis=0)  # dense graph: every pair is an edge, buffer regrows
+    ids, cen = fused_butina_device(_dev(one, cuda), 0.3)
+    assert (ids.cpu().numpy() == 0).all() and cen.cpu().numpy().tolist() == [599]
