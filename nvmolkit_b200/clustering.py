@@ -61,6 +61,7 @@ def fused_butina_device(x, cutoff: float, stream=None, metric: str = "tanimoto")
     sptr = stream_ptr(stream)
     if cutoff < 0 or cutoff > 1:
         raise ValueError(f"cutoff must be in [0, 1], got {cutoff}")
+    require_cuda()
     x = x.contiguous()
     n = x.shape[0]
     with stream_ctx(stream):

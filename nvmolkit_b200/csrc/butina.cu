@@ -213,7 +213,9 @@ void clusterFromCsr(int n, const long long* offsets, const int* adj, int32_t* co
   int       perSm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, butinaLoopKernel, kLoopThreads, 0));
   B200_REQUIRE(perSm >= 1, "butina loop kernel does not fit on an SM");
-  const int blocks = smCount();  // one CTA per SM
+  // The loop is latency-bound (two grid-wide barriers per cluster): a small grid keeps the barrier cheap, and 32 CTAs x
+  // 32 warps are plenty for the ~100 dirty slices and ~100 member warps of a round.
+  const int blocks = smCount() < 32 ? smCount() : 32;
   void*     args[] = {&st};
   B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(butinaLoopKernel), dim3(blocks), dim3(kLoopThreads), args, 0, s));
   g_launchCount.fetch_add(1);

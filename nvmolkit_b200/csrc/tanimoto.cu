@@ -408,6 +408,16 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
   });
 }
 
+// Keep stream-ordered scratch (GBs for the 1M x 1M pass) in the pool across synchronisations instead of returning it to
+// the OS at every sync (the default release threshold is 0).
+static void retainPoolMemory(int dev) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
+
 extern "C" int b200mol_check_device(int dev) {
   return guarded([&] {
     int n = 0;
@@ -416,6 +426,7 @@ extern "C" int b200mol_check_device(int dev) {
     int major = 0;
     B200_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) fail(B200MOL_ERR_NODEVICE, "device %d is compute capability %d.x; libb200mol is sm_100a only", dev, major);
+    retainPoolMemory(dev);
   });
 }
 

@@ -39,6 +39,7 @@ struct TcParams {
   int             kChunks;
   uint32_t        tilesM, tilesN;
   int             symmetric;
+  uint32_t        groupOffset, groupStride;  // multi-GPU: this rank owns tile-row groups with group % stride == offset
   const int32_t*  popX;
   const int32_t*  popY;
   const uint16_t* thresh;
@@ -106,6 +107,7 @@ __device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32
   const uint32_t group    = static_cast<uint32_t>(t / perGroup);
   const uint32_t inGroup  = static_cast<uint32_t>(t % perGroup);
   if (group * kGroupTC >= p.tilesM) return false;
+  if (group % p.groupStride != p.groupOffset) return false;
   const uint32_t gRows = min(static_cast<uint32_t>(kGroupTC), p.tilesM - group * kGroupTC);
   tm                   = group * kGroupTC + inGroup % gRows;
   tn                   = inGroup / gRows;
@@ -302,7 +304,6 @@ void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s
 bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
   const int bits = q.words * 32;
   if (bits % kTK != 0 || bits > 4096) return false;
-  if (q.groupStride != 1 || q.groupOffset != 0) return false;  // multi-GPU row-group sharding stays on the SIMT tile
   const bool same = (q.x == q.y && q.nX == q.nY);
   if (q.symmetric && !same) return false;
 
@@ -313,6 +314,8 @@ bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
   p.tilesM    = static_cast<uint32_t>((q.nX + kTM - 1) / kTM);
   p.tilesN    = static_cast<uint32_t>((q.nY + kTN - 1) / kTN);
   p.symmetric = q.symmetric ? 1 : 0;
+  p.groupOffset = q.groupOffset;
+  p.groupStride = q.groupStride < 1 ? 1 : q.groupStride;
   p.sign      = q.sign;
   p.counts    = q.rowCounts;
   p.countsY   = q.symmetric ? q.rowCounts : nullptr;
