@@ -230,6 +230,35 @@ def run_b200(args) -> None:
         step_e2e()
         ms_e2e, _ = timed(step_e2e, args.steps)
 
+    # materialised cross-similarity (the reference's crossTanimotoSimilarity output format): HBM-write bound, 8 B / pair
+    cross = None
+    if args.cross_n > 0 and rank == 0:
+        from nvmolkit_b200.similarity import crossTanimotoSimilarity
+
+        xa = d_fp[: args.cross_n]
+        xb = d_fp[args.cross_n: 2 * args.cross_n] if n >= 2 * args.cross_n else d_fp[: args.cross_n]
+        for _ in range(2):
+            res = crossTanimotoSimilarity(xa, xb)
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(3):
+            res = crossTanimotoSimilarity(xa, xb)
+            try:
+                times.append(_lib.profile_read("cross_tc"))
+            except ValueError:
+                times = []
+                break
+        if times:
+            nb = xb.shape[0]
+            ms_c = float(np.mean(times))
+            bytes_c = 8.0 * args.cross_n * nb + 256.0 * (args.cross_n + nb)
+            peak_c, src_c = measured_peaks()
+            cross = {"pairs_per_s": args.cross_n * nb / (ms_c * 1e-3), "kernel_ms": ms_c, "shape": [args.cross_n, nb],
+                     "roofline": {"bound": "hbm", "achieved": bytes_c / (ms_c * 1e-3) / 1e9, "peak": peak_c, "unit": "GB/s",
+                                  "frac": bytes_c / (ms_c * 1e-3) / 1e9 / peak_c, "algorithmic_bytes": bytes_c,
+                                  "kernel": "simTensorKernel<materialise> (cross_tc)", "peak_source": src_c}}
+        del res
+
     # second half of the BASELINE metric: ETKDG + MMFF mols/s (config 3 shape, reduced count so the default run stays short)
     path_b = None
     if args.etkdg_mols > 0:
@@ -315,6 +344,7 @@ def run_b200(args) -> None:
                            "sample": f"{len(fps)}x{len(fps)} clustered 2048-bit fingerprints, cutoff {CUTOFF}, {dt:.1f} s"}
     out["parity_on_sample"] = "bit-exact" if parity else "MISMATCH"
     out["etkdg_mmff"] = path_b
+    out["cross_similarity"] = cross
     if path_b is not None:
         flat_b, mmff_b = path_b_pool(args.pool, synthetic.SEED)
         nb = min(args.etkdg_cpu_mols, path_b["n_mols"])
@@ -430,6 +460,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="butina")
     ap.add_argument("--n-centres", type=int, default=0, help="override the problem size (x50 fingerprints); testing only")
+    ap.add_argument("--cross-n", type=int, default=32768, help="rows of the materialised cross-similarity leg (0 = skip)")
     ap.add_argument("--etkdg-mols", type=int, default=512, help="molecules of the ETKDG+MMFF leg (0 = skip)")
     ap.add_argument("--confs", type=int, default=10)
     ap.add_argument("--pool", type=int, default=64, help="distinct pseudo-molecules cycled to fill the batch")

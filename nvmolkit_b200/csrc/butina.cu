@@ -80,6 +80,7 @@ struct LoopState {
   unsigned long long* sliceBest;  // [nSlices] key = count<<32 | idx ; 0 = nothing
   int*                sliceDirty;
   int*                nClustersOut;  // clusters formed by the loop (non-singletons + isolated leftovers come later)
+  int                 vecOk;         // ids / counts are 16-byte aligned: full slices use vector loads
 };
 
 __device__ __forceinline__ unsigned long long warpMax(unsigned long long v) {
@@ -109,12 +110,38 @@ __global__ void __launch_bounds__(kLoopThreads, 1) butinaLoopKernel(LoopState st
       if (!st.sliceDirty[sl]) continue;
       unsigned long long best = 0;
       const int          base = sl << kSliceShift;
-      for (int k = lane; k < kSlice; k += 32) {
-        const int i = base + k;
-        if (i < st.n && st.ids[i] < 0) {
-          const unsigned long long key =
-            (static_cast<unsigned long long>(static_cast<unsigned>(st.counts[i])) << 32) | static_cast<unsigned>(i);
-          best = key > best ? key : best;
+      if (base + kSlice <= st.n && st.vecOk) {
+        // full slice: 8 independent 16-byte loads of ids and counts per lane (no dependent-load chain)
+        const int4* ids4 = reinterpret_cast<const int4*>(st.ids + base);
+        const int4* cnt4 = reinterpret_cast<const int4*>(st.counts + base);
+        int4        id[8], ct[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          id[k] = ids4[k * 32 + lane];
+          ct[k] = cnt4[k * 32 + lane];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int  i0   = base + (k * 32 + lane) * 4;
+          const int  iv[4] = {id[k].x, id[k].y, id[k].z, id[k].w};
+          const int  cv[4] = {ct[k].x, ct[k].y, ct[k].z, ct[k].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (iv[q] < 0) {
+              const unsigned long long key =
+                (static_cast<unsigned long long>(static_cast<unsigned>(cv[q])) << 32) | static_cast<unsigned>(i0 + q);
+              best = key > best ? key : best;
+            }
+          }
+        }
+      } else {
+        for (int k = lane; k < kSlice; k += 32) {
+          const int i = base + k;
+          if (i < st.n && st.ids[i] < 0) {
+            const unsigned long long key =
+              (static_cast<unsigned long long>(static_cast<unsigned>(st.counts[i])) << 32) | static_cast<unsigned>(i);
+            best = key > best ? key : best;
+          }
         }
       }
       best = warpMax(best);
@@ -209,7 +236,8 @@ void clusterFromCsr(int n, const long long* offsets, const int* adj, int32_t* co
   fillKernel<<<(nSlices + 255) / 256, 256, 0, s>>>(sliceDirty.get(), nSlices, 1);
   B200_LAUNCHED();
 
-  LoopState st{n, nSlices, offsets, adj, counts, ids, centroids, sliceBest.get(), sliceDirty.get(), nLoop.get()};
+  const int vecOk = ((reinterpret_cast<uintptr_t>(ids) | reinterpret_cast<uintptr_t>(counts)) & 15) == 0;
+  LoopState st{n, nSlices, offsets, adj, counts, ids, centroids, sliceBest.get(), sliceDirty.get(), nLoop.get(), vecOk};
   int       perSm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, butinaLoopKernel, kLoopThreads, 0));
   B200_REQUIRE(perSm >= 1, "butina loop kernel does not fit on an SM");

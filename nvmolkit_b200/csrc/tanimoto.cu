@@ -294,7 +294,7 @@ void launchTile(const CUtensorMap& tmX, const CUtensorMap& tmY, const TileParams
 
 }  // namespace
 
-bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s);
+bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s);
 long long g_tensorMinPairs = 1ll << 24;  // pair count from which the count mode runs on tcgen05 (< 0: never)
 
 void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s) {
@@ -314,10 +314,10 @@ void launchSimilarity(SimMode mode, const SimLaunch& q, cudaStream_t s) {
                "fingerprint width must be a multiple of 128 bits and at most 4096 bits (got %d words)", q.words);
   if (q.nX == 0 || q.nY == 0) return;
   B200_REQUIRE(q.nX < (1ull << 31) && q.nY < (1ull << 31), "too many fingerprints");
-  if (mode == kCountTanimoto && g_tensorMinPairs >= 0 &&
+  if (mode != kCountCosine && g_tensorMinPairs >= 0 &&
       static_cast<double>(q.nX) * static_cast<double>(q.nY) >= static_cast<double>(g_tensorMinPairs) &&
       (reinterpret_cast<uintptr_t>(q.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.y) & 15) == 0) {
-    if (launchSimilarityTensor(q, s)) return;
+    if (launchSimilarityTensor(mode, q, s)) return;
   }
   B200_REQUIRE((reinterpret_cast<uintptr_t>(q.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.y) & 15) == 0,
                "fingerprint buffers must be 16-byte aligned");

@@ -50,7 +50,10 @@ struct TcParams {
   int2*           edges;
   unsigned long long* edgeCursor;
   unsigned long long  edgeCap;
+  double*         out;  // materialise modes: [n][nY] fp64
 };
+
+enum TcMode : int { kTcCount = 0, kTcTanimoto = 1, kTcCosine = 2 };
 
 __global__ void expandBitsKernel(const uint32_t* __restrict__ fp, size_t nWords, uint4* __restrict__ out) {
   const size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -117,6 +120,7 @@ __device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32
   return true;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreadsTC, 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                   uint64_t totalTiles) {
@@ -231,6 +235,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       for (int cb = 0; cb < kTN / 32; ++cb) {
         uint32_t r[32];
         tmemLoad32(tmem + as * kTN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+        if constexpr (MODE != kTcCount) {
+          // fp64 similarity of this thread's row against 32 consecutive columns: 256 contiguous bytes per thread
+          if (gr < p.n) {
+            double* orow = p.out + static_cast<size_t>(gr) * p.nY + tn * kTN + cb * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t gc = tn * kTN + cb * 32 + j;
+              if (gc >= p.nY) break;
+              const int c  = static_cast<int>(r[j]);
+              const int pb = popB[as][cb * 32 + j];
+              double    v  = 0.0;
+              if (c != 0) {
+                if constexpr (MODE == kTcTanimoto) v = __ddiv_rn(static_cast<double>(c), static_cast<double>(pa + pb - c));
+                else v = __ddiv_rn(static_cast<double>(c), __dsqrt_rn(__dmul_rn(static_cast<double>(pa), static_cast<double>(pb))));
+              }
+              __stcs(orow + j, v);
+            }
+          }
+          continue;
+        }
         uint32_t mask = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -276,8 +300,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       tcFenceBefore();
       __syncwarp();
       if (lane == 0) mbarArrive(&tmemEmpty[as]);  // accumulator may be overwritten
-      if (rowHits) atomicAdd(p.counts + gr, p.sign * rowHits);
-      if (p.countsY) {
+      if (MODE == kTcCount && rowHits) atomicAdd(p.counts + gr, p.sign * rowHits);
+      if (MODE == kTcCount && p.countsY) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int c = et; c < kTN; c += 128) {
           const int v = colAcc[as][c];
@@ -300,8 +324,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 void launchRowPopcount(const uint32_t* fp, size_t n, int words, int32_t* pop, cudaStream_t s);
 void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s);
 
-// Tanimoto count mode on tensor cores. Returns false when the problem shape is not eligible (caller uses the SIMT tile).
-bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
+// Count / materialise modes on tensor cores. Returns false when the problem shape is not eligible (caller uses the SIMT tile).
+bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
+  if (mode == kCountCosine) return false;
   const int bits = q.words * 32;
   if (bits % kTK != 0 || bits > 4096) return false;
   const bool same = (q.x == q.y && q.nX == q.nY);
@@ -322,6 +347,7 @@ bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
   p.edges     = q.edges;
   p.edgeCursor = q.edgeCursor;
   p.edgeCap   = q.edgeCap;
+  p.out       = q.out;
 
   // 0/1 byte expansion of the fingerprints (2 KB per 2048-bit row)
   Scratch<uint8_t> expX(q.nX * static_cast<size_t>(bits), s);
@@ -345,9 +371,11 @@ bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
   p.popY = same ? popX.get() : popYown.get();
   const int         maxS = 2 * bits;
   Scratch<uint16_t> thresh(maxS + 1, s);
-  launchThreshTable(maxS, q.cutoff, thresh.get(), s);
-  p.thresh    = thresh.get();
-  p.threshLen = maxS + 1;
+  if (mode == kCountTanimoto) {
+    launchThreshTable(maxS, q.cutoff, thresh.get(), s);
+    p.threshLen = maxS + 1;
+  }
+  p.thresh = thresh.get();
 
   CUtensorMap tmA, tmB;
   makeTensorMap2D(&tmA, expX.get(), q.nX, bits, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
@@ -356,7 +384,9 @@ bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
   const size_t smemBytes = static_cast<size_t>(kStagesTC) * (kABytes + kBBytes) + static_cast<size_t>(maxS + 1) * 2 + 1024 + 64;
   static bool  configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     configured = true;
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
@@ -364,8 +394,16 @@ bool launchSimilarityTensor(const SimLaunch& q, cudaStream_t s) {
   const uint64_t total   = groupsM * kGroupTC * p.tilesN;
   int            blocks  = smCount();
   if (static_cast<uint64_t>(blocks) > total) blocks = static_cast<int>(total);
-  PhaseTimer t("neighbor_pass_tc", s);
-  simTensorKernel<<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+  if (mode == kCountTanimoto) {
+    PhaseTimer t("neighbor_pass_tc", s);
+    simTensorKernel<kTcCount><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+  } else if (mode == kMaterialiseTanimoto) {
+    PhaseTimer t("cross_tc", s);
+    simTensorKernel<kTcTanimoto><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+  } else {
+    PhaseTimer t("cross_tc", s);
+    simTensorKernel<kTcCosine><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+  }
   B200_LAUNCHED();
   return true;
 }

@@ -300,3 +300,18 @@ def test_tensor_and_simt_paths_agree_on_identical_rows(cuda, force_tensor_path):
     one = np.repeat(S.random_fingerprints(1, seed=1), 600, axis=0)  # dense graph: every pair is an edge, buffer regrows
     ids, cen = fused_butina_device(_dev(one, cuda), 0.3)
     assert (ids.cpu().numpy() == 0).all() and cen.cpu().numpy().tolist() == [599]
+
+
+@pytest.mark.parametrize("bits", [128, 1024, 2048])
+@pytest.mark.parametrize("n,m", [(1, 1), (127, 300), (129, 256), (640, 513)])
+def test_tensor_cross_similarity_bit_exact(cuda, force_tensor_path, bits, n, m):
+    from nvmolkit_b200.similarity import crossCosineSimilarity, crossTanimotoSimilarity
+
+    a = S.random_fingerprints(n, bits=bits, p=0.05, seed=n * 7 + bits, near_dups=n // 4)
+    b = S.random_fingerprints(m, bits=bits, p=0.05, seed=m * 11 + bits + 1, near_dups=m // 4)
+    b[: min(n, m) // 2] = a[: min(n, m) // 2]
+    a[0] = 0  # empty fingerprint row
+    da, db = _dev(a, cuda), _dev(b, cuda)
+    assert (crossTanimotoSimilarity(da, db).numpy() == oracle.similarity_cross(a, b)).all()
+    assert (crossCosineSimilarity(da, db).numpy() == oracle.similarity_cross(a, b, metric="cosine")).all()
+    assert (crossTanimotoSimilarity(da).numpy() == oracle.similarity_cross(a)).all()
