@@ -40,7 +40,8 @@ uint64_t b200mol_launch_count(void);
 int b200mol_check_device(int dev);
 int b200mol_free_async(void* d_ptr, void* stream);
 /* Tuning knobs. "similarity_tensor_min_pairs": pair count (nX * nY) from which the thresholded Tanimoto pass runs on
- * the tcgen05 int8 tensor-core tile instead of the SIMT popcount tile (default 2^24; 0 = always, < 0 = never). */
+ * the tcgen05 int8 tensor-core tile instead of the SIMT popcount tile (default 2^24; 0 = always, < 0 = never).
+ * "bfgs_ctas_per_sm": resident CTAs per SM of the minimiser / embedder kernels (default 4). */
 int b200mol_set_option(const char* key, long long value);
 /* Per-phase CUDA-event timing inside the library (off by default). Phases: "neighbor_pass" (the N^2 tile kernel
  * alone), "csr_build", "cluster_loop", "bfgs". b200mol_profile_read waits for the phase's stop event. */

@@ -15,6 +15,7 @@
 #include "profile.cuh"
 
 namespace b200 {
+int g_bfgsCtasPerSm = 4;  // resident minimisation CTAs per SM (option "bfgs_ctas_per_sm")
 namespace {
 
 struct Batch {
@@ -37,7 +38,7 @@ struct Batch {
 };
 
 template <class FF>
-__global__ void __launch_bounds__(kT) bfgsKernel(const typename FF::System sys, const typename FF::Params par, const Batch b) {
+__global__ void __launch_bounds__(kT, 4) bfgsKernel(const typename FF::System sys, const typename FF::Params par, const Batch b) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kWarps];
   __shared__ int                        nextConf;
@@ -123,7 +124,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   int perSm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, bfgsKernel<FF>, kT, smem));
   B200_REQUIRE(perSm >= 1, "BFGS kernel does not fit");
-  perSm            = perSm > 2 ? 2 : perSm;
+  perSm            = perSm > g_bfgsCtasPerSm ? g_bfgsCtasPerSm : perSm;
   int blocks       = smCount() * perSm;
   if (blocks > nConf) blocks = nConf;
   const size_t       stride = static_cast<size_t>(maxN) * maxN;

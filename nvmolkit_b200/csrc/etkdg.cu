@@ -20,6 +20,7 @@
 #include "profile.cuh"
 
 namespace b200 {
+extern int g_bfgsCtasPerSm;
 namespace {
 
 using ff::V3;
@@ -181,7 +182,7 @@ __device__ unsigned finalChecks(const EmbedArgs& a, int mol, const double* pos, 
   return m;
 }
 
-__global__ void __launch_bounds__(kT) etkdgKernel(const EmbedArgs a) {
+__global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kWarps];
   __shared__ int                        nextSlot;
@@ -305,7 +306,7 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     int perSm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, etkdgKernel, kT, smem));
     B200_REQUIRE(perSm >= 1, "embedding kernel does not fit");
-    perSm      = perSm > 2 ? 2 : perSm;
+    perSm      = perSm > g_bfgsCtasPerSm ? g_bfgsCtasPerSm : perSm;
     int blocks = smCount() * perSm;
     if (blocks > nSlots) blocks = nSlots;
     const size_t    stride = static_cast<size_t>(maxN) * maxN;

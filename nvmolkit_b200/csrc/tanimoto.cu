@@ -295,6 +295,7 @@ void launchTile(const CUtensorMap& tmX, const CUtensorMap& tmY, const TileParams
 }  // namespace
 
 bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s);
+extern int g_bfgsCtasPerSm;
 long long g_tensorMinPairs = 1ll << 24;  // pair count from which the count mode runs on tcgen05 (< 0: never)
 
 void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s) {
@@ -404,6 +405,10 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
     B200_REQUIRE(key, "null key");
     const std::string k(key);
     if (k == "similarity_tensor_min_pairs") g_tensorMinPairs = value;
+    else if (k == "bfgs_ctas_per_sm") {
+      B200_REQUIRE(value >= 1 && value <= 8, "bfgs_ctas_per_sm must be in [1, 8]");
+      g_bfgsCtasPerSm = static_cast<int>(value);
+    }
     else fail(B200MOL_ERR_INVALID, "unknown option '%s'", key);
   });
 }

