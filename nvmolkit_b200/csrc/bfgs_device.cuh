@@ -69,12 +69,17 @@ __device__ void gradOf(const typename FF::View& v, const double* x, double* grad
 }
 
 // Shared-memory working set of one CTA: six vectors of maxN doubles + the per-CTA inverse-Hessian slab (global/L2).
-struct BfgsWork {
+// HT = storage type of the inverse Hessian: double (default; bit-for-bit the RDKit recurrence) or float (half the slab
+// traffic, products and sums still accumulate in fp64) for the embedding stages whose trajectories are chaotic anyway.
+template <class HT = double>
+struct BfgsWorkT {
   double *pos, *grad, *dir, *newPos, *dGrad, *hdg;  // shared memory, maxN each
-  double* H;                                        // [n*n] global slab of this CTA
+  HT*     H;                                        // [n*n] global slab of this CTA
   double* red;                                      // kWarps doubles of shared memory
 };
-__device__ __forceinline__ BfgsWork carveWork(double* sm, int maxN, double* H, double* red) {
+using BfgsWork = BfgsWorkT<double>;
+template <class HT = double>
+__device__ __forceinline__ BfgsWorkT<HT> carveWork(double* sm, int maxN, HT* H, double* red) {
   return {sm, sm + maxN, sm + 2 * maxN, sm + 3 * maxN, sm + 4 * maxN, sm + 5 * maxN, H, red};
 }
 
@@ -86,19 +91,19 @@ struct BfgsOutcome {
 
 // Minimises w.pos[0..n) in place. maxRestarts > 0 re-runs (H = I, fresh gradient) while the run ends unconverged:
 // RDKit's `while (needMore) needMore = field->minimize(...)` (src/etkdg_stage_distgeom_minimize.cu repeatUntilConverged).
-template <class FF>
-__device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWork& w, int n, int maxIters, double gradTol,
-                                    bool scaleGrads, int maxRestarts) {
+template <class FF, class HT = double>
+__device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWorkT<HT>& w, int n, int maxIters,
+                                    double gradTol, bool scaleGrads, int maxRestarts) {
   constexpr double FUNCTOL = 1e-4, MOVETOL = 1e-7, TOLX = 4. * 3e-8, EPS = 3e-8;
-  double *pos = w.pos, *grad = w.grad, *dir = w.dir, *newPos = w.newPos, *dGrad = w.dGrad, *hdg = w.hdg, *H = w.H,
-         *red = w.red;
+  double *pos = w.pos, *grad = w.grad, *dir = w.dir, *newPos = w.newPos, *dGrad = w.dGrad, *hdg = w.hdg, *red = w.red;
+  HT*     H   = w.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int       status = 1, iter = 0;
   for (int restart = 0;; ++restart) {
     __syncthreads();
-    for (size_t i = tid; i < static_cast<size_t>(n) * n; i += kT) H[i] = 0.0;
+    for (size_t i = tid; i < static_cast<size_t>(n) * n; i += kT) H[i] = HT(0);
     __syncthreads();
-    for (int i = tid; i < n; i += kT) H[static_cast<size_t>(i) * n + i] = 1.0;
+    for (int i = tid; i < n; i += kT) H[static_cast<size_t>(i) * n + i] = HT(1);
 
     double fp = energyOf<FF>(view, pos, red);
     gradOf<FF>(view, pos, grad, n);
@@ -188,9 +193,9 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       }
       // ---------------- inverse Hessian (bfgs_hessian.cu:37-239) ----------------
       for (int row = warp; row < n; row += kWarps) {
-        const double* hr = H + static_cast<size_t>(row) * n;
-        double        a  = 0.0;
-        for (int c = lane; c < n; c += 32) a += hr[c] * dGrad[c];
+        const HT* hr = H + static_cast<size_t>(row) * n;
+        double    a  = 0.0;
+        for (int c = lane; c < n; c += 32) a += static_cast<double>(hr[c]) * dGrad[c];
         a = warpSum(a);
         if (lane == 0) hdg[row] = a;
       }
@@ -216,17 +221,17 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       __syncthreads();
       // fused: rank-2 update of row + dot with the new gradient -> next direction (into newPos, free here)
       for (int row = warp; row < n; row += kWarps) {
-        double*      hr  = H + static_cast<size_t>(row) * n;
+        HT*          hr  = H + static_cast<size_t>(row) * n;
         const double pxi = fac * dir[row], hdgi = fad * hdg[row], dgi = fae * dGrad[row];
         double       a   = 0.0;
         if (update) {
           for (int c = lane; c < n; c += 32) {
-            const double h = hr[c] + (pxi * dir[c] - hdgi * hdg[c] + dgi * dGrad[c]);
-            hr[c]          = h;
+            const double h = static_cast<double>(hr[c]) + (pxi * dir[c] - hdgi * hdg[c] + dgi * dGrad[c]);
+            hr[c]          = static_cast<HT>(h);
             a += h * grad[c];
           }
         } else {
-          for (int c = lane; c < n; c += 32) a += hr[c] * grad[c];
+          for (int c = lane; c < n; c += 32) a += static_cast<double>(hr[c]) * grad[c];
         }
         a = warpSum(a);
         if (lane == 0) newPos[row] = -a;

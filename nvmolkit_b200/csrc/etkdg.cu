@@ -38,7 +38,7 @@ struct EmbedArgs {
   int32_t*                attempts;       // [nSlots]
   double*                 energy;         // [nSlots] DG energy (first-stage weights) of the accepted attempt
   unsigned long long*     stageFailures;  // [kNumStages] (may be NULL)
-  double*                 hessWs;
+  float*                  hessWs;  // fp32 inverse-Hessian slabs (fp64 accumulation): half the traffic, L2-resident
   size_t                  hessStride;
   int*                    queue;
   int                     maxN;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kWarps];
   __shared__ int                        nextSlot;
-  const BfgsWork w   = carveWork(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red);
+  const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red);
   double*        ref = sm + 6 * a.maxN;  // ETK reference geometry
   const int      tid = threadIdx.x;
   for (;;) {
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
       // 1: first minimisation
       {
         const auto        v = ff::Dg<4>::view(a.dg, mol, {1.0, 0.1});
-        const BfgsOutcome o = bfgsMinimize<ff::Dg<4>>(v, w, n, a.par.dgIters, a.par.optimizerForceTol, true, a.par.maxRestarts);
+        const BfgsOutcome o = bfgsMinimize<ff::Dg<4>, float>(v, w, n, a.par.dgIters, a.par.optimizerForceTol, true, a.par.maxRestarts);
         eAccepted           = o.energy;
         if (o.energy / nA >= 0.05) failedStage = 1;
       }
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
       // 4: fourth-dimension collapse
       if (failedStage < 0) {
         const auto v = ff::Dg<4>::view(a.dg, mol, {0.2, 1.0});
-        bfgsMinimize<ff::Dg<4>>(v, w, n, a.par.fourthIters, a.par.optimizerForceTol, true, 0);
+        bfgsMinimize<ff::Dg<4>, float>(v, w, n, a.par.fourthIters, a.par.optimizerForceTol, true, 0);
       }
       // 5: ETK refinement + planarity
       if (failedStage < 0 && (a.par.useExpTorsions || a.par.useBasicKnowledge)) {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
         __syncthreads();
         auto v   = ff::Etk::view(a.etk, mol, {a.par.useBasicKnowledge ? 0 : 1, 1});
         v.refPos = ref;
-        bfgsMinimize<ff::Etk>(v, w, n, a.par.etkIters, a.par.optimizerForceTol, true, 0);
+        bfgsMinimize<ff::Etk, float>(v, w, n, a.par.etkIters, a.par.optimizerForceTol, true, 0);
         if (a.par.useBasicKnowledge && planarityFails(a.etk, a.chk.numImpropers, mol, w.pos, red)) failedStage = 5;
       }
       // 6-10: final checks
@@ -310,7 +310,7 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     int blocks = smCount() * perSm;
     if (blocks > nSlots) blocks = nSlots;
     const size_t    stride = static_cast<size_t>(maxN) * maxN;
-    Scratch<double> hess(stride * blocks, s);
+    Scratch<float>  hess(stride * blocks, s);
     Scratch<int>    queue(1, s);
     B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));
     if (d_stage_failures) B200_CUDA(cudaMemsetAsync(d_stage_failures, 0, kNumStages * sizeof(uint64_t), s));

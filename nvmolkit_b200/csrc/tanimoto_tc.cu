@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
   __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
   __shared__ uint32_t tmemBase;
   __shared__ int      popB[2][kTN];
+  __shared__ int      popA[2][kTM];
   __shared__ int      colAcc[2][kTN];
 
   const uint32_t smemBase = (smemAddr(smemRaw) + 1023u) & ~1023u;
@@ -228,6 +229,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
         popB[as][c]       = gc < p.nY ? __ldg(p.popY + gc) : 0;
         colAcc[as][c]     = 0;
       }
+      if (MODE != kTcCount && et < kTM) {
+        const uint32_t ga = tm * kTM + et;
+        popA[as][et]      = ga < p.n ? __ldg(p.popX + ga) : 0;
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       const uint32_t gr = tm * kTM + quarter * 32 + lane;
       const int      pa = gr < p.n ? __ldg(p.popX + gr) : 0;
@@ -238,28 +243,45 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
         uint32_t r[32];
         tmemLoad32(tmem + as * kTN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
         if constexpr (MODE != kTcCount) {
-          // fp64 similarity of this thread's row against 32 consecutive columns: 256 contiguous bytes per thread
-          if (gr < p.n) {
-            double* orow = p.out + static_cast<size_t>(gr) * p.nY + tn * kTN + cb * 32;
+          // Transpose the 32 x 32 block in registers (5 butterfly rounds of SHFL) so that lane = column and k = row:
+          // every store instruction then writes 32 consecutive doubles of one output row (8 full sectors) instead of
+          // 32 scattered 8-byte pieces.
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const uint32_t gc = tn * kTN + cb * 32 + j;
-              if (gc >= p.nY) break;
-              const int c  = static_cast<int>(r[j]);
-              const int pb = popB[as][cb * 32 + j];
-              double    v  = 0.0;
+              if (!(j & sft)) {
+                const bool     hi   = (lane & sft) != 0;
+                const uint32_t send = hi ? r[j] : r[j + sft];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, sft);
+                if (hi) r[j] = recv;
+                else r[j + sft] = recv;
+              }
+            }
+          }
+          const uint32_t gc = tn * kTN + cb * 32 + lane;
+          const int      pb = popB[as][cb * 32 + lane];
+          if (gc < p.nY) {
+            const uint32_t row0 = tm * kTM + quarter * 32;
+            double*        ocol = p.out + static_cast<size_t>(row0) * p.nY + gc;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              if (row0 + k >= p.n) break;
+              const int c   = static_cast<int>(r[k]);
+              const int pak = popA[as][quarter * 32 + k];
+              double    v   = 0.0;
               if (c != 0) {
                 if constexpr (MODE == kTcTanimoto) {
                   // c / u through one reciprocal + one Newton step: exhaustively verified on the CPU to equal the
                   // correctly rounded quotient for every 1 <= c <= u <= 8192 (tests/test_oracle_golden.py)
-                  const double dc = static_cast<double>(c), du = static_cast<double>(pa + pb - c);
+                  const double dc = static_cast<double>(c), du = static_cast<double>(pak + pb - c);
                   const double rc = __drcp_rn(du), q0 = __dmul_rn(dc, rc);
                   v               = __fma_rn(__fma_rn(-q0, du, dc), rc, q0);
                 } else {
-                  v = __ddiv_rn(static_cast<double>(c), __dsqrt_rn(__dmul_rn(static_cast<double>(pa), static_cast<double>(pb))));
+                  v = __ddiv_rn(static_cast<double>(c), __dsqrt_rn(__dmul_rn(static_cast<double>(pak), static_cast<double>(pb))));
                 }
               }
-              __stcs(orow + j, v);
+              __stcs(ocol + static_cast<size_t>(k) * p.nY, v);
             }
           }
           continue;
