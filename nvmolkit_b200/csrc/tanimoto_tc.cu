@@ -27,7 +27,8 @@ namespace {
 constexpr int kTM       = 128;
 constexpr int kTN       = 256;
 constexpr int kTK       = 128;  // bytes (= bits of the fingerprint) per K chunk
-constexpr int kStagesTC = 4;
+constexpr int kStagesCount = 4;  // smem ring depth of the count mode
+constexpr int kStagesMat   = 3;  // materialise modes: one stage less, the space holds the reciprocal table
 constexpr int kEpiWarps  = 8;    // two warps per TMEM lane quarter, each takes half of the 256 columns
 constexpr int kThreadsTC = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kABytes   = kTM * kTK;
@@ -52,6 +53,7 @@ struct TcParams {
   unsigned long long* edgeCursor;
   unsigned long long  edgeCap;
   double*         out;  // materialise modes: [n][nY] fp64
+  int             recipLen;  // 2 * bits (materialise Tanimoto)
 };
 
 enum TcMode : int { kTcCount = 0, kTcTanimoto = 1, kTcCosine = 2 };
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                   uint64_t totalTiles) {
   extern __shared__ __align__(1024) uint8_t smemRaw[];
+  constexpr int kStagesTC = MODE == kTcCount ? kStagesCount : kStagesMat;
   __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
   __shared__ uint32_t tmemBase;
   __shared__ int      popB[2][kTN];
@@ -156,6 +159,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = threadIdx.x; i < p.threshLen; i += kThreadsTC) threshS[i] = p.thresh[i];
+  double* recipS = reinterpret_cast<double*>(threshS);  // materialise Tanimoto: RN(1/u), u = |A u B| <= 2 * bits
+  if constexpr (MODE == kTcTanimoto) {
+    for (int u = threadIdx.x; u <= p.recipLen; u += kThreadsTC) recipS[u] = u ? __drcp_rn(static_cast<double>(u)) : 0.0;
+  }
   tcFenceBefore();
   __syncthreads();
   tcFenceAfter();
@@ -274,8 +281,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
                 if constexpr (MODE == kTcTanimoto) {
                   // c / u through one reciprocal + one Newton step: exhaustively verified on the CPU to equal the
                   // correctly rounded quotient for every 1 <= c <= u <= 8192 (tests/test_oracle_golden.py)
-                  const double dc = static_cast<double>(c), du = static_cast<double>(pak + pb - c);
-                  const double rc = __drcp_rn(du), q0 = __dmul_rn(dc, rc);
+                  // int -> double through the 2^52 trick (1 DADD) and RN(1/u) from the shared-memory table
+                  const int    u  = pak + pb - c;
+                  const double dc = __hiloint2double(0x43300000, c) - 4503599627370496.0;
+                  const double du = __hiloint2double(0x43300000, u) - 4503599627370496.0;
+                  const double rc = recipS[u], q0 = __dmul_rn(dc, rc);
                   v               = __fma_rn(__fma_rn(-q0, du, dc), rc, q0);
                 } else {
                   v = __ddiv_rn(static_cast<double>(c), __dsqrt_rn(__dmul_rn(static_cast<double>(pak), static_cast<double>(pb))));
@@ -379,6 +389,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   p.edgeCursor = q.edgeCursor;
   p.edgeCap   = q.edgeCap;
   p.out       = q.out;
+  p.recipLen  = 2 * bits;
 
   // 0/1 byte expansion of the fingerprints (2 KB per 2048-bit row)
   Scratch<uint8_t> expX(q.nX * static_cast<size_t>(bits), s);
@@ -412,7 +423,9 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   makeTensorMap2D(&tmA, expX.get(), q.nX, bits, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
   makeTensorMap2D(&tmB, expY, q.nY, bits, kTN, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
-  const size_t smemBytes = static_cast<size_t>(kStagesTC) * (kABytes + kBBytes) + static_cast<size_t>(maxS + 1) * 2 + 1024 + 64;
+  const bool   count     = mode == kCountTanimoto;
+  const size_t smemBytes = static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + kBBytes) +
+                           (count ? static_cast<size_t>(maxS + 1) * 2 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
   static bool  configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
