@@ -283,3 +283,7 @@ extern "C" int b200mol_poly_minimize(int32_t nSys, const int32_t* d_starts, int 
                           d_status, d_iters, asStream(stream));
   });
 }
+
+#ifdef B200_BFGS_TIMING
+extern "C" void b200mol_debug_clocks_bfgs(unsigned long long* out8) { b200::readBfgsClocks(out8); }
+#endif

@@ -91,6 +91,21 @@ struct BfgsOutcome {
 
 // Minimises w.pos[0..n) in place. maxRestarts > 0 re-runs (H = I, fresh gradient) while the run ends unconverged:
 // RDKit's `while (needMore) needMore = field->minimize(...)` (src/etkdg_stage_distgeom_minimize.cu repeatUntilConverged).
+#ifdef B200_BFGS_TIMING
+static __device__ unsigned long long g_bfgsClk[8];  // per translation unit
+static inline void readBfgsClocks(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_bfgsClk, sizeof(g_bfgsClk));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_bfgsClk, z, sizeof(z));
+}
+#define B200_T0() const long long t0_ = clock64()
+#define B200_T1(slot) tim[slot] += clock64() - t0_
+#else
+#define B200_T0()
+#define B200_T1(slot)
+#endif
+
 template <class FF, class HT = double>
 __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWorkT<HT>& w, int n, int maxIters,
                                     double gradTol, bool scaleGrads, int maxRestarts) {
@@ -99,6 +114,10 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
   HT*     H   = w.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int       status = 1, iter = 0;
+#ifdef B200_BFGS_TIMING
+  long long tim[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long tAll = clock64();
+#endif
   for (int restart = 0;; ++restart) {
     __syncthreads();
     for (size_t i = tid; i < static_cast<size_t>(n) * n; i += kT) H[i] = HT(0);
@@ -137,7 +156,11 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         if (lambda < lambdaMin) break;
         for (int i = tid; i < n; i += kT) newPos[i] = pos[i] + lambda * dir[i];
         __syncthreads();
-        newVal = energyOf<FF>(view, newPos, red);
+        {
+          B200_T0();
+          newVal = energyOf<FF>(view, newPos, red);
+          B200_T1(0);
+        }
         if (newVal - fp <= FUNCTOL * lambda * slope) {
           accepted = true;
           break;
@@ -180,7 +203,11 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         status = 0;
         break;
       }
-      gradOf<FF>(view, pos, grad, n);
+      {
+        B200_T0();
+        gradOf<FF>(view, pos, grad, n);
+        B200_T1(1);
+      }
       gradScale = scaleGrad(n, grad, scaleGrads, red);
       tst       = 0.0;
       for (int i = tid; i < n; i += kT) {
@@ -192,6 +219,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         break;
       }
       // ---------------- inverse Hessian (bfgs_hessian.cu:37-239) ----------------
+      B200_T0();
       for (int row = warp; row < n; row += kWarps) {
         const HT* hr = H + static_cast<size_t>(row) * n;
         double    a  = 0.0;
@@ -200,6 +228,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         if (lane == 0) hdg[row] = a;
       }
       __syncthreads();
+      B200_T1(2);
       double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
       for (int i = tid; i < n; i += kT) {
         f1 += dGrad[i] * dir[i];
@@ -220,6 +249,8 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       }
       __syncthreads();
       // fused: rank-2 update of row + dot with the new gradient -> next direction (into newPos, free here)
+      const long long tU_ = clock64();
+      (void)tU_;
       for (int row = warp; row < n; row += kWarps) {
         HT*          hr  = H + static_cast<size_t>(row) * n;
         const double pxi = fac * dir[row], hdgi = fad * hdg[row], dgi = fae * dGrad[row];
@@ -237,6 +268,10 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         if (lane == 0) newPos[row] = -a;
       }
       __syncthreads();
+#ifdef B200_BFGS_TIMING
+      tim[3] += clock64() - tU_;
+      tim[4] += 1;
+#endif
       for (int i = tid; i < n; i += kT) dir[i] = newPos[i];
       __syncthreads();
     }
@@ -247,6 +282,12 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
   out.status = status;
   out.iters  = iter;
   out.energy = energyOf<FF>(view, pos, red);
+#ifdef B200_BFGS_TIMING
+  if (tid == 0) {
+    tim[5] = clock64() - tAll;
+    for (int k = 0; k < 6; ++k) atomicAdd(&g_bfgsClk[k], static_cast<unsigned long long>(tim[k]));
+  }
+#endif
   return out;
 }
 

@@ -345,3 +345,7 @@ extern "C" int b200mol_etkdg_check(const b200mol_dg_system* dg, const b200mol_et
     B200_LAUNCHED();
   });
 }
+
+#ifdef B200_BFGS_TIMING
+extern "C" void b200mol_debug_clocks_etkdg(unsigned long long* out8) { b200::readBfgsClocks(out8); }
+#endif
