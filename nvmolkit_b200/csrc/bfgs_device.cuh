@@ -112,7 +112,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
   constexpr double FUNCTOL = 1e-4, MOVETOL = 1e-7, TOLX = 4. * 3e-8, EPS = 3e-8;
   double *pos = w.pos, *grad = w.grad, *dir = w.dir, *newPos = w.newPos, *dGrad = w.dGrad, *hdg = w.hdg, *red = w.red;
   HT*     H   = w.H;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   int       status = 1, iter = 0;
 #ifdef B200_BFGS_TIMING
   long long tim[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -220,12 +220,22 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       }
       // ---------------- inverse Hessian (bfgs_hessian.cu:37-239) ----------------
       B200_T0();
-      for (int row = warp; row < n; row += kWarps) {
-        const HT* hr = H + static_cast<size_t>(row) * n;
+      // hdg = H * dGrad, thread per COLUMN (H is symmetric): every load is coalesced along a row, consecutive rows are
+      // independent loads (deep memory-level parallelism) and no cross-lane reduction is needed. The warp-per-row form
+      // exposed one L2 round trip + a shuffle tree per row and was 78 % of the embedder's time (profiles/).
+      // Work item = (column j, row segment): items are spread evenly over the CTA whatever n is; partial sums meet in
+      // shared memory (a few hundred fp64 atomics per pass).
+      const int nSeg   = min(32, max(1, (4 * kT + n - 1) / n));
+      const int segLen = (n + nSeg - 1) / nSeg;
+      for (int i = tid; i < n; i += kT) hdg[i] = 0.0;
+      __syncthreads();
+      for (int w = tid; w < n * nSeg; w += kT) {
+        const int j = w % n, i0 = (w / n) * segLen, i1 = min(n, i0 + segLen);
+        const HT* hc = H + j;
         double    a  = 0.0;
-        for (int c = lane; c < n; c += 32) a += static_cast<double>(hr[c]) * dGrad[c];
-        a = warpSum(a);
-        if (lane == 0) hdg[row] = a;
+#pragma unroll 8
+        for (int i = i0; i < i1; ++i) a += static_cast<double>(hc[static_cast<size_t>(i) * n]) * dGrad[i];
+        atomicAdd(&hdg[j], a);
       }
       __syncthreads();
       B200_T1(2);
@@ -251,21 +261,28 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       // fused: rank-2 update of row + dot with the new gradient -> next direction (into newPos, free here)
       const long long tU_ = clock64();
       (void)tU_;
-      for (int row = warp; row < n; row += kWarps) {
-        HT*          hr  = H + static_cast<size_t>(row) * n;
-        const double pxi = fac * dir[row], hdgi = fad * hdg[row], dgi = fae * dGrad[row];
-        double       a   = 0.0;
+      // per-row scalars of the rank-2 update, staged in newPos (free here) as fac*xi_i | hdg holds fad*hdg_i after scaling
+      // thread per column: H[i][j] += (fac xi_i) xi_j - (fad hdg_i) hdg_j + (fae u_i) u_j ; a_j += H[i][j] g_i
+      for (int i = tid; i < n; i += kT) newPos[i] = 0.0;
+      __syncthreads();
+      for (int w = tid; w < n * nSeg; w += kT) {
+        const int    j = w % n, i0 = (w / n) * segLen, i1 = min(n, i0 + segLen);
+        HT*          hc = H + j;
+        const double xj = dir[j], hj = hdg[j], uj = dGrad[j];
+        double       a  = 0.0;
         if (update) {
-          for (int c = lane; c < n; c += 32) {
-            const double h = static_cast<double>(hr[c]) + (pxi * dir[c] - hdgi * hdg[c] + dgi * dGrad[c]);
-            hr[c]          = static_cast<HT>(h);
-            a += h * grad[c];
+#pragma unroll 4
+          for (int i = i0; i < i1; ++i) {
+            const double h = static_cast<double>(hc[static_cast<size_t>(i) * n]) +
+                             ((fac * dir[i]) * xj - (fad * hdg[i]) * hj + (fae * dGrad[i]) * uj);
+            hc[static_cast<size_t>(i) * n] = static_cast<HT>(h);
+            a += h * grad[i];
           }
         } else {
-          for (int c = lane; c < n; c += 32) a += static_cast<double>(hr[c]) * grad[c];
+#pragma unroll 8
+          for (int i = i0; i < i1; ++i) a += static_cast<double>(hc[static_cast<size_t>(i) * n]) * grad[i];
         }
-        a = warpSum(a);
-        if (lane == 0) newPos[row] = -a;
+        atomicAdd(&newPos[j], -a);
       }
       __syncthreads();
 #ifdef B200_BFGS_TIMING

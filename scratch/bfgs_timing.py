@@ -9,6 +9,7 @@ subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-s
 from nvmolkit_b200 import _lib
 _lib.LIB_PATH = out
 import bench, torch
+_lib.profile_enable(True)
 flat, mmff = bench.path_b_pool(64, 20260924)
 dev = torch.device("cuda", 0)
 import numpy as np
