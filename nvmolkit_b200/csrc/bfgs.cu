@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kT, 4) bfgsKernel(const typename FF::System sy
     for (int i = tid; i < n; i += kT) w.pos[i] = gpos[i];
     if constexpr (FF::kHasRef) {
       if (par.recentre) {  // seventh shared vector: the reference geometry of the window refresh
-        double* ref = sm + 6 * b.maxN;
+        double* ref = sm + kBfgsVectors * b.maxN;
         for (int i = tid; i < n; i += kT) ref[i] = gpos[i];
         view.refPos = ref;
       }
@@ -114,7 +114,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   B200_REQUIRE(nConf > 0 && maxAtoms > 0 && maxIters >= 0, "bad batch arguments");
   B200_REQUIRE(confAtomStart && pos && energy, "null pointer");
   const int    maxN = FF::kDim * maxAtoms;
-  const size_t smem = static_cast<size_t>(FF::kHasRef ? 7 : 6) * maxN * sizeof(double);
+  const size_t smem = static_cast<size_t>(kBfgsVectors + (FF::kHasRef ? 1 : 0)) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large for the shared-memory BFGS (%d atoms)", maxAtoms);
   static size_t configured = 0;  // per instantiation
   if (smem > 48 * 1024 && smem > configured) {

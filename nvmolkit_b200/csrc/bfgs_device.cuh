@@ -76,11 +76,13 @@ struct BfgsWorkT {
   double *pos, *grad, *dir, *newPos, *dGrad, *hdg;  // shared memory, maxN each
   HT*     H;                                        // [n*n] global slab of this CTA
   double* red;                                      // kWarps doubles of shared memory
+  double* scratch;                                  // shared memory, 4 * maxN doubles (scaled vectors of the Hessian passes)
 };
+constexpr int kBfgsVectors = 10;  // six working vectors + four scratch vectors of maxN doubles
 using BfgsWork = BfgsWorkT<double>;
 template <class HT = double>
 __device__ __forceinline__ BfgsWorkT<HT> carveWork(double* sm, int maxN, HT* H, double* red) {
-  return {sm, sm + maxN, sm + 2 * maxN, sm + 3 * maxN, sm + 4 * maxN, sm + 5 * maxN, H, red};
+  return {sm, sm + maxN, sm + 2 * maxN, sm + 3 * maxN, sm + 4 * maxN, sm + 5 * maxN, H, red, sm + 6 * maxN};
 }
 
 struct BfgsOutcome {
@@ -224,18 +226,24 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       // independent loads (deep memory-level parallelism) and no cross-lane reduction is needed. The warp-per-row form
       // exposed one L2 round trip + a shuffle tree per row and was 78 % of the embedder's time (profiles/).
       // Work item = (column j, row segment): items are spread evenly over the CTA whatever n is; partial sums meet in
-      // shared memory (a few hundred fp64 atomics per pass).
+      // shared memory (a few hundred fp64 atomics per pass). With fp32 slabs the whole pass runs in fp32 (no
+      // conversions: F2F and fp64 are the slow pipes of this part, profiles/r01_path_b_summary.md).
+      using AT         = HT;  // arithmetic type of the Hessian passes = storage type
       const int nSeg   = min(32, max(1, (4 * kT + n - 1) / n));
       const int segLen = (n + nSeg - 1) / nSeg;
-      for (int i = tid; i < n; i += kT) hdg[i] = 0.0;
+      AT*       vD     = reinterpret_cast<AT*>(w.scratch);  // dGrad as AT
+      for (int i = tid; i < n; i += kT) {
+        hdg[i] = 0.0;
+        vD[i]  = static_cast<AT>(dGrad[i]);
+      }
       __syncthreads();
-      for (int w = tid; w < n * nSeg; w += kT) {
-        const int j = w % n, i0 = (w / n) * segLen, i1 = min(n, i0 + segLen);
+      for (int wi = tid; wi < n * nSeg; wi += kT) {
+        const int j = wi % n, i0 = (wi / n) * segLen, i1 = min(n, i0 + segLen);
         const HT* hc = H + j;
-        double    a  = 0.0;
+        AT        a  = AT(0);
 #pragma unroll 8
-        for (int i = i0; i < i1; ++i) a += static_cast<double>(hc[static_cast<size_t>(i) * n]) * dGrad[i];
-        atomicAdd(&hdg[j], a);
+        for (int i = i0; i < i1; ++i) a += hc[static_cast<size_t>(i) * n] * vD[i];
+        atomicAdd(&hdg[j], static_cast<double>(a));
       }
       __syncthreads();
       B200_T1(2);
@@ -263,26 +271,65 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       (void)tU_;
       // per-row scalars of the rank-2 update, staged in newPos (free here) as fac*xi_i | hdg holds fad*hdg_i after scaling
       // thread per column: H[i][j] += (fac xi_i) xi_j - (fad hdg_i) hdg_j + (fae u_i) u_j ; a_j += H[i][j] g_i
-      for (int i = tid; i < n; i += kT) newPos[i] = 0.0;
+      // scaled row vectors (index i) and plain column vectors (index j), in the arithmetic type:
+      //   H[i][j] += sx_i x_j - sh_i h_j + su_i u_j ,  a_j += H[i][j] g_i        (3 + 1 FMAs per element)
+      AT* sx = reinterpret_cast<AT*>(w.scratch);
+      AT* sh = sx + n;
+      AT* su = sh + n;
+      AT* vg = su + n;
+      AT* vx = vg + n;
+      AT* vh = vx + n;
+      AT* vu = vh + n;  // 7 n elements of AT <= 4 n doubles when AT = float; AT = double keeps x/h/u in place (below)
+      if constexpr (sizeof(AT) == 4) {
+        for (int i = tid; i < n; i += kT) {
+          sx[i] = static_cast<AT>(fac * dir[i]);
+          sh[i] = static_cast<AT>(fad * hdg[i]);
+          su[i] = static_cast<AT>(fae * dGrad[i]);
+          vg[i] = static_cast<AT>(grad[i]);
+          vx[i] = static_cast<AT>(dir[i]);
+          vh[i] = static_cast<AT>(hdg[i]);
+          vu[i] = static_cast<AT>(dGrad[i]);
+          newPos[i] = 0.0;
+        }
+      } else {
+        for (int i = tid; i < n; i += kT) {
+          sx[i] = static_cast<AT>(fac * dir[i]);
+          sh[i] = static_cast<AT>(fad * hdg[i]);
+          su[i] = static_cast<AT>(fae * dGrad[i]);
+          newPos[i] = 0.0;
+        }
+      }
       __syncthreads();
-      for (int w = tid; w < n * nSeg; w += kT) {
-        const int    j = w % n, i0 = (w / n) * segLen, i1 = min(n, i0 + segLen);
-        HT*          hc = H + j;
-        const double xj = dir[j], hj = hdg[j], uj = dGrad[j];
-        double       a  = 0.0;
+      for (int wi = tid; wi < n * nSeg; wi += kT) {
+        const int j = wi % n, i0 = (wi / n) * segLen, i1 = min(n, i0 + segLen);
+        HT*       hc = H + j;
+        AT        xj, hj, uj;
+        if constexpr (sizeof(AT) == 4) {
+          xj = vx[j];
+          hj = vh[j];
+          uj = vu[j];
+        } else {
+          xj = dir[j];
+          hj = hdg[j];
+          uj = dGrad[j];
+        }
+        AT a = AT(0);
         if (update) {
 #pragma unroll 4
           for (int i = i0; i < i1; ++i) {
-            const double h = static_cast<double>(hc[static_cast<size_t>(i) * n]) +
-                             ((fac * dir[i]) * xj - (fad * hdg[i]) * hj + (fae * dGrad[i]) * uj);
-            hc[static_cast<size_t>(i) * n] = static_cast<HT>(h);
-            a += h * grad[i];
+            const AT h = hc[static_cast<size_t>(i) * n] + (sx[i] * xj - sh[i] * hj + su[i] * uj);
+            hc[static_cast<size_t>(i) * n] = h;
+            if constexpr (sizeof(AT) == 4) a += h * vg[i];
+            else a += h * grad[i];
           }
         } else {
 #pragma unroll 8
-          for (int i = i0; i < i1; ++i) a += static_cast<double>(hc[static_cast<size_t>(i) * n]) * grad[i];
+          for (int i = i0; i < i1; ++i) {
+            if constexpr (sizeof(AT) == 4) a += hc[static_cast<size_t>(i) * n] * vg[i];
+            else a += hc[static_cast<size_t>(i) * n] * grad[i];
+          }
         }
-        atomicAdd(&newPos[j], -a);
+        atomicAdd(&newPos[j], -static_cast<double>(a));
       }
       __syncthreads();
 #ifdef B200_BFGS_TIMING

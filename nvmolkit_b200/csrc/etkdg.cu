@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
   __shared__ double                     red[kWarps];
   __shared__ int                        nextSlot;
   const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red);
-  double*        ref = sm + 6 * a.maxN;  // ETK reference geometry
+  double*        ref = sm + kBfgsVectors * a.maxN;  // ETK reference geometry
   const int      tid = threadIdx.x;
   for (;;) {
     __syncthreads();
@@ -296,7 +296,7 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     B200_REQUIRE(d_slot_mol && d_slot_atom_start && d_coords && d_ok, "null pointer");
     cudaStream_t s    = asStream(stream);
     const int    maxN = 4 * max_atoms;
-    const size_t smem = static_cast<size_t>(7) * maxN * sizeof(double);
+    const size_t smem = static_cast<size_t>(kBfgsVectors + 1) * maxN * sizeof(double);
     B200_REQUIRE(max_atoms > 0 && smem <= 200 * 1024, "molecule too large for the shared-memory embedder (%d atoms)", max_atoms);
     static bool configured = false;
     if (!configured) {
