@@ -127,7 +127,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   perSm            = perSm > g_bfgsCtasPerSm ? g_bfgsCtasPerSm : perSm;
   int blocks       = smCount() * perSm;
   if (blocks > nConf) blocks = nConf;
-  const size_t       stride = static_cast<size_t>(maxN) * maxN;
+  const size_t       stride = static_cast<size_t>(maxN) * bfgsLd<double>(maxN);
   Scratch<double>    hess(stride * blocks, s);
   Scratch<int>       queue(1, s);
   B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));

@@ -78,7 +78,12 @@ struct BfgsWorkT {
   double* red;                                      // kWarps doubles of shared memory
   double* scratch;                                  // shared memory, 4 * maxN doubles (scaled vectors of the Hessian passes)
 };
-constexpr int kBfgsVectors = 10;  // six working vectors + four scratch vectors of maxN doubles
+constexpr int kBfgsVectors = 10;
+template <class HT>
+__host__ __device__ inline int bfgsLd(int n) {
+  constexpr int per = 128 / static_cast<int>(sizeof(HT));
+  return (n + per - 1) / per * per;
+}  // six working vectors + four scratch vectors of maxN doubles
 using BfgsWork = BfgsWorkT<double>;
 template <class HT = double>
 __device__ __forceinline__ BfgsWorkT<HT> carveWork(double* sm, int maxN, HT* H, double* red) {
@@ -115,6 +120,8 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
   double *pos = w.pos, *grad = w.grad, *dir = w.dir, *newPos = w.newPos, *dGrad = w.dGrad, *hdg = w.hdg, *red = w.red;
   HT*     H   = w.H;
   const int tid = threadIdx.x;
+  // leading dimension of the slab: rows padded to 128 bytes so that every warp access is whole, aligned cache lines
+  const int ld = bfgsLd<HT>(n);
   int       status = 1, iter = 0;
 #ifdef B200_BFGS_TIMING
   long long tim[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -122,9 +129,9 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
 #endif
   for (int restart = 0;; ++restart) {
     __syncthreads();
-    for (size_t i = tid; i < static_cast<size_t>(n) * n; i += kT) H[i] = HT(0);
+    for (size_t i = tid; i < static_cast<size_t>(n) * ld; i += kT) H[i] = HT(0);
     __syncthreads();
-    for (int i = tid; i < n; i += kT) H[static_cast<size_t>(i) * n + i] = HT(1);
+    for (int i = tid; i < n; i += kT) H[static_cast<size_t>(i) * ld + i] = HT(1);
 
     double fp = energyOf<FF>(view, pos, red);
     gradOf<FF>(view, pos, grad, n);
@@ -242,7 +249,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         const HT* hc = H + j;
         AT        a  = AT(0);
 #pragma unroll 8
-        for (int i = i0; i < i1; ++i) a += hc[static_cast<size_t>(i) * n] * vD[i];
+        for (int i = i0; i < i1; ++i) a += hc[static_cast<size_t>(i) * ld] * vD[i];
         atomicAdd(&hdg[j], static_cast<double>(a));
       }
       __syncthreads();
@@ -317,16 +324,16 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         if (update) {
 #pragma unroll 4
           for (int i = i0; i < i1; ++i) {
-            const AT h = hc[static_cast<size_t>(i) * n] + (sx[i] * xj - sh[i] * hj + su[i] * uj);
-            hc[static_cast<size_t>(i) * n] = h;
+            const AT h = hc[static_cast<size_t>(i) * ld] + (sx[i] * xj - sh[i] * hj + su[i] * uj);
+            hc[static_cast<size_t>(i) * ld] = h;
             if constexpr (sizeof(AT) == 4) a += h * vg[i];
             else a += h * grad[i];
           }
         } else {
 #pragma unroll 8
           for (int i = i0; i < i1; ++i) {
-            if constexpr (sizeof(AT) == 4) a += hc[static_cast<size_t>(i) * n] * vg[i];
-            else a += hc[static_cast<size_t>(i) * n] * grad[i];
+            if constexpr (sizeof(AT) == 4) a += hc[static_cast<size_t>(i) * ld] * vg[i];
+            else a += hc[static_cast<size_t>(i) * ld] * grad[i];
           }
         }
         atomicAdd(&newPos[j], -static_cast<double>(a));

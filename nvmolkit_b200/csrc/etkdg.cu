@@ -309,7 +309,7 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     perSm      = perSm > g_bfgsCtasPerSm ? g_bfgsCtasPerSm : perSm;
     int blocks = smCount() * perSm;
     if (blocks > nSlots) blocks = nSlots;
-    const size_t    stride = static_cast<size_t>(maxN) * maxN;
+    const size_t    stride = static_cast<size_t>(maxN) * bfgsLd<float>(maxN);
     Scratch<float>  hess(stride * blocks, s);
     Scratch<int>    queue(1, s);
     B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));

@@ -17,6 +17,8 @@ L = _lib.load()
 buf = (C.c_ulonglong * 8)()
 for name in ("etkdg", "bfgs"):
     getattr(L, f"b200mol_debug_clocks_{name}")(buf)  # reset
+import sys
+if len(sys.argv) > 1: _lib.set_option('bfgs_ctas_per_sm', int(sys.argv[1]))
 r = bench.run_path_b_gpu(flat, mmff, 256, 10, dev, 1, 0)
 print({k: r[k] for k in ("mols_per_s", "phases_ms", "mean_attempts")})
 labels = ["energy evals", "gradient evals", "H*dGrad pass", "H update+dir pass", "iterations", "total in bfgsMinimize"]
