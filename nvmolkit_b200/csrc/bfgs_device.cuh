@@ -236,21 +236,34 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       // shared memory (a few hundred fp64 atomics per pass). With fp32 slabs the whole pass runs in fp32 (no
       // conversions: F2F and fp64 are the slow pipes of this part, profiles/r01_path_b_summary.md).
       using AT         = HT;  // arithmetic type of the Hessian passes = storage type
-      const int nSeg   = min(32, max(1, (4 * kT + n - 1) / n));
-      const int segLen = (n + nSeg - 1) / nSeg;
+      constexpr int kSlots = sizeof(HT) == 4 ? 8 : 4;  // column slots a lane keeps in registers per sweep
       AT*       vD     = reinterpret_cast<AT*>(w.scratch);  // dGrad as AT
       for (int i = tid; i < n; i += kT) {
         hdg[i] = 0.0;
         vD[i]  = static_cast<AT>(dGrad[i]);
       }
       __syncthreads();
-      for (int wi = tid; wi < n * nSeg; wi += kT) {
-        const int j = wi % n, i0 = (wi / n) * segLen, i1 = min(n, i0 + segLen);
-        const HT* hc = H + j;
-        AT        a  = AT(0);
-#pragma unroll 8
-        for (int i = i0; i < i1; ++i) a += hc[static_cast<size_t>(i) * ld] * vD[i];
-        atomicAdd(&hdg[j], static_cast<double>(a));
+      // Row-streaming, column-accumulating: a warp walks whole rows (contiguous, line-aligned loads), each lane keeps
+      // the partial sums of ITS columns (H is symmetric: sum_i H[i][j] v_i = (H v)_j), rows are independent so several
+      // are in flight; the eight warps' partial column sums meet in shared memory. No shuffles, no per-row round trip.
+      {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int c0 = 0; c0 < n; c0 += 32 * kSlots) {  // kSlots column slots per lane per sweep
+          AT acc[kSlots];
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k) acc[k] = AT(0);
+#pragma unroll 2
+          for (int i = warp; i < n; i += kWarps) {
+            const HT* hr = H + static_cast<size_t>(i) * ld + c0 + lane;
+            const AT  vi = vD[i];
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k)
+              if (c0 + lane + 32 * k < n) acc[k] += hr[32 * k] * vi;
+          }
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k)
+            if (c0 + lane + 32 * k < n) atomicAdd(&hdg[c0 + lane + 32 * k], static_cast<double>(acc[k]));
+        }
       }
       __syncthreads();
       B200_T1(2);
@@ -307,36 +320,49 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         }
       }
       __syncthreads();
-      for (int wi = tid; wi < n * nSeg; wi += kT) {
-        const int j = wi % n, i0 = (wi / n) * segLen, i1 = min(n, i0 + segLen);
-        HT*       hc = H + j;
-        AT        xj, hj, uj;
-        if constexpr (sizeof(AT) == 4) {
-          xj = vx[j];
-          hj = vh[j];
-          uj = vu[j];
-        } else {
-          xj = dir[j];
-          hj = hdg[j];
-          uj = dGrad[j];
-        }
-        AT a = AT(0);
-        if (update) {
-#pragma unroll 4
-          for (int i = i0; i < i1; ++i) {
-            const AT h = hc[static_cast<size_t>(i) * ld] + (sx[i] * xj - sh[i] * hj + su[i] * uj);
-            hc[static_cast<size_t>(i) * ld] = h;
-            if constexpr (sizeof(AT) == 4) a += h * vg[i];
-            else a += h * grad[i];
+      {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int c0 = 0; c0 < n; c0 += 32 * kSlots) {
+          AT acc[kSlots], xj[kSlots], hj[kSlots], uj[kSlots];
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k) {
+            const int j = c0 + lane + 32 * k;
+            acc[k]      = AT(0);
+            if constexpr (sizeof(AT) == 4) {
+              xj[k] = j < n ? vx[j] : AT(0);
+              hj[k] = j < n ? vh[j] : AT(0);
+              uj[k] = j < n ? vu[j] : AT(0);
+            } else {
+              xj[k] = j < n ? dir[j] : 0.0;
+              hj[k] = j < n ? hdg[j] : 0.0;
+              uj[k] = j < n ? dGrad[j] : 0.0;
+            }
           }
-        } else {
-#pragma unroll 8
-          for (int i = i0; i < i1; ++i) {
-            if constexpr (sizeof(AT) == 4) a += hc[static_cast<size_t>(i) * ld] * vg[i];
-            else a += hc[static_cast<size_t>(i) * ld] * grad[i];
+#pragma unroll 2
+          for (int i = warp; i < n; i += kWarps) {
+            HT*      hr = H + static_cast<size_t>(i) * ld + c0 + lane;
+            const AT si = sx[i], ti = sh[i], wi2 = su[i];
+            AT       gi;
+            if constexpr (sizeof(AT) == 4) gi = vg[i];
+            else gi = grad[i];
+            if (update) {
+#pragma unroll
+              for (int k = 0; k < kSlots; ++k)
+                if (c0 + lane + 32 * k < n) {
+                  const AT h = hr[32 * k] + (si * xj[k] - ti * hj[k] + wi2 * uj[k]);
+                  hr[32 * k] = h;
+                  acc[k] += h * gi;
+                }
+            } else {
+#pragma unroll
+              for (int k = 0; k < kSlots; ++k)
+                if (c0 + lane + 32 * k < n) acc[k] += hr[32 * k] * gi;
+            }
           }
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k)
+            if (c0 + lane + 32 * k < n) atomicAdd(&newPos[c0 + lane + 32 * k], -static_cast<double>(acc[k]));
         }
-        atomicAdd(&newPos[j], -static_cast<double>(a));
       }
       __syncthreads();
 #ifdef B200_BFGS_TIMING
