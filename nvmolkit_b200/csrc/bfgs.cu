@@ -40,7 +40,7 @@ struct Batch {
 template <class FF>
 __global__ void __launch_bounds__(kT, 4) bfgsKernel(const typename FF::System sys, const typename FF::Params par, const Batch b) {
   extern __shared__ __align__(16) double sm[];
-  __shared__ double                     red[kWarps];
+  __shared__ double                     red[kRed];
   __shared__ int                        nextConf;
   constexpr int                         DIM = FF::kDim;
   const BfgsWork w = carveWork(sm, b.maxN, b.hessWs + static_cast<size_t>(blockIdx.x) * b.hessStride, red);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kT) energyGradKernel(const typename FF::System
                                                      const int32_t* confMol, const int32_t* confAtomStart,
                                                      const double* posIn, double* energy, double* gradOut, int maxN) {
   extern __shared__ __align__(16) double sm[];
-  __shared__ double                     red[kWarps];
+  __shared__ double                     red[kRed];
   constexpr int                         DIM = FF::kDim;
   double*                               pos  = sm;
   double*                               grad = sm + maxN;

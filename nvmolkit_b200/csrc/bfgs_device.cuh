@@ -6,6 +6,7 @@ namespace b200 {
 
 constexpr int kT     = 256;  // threads per CTA
 constexpr int kWarps = kT / 32;
+constexpr int kRed   = kWarps * 6;  // doubles of shared memory behind `red`
 
 __device__ __forceinline__ double warpSum(double v) {
 #pragma unroll
@@ -17,7 +18,7 @@ __device__ __forceinline__ double warpMaxD(double v) {
   for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// Block-wide reductions; every thread receives the same value. `red` is kWarps doubles of shared memory.
+// Block-wide reductions; every thread receives the same value. `red` is kRed doubles of shared memory.
 __device__ __forceinline__ double blockSum(double v, double* red) {
   v = warpSum(v);
   __syncthreads();
@@ -27,6 +28,25 @@ __device__ __forceinline__ double blockSum(double v, double* red) {
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) t += red[w];
   return t;
+}
+// N sums with one barrier pair; `red` holds kRed doubles.
+template <int N>
+__device__ __forceinline__ void blockSumN(double (&v)[N], double* red) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warpSum(v[k]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) red[k * kWarps + (threadIdx.x >> 5)] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += red[k * kWarps + w];
+    v[k] = t;
+  }
 }
 __device__ __forceinline__ double blockMax(double v, double* red) {
   v = warpMaxD(v);
@@ -129,9 +149,8 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
 #endif
   for (int restart = 0;; ++restart) {
     __syncthreads();
-    for (size_t i = tid; i < static_cast<size_t>(n) * ld; i += kT) H[i] = HT(0);
-    __syncthreads();
-    for (int i = tid; i < n; i += kT) H[static_cast<size_t>(i) * ld + i] = HT(1);
+    bool   fresh = true, pending = false;  // H = I (not materialised); no rank-2 update waiting
+    double pfac = 0.0, pfad = 0.0, pfae = 0.0;
 
     double fp = energyOf<FF>(view, pos, red);
     gradOf<FF>(view, pos, grad, n);
@@ -228,148 +247,167 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         break;
       }
       // ---------------- inverse Hessian (bfgs_hessian.cu:37-239) ----------------
+      // ONE sweep over the UPPER TRIANGLE of H per iteration. The reference makes three passes over the full matrix
+      // (H*dGrad; rank-2 update; -H*grad). Here the rank-2 update of iteration k stays PENDING (three vectors, three
+      // scalars) and is applied by the sweep of iteration k+1, which in the same pass accumulates H*dGrad and H*grad;
+      // the next direction follows from H*grad and the pending vectors by O(n) algebra:
+      //   H' g = H g + fac x (x.g) - fad h (h.g) + fae u (u.g),  u = fac x - fad h.
+      // H is symmetric, so only j >= i is stored/streamed: element (i,j) feeds column sums (lane-private registers)
+      // and row sums (one shuffle tree per row). Traffic per iteration: n^2/2 read + n^2/2 written instead of
+      // 2 n^2 read + n^2 written. A fresh H (= I) is never materialised: the first sweep with a pending update writes it.
       B200_T0();
-      // hdg = H * dGrad, thread per COLUMN (H is symmetric): every load is coalesced along a row, consecutive rows are
-      // independent loads (deep memory-level parallelism) and no cross-lane reduction is needed. The warp-per-row form
-      // exposed one L2 round trip + a shuffle tree per row and was 78 % of the embedder's time (profiles/).
-      // Work item = (column j, row segment): items are spread evenly over the CTA whatever n is; partial sums meet in
-      // shared memory (a few hundred fp64 atomics per pass). With fp32 slabs the whole pass runs in fp32 (no
-      // conversions: F2F and fp64 are the slow pipes of this part, profiles/r01_path_b_summary.md).
-      using AT         = HT;  // arithmetic type of the Hessian passes = storage type
-      constexpr int kSlots = sizeof(HT) == 4 ? 8 : 4;  // column slots a lane keeps in registers per sweep
-      AT*       vD     = reinterpret_cast<AT*>(w.scratch);  // dGrad as AT
-      for (int i = tid; i < n; i += kT) {
-        hdg[i] = 0.0;
-        vD[i]  = static_cast<AT>(dGrad[i]);
-      }
-      __syncthreads();
-      // Row-streaming, column-accumulating: a warp walks whole rows (contiguous, line-aligned loads), each lane keeps
-      // the partial sums of ITS columns (H is symmetric: sum_i H[i][j] v_i = (H v)_j), rows are independent so several
-      // are in flight; the eight warps' partial column sums meet in shared memory. No shuffles, no per-row round trip.
-      {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int c0 = 0; c0 < n; c0 += 32 * kSlots) {  // kSlots column slots per lane per sweep
-          AT acc[kSlots];
-#pragma unroll
-          for (int k = 0; k < kSlots; ++k) acc[k] = AT(0);
-#pragma unroll 2
-          for (int i = warp; i < n; i += kWarps) {
-            const HT* hr = H + static_cast<size_t>(i) * ld + c0 + lane;
-            const AT  vi = vD[i];
-#pragma unroll
-            for (int k = 0; k < kSlots; ++k)
-              if (c0 + lane + 32 * k < n) acc[k] += hr[32 * k] * vi;
-          }
-#pragma unroll
-          for (int k = 0; k < kSlots; ++k)
-            if (c0 + lane + 32 * k < n) atomicAdd(&hdg[c0 + lane + 32 * k], static_cast<double>(acc[k]));
-        }
-      }
-      __syncthreads();
-      B200_T1(2);
-      double f1 = 0, f2 = 0, f3 = 0, f4 = 0;
-      for (int i = tid; i < n; i += kT) {
-        f1 += dGrad[i] * dir[i];
-        f2 += dGrad[i] * hdg[i];
-        f3 += dGrad[i] * dGrad[i];
-        f4 += dir[i] * dir[i];
-      }
-      double       fac      = blockSum(f1, red);
-      const double fae      = blockSum(f2, red);
-      const double sumDGrad = blockSum(f3, red);
-      const double sumXi    = blockSum(f4, red);
-      const bool   update   = fac > sqrt(EPS * sumDGrad * sumXi);
-      double       fad      = 0.0;
-      if (update) {
-        fac = 1.0 / fac;
-        fad = 1.0 / fae;
-        for (int i = tid; i < n; i += kT) dGrad[i] = fac * dir[i] - fad * hdg[i];
-      }
-      __syncthreads();
-      // fused: rank-2 update of row + dot with the new gradient -> next direction (into newPos, free here)
-      const long long tU_ = clock64();
-      (void)tU_;
-      // per-row scalars of the rank-2 update, staged in newPos (free here) as fac*xi_i | hdg holds fad*hdg_i after scaling
-      // thread per column: H[i][j] += (fac xi_i) xi_j - (fad hdg_i) hdg_j + (fae u_i) u_j ; a_j += H[i][j] g_i
-      // scaled row vectors (index i) and plain column vectors (index j), in the arithmetic type:
-      //   H[i][j] += sx_i x_j - sh_i h_j + su_i u_j ,  a_j += H[i][j] g_i        (3 + 1 FMAs per element)
-      AT* sx = reinterpret_cast<AT*>(w.scratch);
-      AT* sh = sx + n;
-      AT* su = sh + n;
-      AT* vg = su + n;
-      AT* vx = vg + n;
-      AT* vh = vx + n;
-      AT* vu = vh + n;  // 7 n elements of AT <= 4 n doubles when AT = float; AT = double keeps x/h/u in place (below)
-      if constexpr (sizeof(AT) == 4) {
+      using AT             = HT;  // arithmetic type of the sweep = storage type
+      constexpr int kSlots = sizeof(HT) == 4 ? 4 : 2;  // column slots a lane keeps in registers per sweep
+      AT*           px     = reinterpret_cast<AT*>(w.scratch);  // pending x (step), h (H dGrad), u
+      AT*           ph     = px + n;
+      AT*           pu     = ph + n;
+      double*       hgv    = newPos;  // H * grad (newPos is free here)
+      if (fresh && !pending) {
         for (int i = tid; i < n; i += kT) {
-          sx[i] = static_cast<AT>(fac * dir[i]);
-          sh[i] = static_cast<AT>(fad * hdg[i]);
-          su[i] = static_cast<AT>(fae * dGrad[i]);
-          vg[i] = static_cast<AT>(grad[i]);
-          vx[i] = static_cast<AT>(dir[i]);
-          vh[i] = static_cast<AT>(hdg[i]);
-          vu[i] = static_cast<AT>(dGrad[i]);
-          newPos[i] = 0.0;
+          hdg[i] = dGrad[i];
+          hgv[i] = grad[i];
         }
+        __syncthreads();
       } else {
-        for (int i = tid; i < n; i += kT) {
-          sx[i] = static_cast<AT>(fac * dir[i]);
-          sh[i] = static_cast<AT>(fad * hdg[i]);
-          su[i] = static_cast<AT>(fae * dGrad[i]);
-          newPos[i] = 0.0;
+        const AT *vD, *vG;
+        if constexpr (sizeof(AT) == 4) {
+          AT* cD = pu + n;
+          AT* cG = cD + n;
+          for (int i = tid; i < n; i += kT) {
+            cD[i] = static_cast<AT>(dGrad[i]);
+            cG[i] = static_cast<AT>(grad[i]);
+          }
+          vD = cD;
+          vG = cG;
+        } else {
+          vD = dGrad;
+          vG = grad;
         }
-      }
-      __syncthreads();
-      {
+        for (int i = tid; i < n; i += kT) {
+          hdg[i] = 0.0;
+          hgv[i] = 0.0;
+        }
+        __syncthreads();
         const int lane = tid & 31, warp = tid >> 5;
+        const AT  cfac = static_cast<AT>(pfac), cfad = static_cast<AT>(pfad), cfae = static_cast<AT>(pfae);
         for (int c0 = 0; c0 < n; c0 += 32 * kSlots) {
-          AT acc[kSlots], xj[kSlots], hj[kSlots], uj[kSlots];
+          AT aD[kSlots], aG[kSlots], xj[kSlots], hj[kSlots], uj[kSlots], dj[kSlots], gj[kSlots];
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k) {
+            const int  j  = c0 + lane + 32 * k;
+            const bool in = j < n;
+            aD[k] = aG[k] = AT(0);
+            xj[k] = (in && pending) ? px[j] : AT(0);
+            hj[k] = (in && pending) ? ph[j] : AT(0);
+            uj[k] = (in && pending) ? pu[j] : AT(0);
+            dj[k] = in ? vD[j] : AT(0);
+            gj[k] = in ? vG[j] : AT(0);
+          }
+          const int rowEnd = min(n, c0 + 32 * kSlots);  // rows below have no element with j >= i in these columns
+          for (int ib = warp; ib < rowEnd; ib += 2 * kWarps) {
+            AT h[2][kSlots];
+            // all loads of two rows first (independent, in flight together), then the arithmetic and the stores
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int i  = ib + r * kWarps;
+              const HT* hr = H + static_cast<size_t>(i) * ld + c0 + lane;
+#pragma unroll
+              for (int k = 0; k < kSlots; ++k) {
+                const int j = c0 + lane + 32 * k;
+                h[r][k]     = (j == i) ? AT(1) : AT(0);
+                if (!fresh && i < rowEnd && j >= i && j < n) h[r][k] = hr[32 * k];
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int i = ib + r * kWarps;
+              if (i >= rowEnd) break;
+              HT*      hr = H + static_cast<size_t>(i) * ld + c0 + lane;
+              const AT di = vD[i], gi = vG[i];
+              AT       si = AT(0), ti = AT(0), wi = AT(0);
+              if (pending) {
+                si = cfac * px[i];
+                ti = cfad * ph[i];
+                wi = cfae * pu[i];
+              }
+              AT rD = AT(0), rG = AT(0);
+#pragma unroll
+              for (int k = 0; k < kSlots; ++k) {
+                const int j = c0 + lane + 32 * k;
+                if (j >= i && j < n) {
+                  AT v = h[r][k];
+                  if (pending) {
+                    v += (si * xj[k] - ti * hj[k] + wi * uj[k]);
+                    hr[32 * k] = v;
+                  }
+                  aD[k] += v * di;
+                  aG[k] += v * gi;
+                  if (j > i) {
+                    rD += v * dj[k];
+                    rG += v * gj[k];
+                  }
+                }
+              }
+#pragma unroll
+              for (int o = 16; o; o >>= 1) {
+                rD += __shfl_xor_sync(0xffffffffu, rD, o);
+                rG += __shfl_xor_sync(0xffffffffu, rG, o);
+              }
+              if (lane == 0) {
+                atomicAdd(&hdg[i], static_cast<double>(rD));
+                atomicAdd(&hgv[i], static_cast<double>(rG));
+              }
+            }
+          }
 #pragma unroll
           for (int k = 0; k < kSlots; ++k) {
             const int j = c0 + lane + 32 * k;
-            acc[k]      = AT(0);
-            if constexpr (sizeof(AT) == 4) {
-              xj[k] = j < n ? vx[j] : AT(0);
-              hj[k] = j < n ? vh[j] : AT(0);
-              uj[k] = j < n ? vu[j] : AT(0);
-            } else {
-              xj[k] = j < n ? dir[j] : 0.0;
-              hj[k] = j < n ? hdg[j] : 0.0;
-              uj[k] = j < n ? dGrad[j] : 0.0;
+            if (j < n) {
+              atomicAdd(&hdg[j], static_cast<double>(aD[k]));
+              atomicAdd(&hgv[j], static_cast<double>(aG[k]));
             }
           }
-#pragma unroll 2
-          for (int i = warp; i < n; i += kWarps) {
-            HT*      hr = H + static_cast<size_t>(i) * ld + c0 + lane;
-            const AT si = sx[i], ti = sh[i], wi2 = su[i];
-            AT       gi;
-            if constexpr (sizeof(AT) == 4) gi = vg[i];
-            else gi = grad[i];
-            if (update) {
-#pragma unroll
-              for (int k = 0; k < kSlots; ++k)
-                if (c0 + lane + 32 * k < n) {
-                  const AT h = hr[32 * k] + (si * xj[k] - ti * hj[k] + wi2 * uj[k]);
-                  hr[32 * k] = h;
-                  acc[k] += h * gi;
-                }
-            } else {
-#pragma unroll
-              for (int k = 0; k < kSlots; ++k)
-                if (c0 + lane + 32 * k < n) acc[k] += hr[32 * k] * gi;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < kSlots; ++k)
-            if (c0 + lane + 32 * k < n) atomicAdd(&newPos[c0 + lane + 32 * k], -static_cast<double>(acc[k]));
         }
+        if (pending) fresh = false;
+        __syncthreads();
       }
-      __syncthreads();
+      B200_T1(2);
+      double f[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = tid; i < n; i += kT) {
+        f[0] += dGrad[i] * dir[i];
+        f[1] += dGrad[i] * hdg[i];
+        f[2] += dGrad[i] * dGrad[i];
+        f[3] += dir[i] * dir[i];
+        f[4] += dir[i] * grad[i];
+        f[5] += hdg[i] * grad[i];
+      }
+      blockSumN<6>(f, red);
+      double       fac      = f[0];
+      const double fae      = f[1];
+      const bool   update   = fac > sqrt(EPS * f[2] * f[3]);
+      if (update) {
+        fac             = 1.0 / fac;
+        const double fad = 1.0 / fae;
+        const double xg = f[4], hg = f[5], ug = fac * xg - fad * hg;
+        for (int i = tid; i < n; i += kT) {
+          const double x = dir[i], hd = hdg[i];
+          const double u = fac * x - fad * hd;
+          px[i]          = static_cast<AT>(x);
+          ph[i]          = static_cast<AT>(hd);
+          pu[i]          = static_cast<AT>(u);
+          dir[i]         = -(hgv[i] + (fac * xg) * x - (fad * hg) * hd + (fae * ug) * u);
+        }
+        pending = true;
+        pfac    = fac;
+        pfad    = fad;
+        pfae    = fae;
+      } else {
+        for (int i = tid; i < n; i += kT) dir[i] = -hgv[i];
+        pending = false;
+      }
 #ifdef B200_BFGS_TIMING
-      tim[3] += clock64() - tU_;
       tim[4] += 1;
 #endif
-      for (int i = tid; i < n; i += kT) dir[i] = newPos[i];
       __syncthreads();
     }
     if (status == 0 || restart >= maxRestarts) break;

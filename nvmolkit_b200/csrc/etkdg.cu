@@ -184,7 +184,7 @@ __device__ unsigned finalChecks(const EmbedArgs& a, int mol, const double* pos, 
 
 __global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
-  __shared__ double                     red[kWarps];
+  __shared__ double                     red[kRed];
   __shared__ int                        nextSlot;
   const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red);
   double*        ref = sm + kBfgsVectors * a.maxN;  // ETK reference geometry
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
 // Check-only: evaluates stages 1 (energy per atom), 2, 3, 5 (planarity), 6-10 on given 4-D coordinates.
 __global__ void __launch_bounds__(kT) etkdgCheckKernel(const EmbedArgs a, const double* pos4, uint32_t* masks) {
   extern __shared__ __align__(16) double sm[];
-  __shared__ double                     red[kWarps];
+  __shared__ double                     red[kRed];
   for (int slot = blockIdx.x; slot < a.nSlots; slot += gridDim.x) {
     const int mol = a.slotMol[slot];
     const int nA  = a.dg.atomCounts[mol];
