@@ -133,6 +133,115 @@ static inline void readBfgsClocks(unsigned long long* out) {
 #define B200_T1(slot)
 #endif
 
+// One sweep over the upper triangle (j >= i) of the inverse Hessian of one conformer, by the whole CTA:
+//   H[i][j] (+)= fac x_i x_j - fad h_i h_j + fae u_i u_j   (if `pending`; a `fresh` H is the identity and is not read)
+//   outD += H d,  outG += H g                               (both symmetric products, from the stored half only)
+// A lane owns V = 16/sizeof(HT) consecutive columns of a 32*V-wide chunk: one 128-bit load and store per row, the
+// column values and column sums stay in registers for all rows of the chunk, the row sums of FOUR rows are reduced
+// together by one exchange-halving butterfly (9 shuffles for 8 values instead of 40). Columns [n, ld) hold zeros, so
+// only the chunk that contains the diagonal needs per-element masks. The sweep is issue-bound, not latency-bound
+// (profiles/r01_path_b_summary.md), hence the instruction diet.
+template <class HT>
+__device__ __noinline__ void hessianSweep(HT* __restrict__ H, int ld, int n, bool fresh, bool pending, HT cfac, HT cfad,
+                                             HT cfae, const HT* px, const HT* ph, const HT* pu, const HT* vD, const HT* vG,
+                                             double* outD, double* outG) {
+  constexpr int V  = 16 / static_cast<int>(sizeof(HT));
+  constexpr int CW = 32 * V;
+  struct alignas(16) Pack {
+    HT e[V];
+  };
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < n; c0 += CW) {
+    const int  cb     = c0 + V * lane;  // first column of this lane
+    const bool laneIn = cb < ld;
+    HT         aD[V], aG[V], xj[V], hj[V], uj[V], dj[V], gj[V];
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      const bool in = cb + t < n;
+      aD[t] = aG[t] = HT(0);
+      xj[t] = (in && pending) ? px[cb + t] : HT(0);
+      hj[t] = (in && pending) ? ph[cb + t] : HT(0);
+      uj[t] = (in && pending) ? pu[cb + t] : HT(0);
+      dj[t] = in ? vD[cb + t] : HT(0);
+      gj[t] = in ? vG[cb + t] : HT(0);
+    }
+    const int rowEnd = min(n, c0 + CW);  // rows below have no element with j >= i in this chunk
+    for (int i0 = 4 * warp; i0 < rowEnd; i0 += 4 * kWarps) {
+      const bool diag = i0 >= c0;  // the four rows' diagonal elements lie in this chunk (CW is a multiple of 4)
+      HT         r[8];             // row sums: [0..3] with d, [4..7] with g
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r[q] = r[q + 4] = HT(0);
+        const int i     = i0 + q;
+        if (i >= rowEnd) continue;
+        Pack* hp = reinterpret_cast<Pack*>(H + static_cast<size_t>(i) * ld + cb);
+        Pack  p;
+        if (!fresh) {
+          if (laneIn) p = *hp;
+        } else {
+#pragma unroll
+          for (int t = 0; t < V; ++t) p.e[t] = (cb + t == i) ? HT(1) : HT(0);
+        }
+        const HT di = vD[i], gi = vG[i];
+        if (pending) {
+          const HT si = cfac * px[i], ti = cfad * ph[i], wi = cfae * pu[i];
+#pragma unroll
+          for (int t = 0; t < V; ++t) p.e[t] += (si * xj[t] - ti * hj[t] + wi * uj[t]);
+        }
+        if (diag) {
+#pragma unroll
+          for (int t = 0; t < V; ++t) p.e[t] = (cb + t >= i) ? p.e[t] : HT(0);
+        }
+        if (pending && laneIn) *hp = p;
+        if (!laneIn) {
+#pragma unroll
+          for (int t = 0; t < V; ++t) p.e[t] = HT(0);
+        }
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          aD[t] += p.e[t] * di;
+          aG[t] += p.e[t] * gi;
+        }
+        if (diag) {
+#pragma unroll
+          for (int t = 0; t < V; ++t) {
+            const HT v = (cb + t > i) ? p.e[t] : HT(0);
+            r[q] += v * dj[t];
+            r[q + 4] += v * gj[t];
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < V; ++t) {
+            r[q] += p.e[t] * dj[t];
+            r[q + 4] += p.e[t] * gj[t];
+          }
+        }
+      }
+      // eight sums over the warp: halve the value set at each of the first three exchange steps
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+      HT         s4[4], s2[2];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s4[k] = (b4 ? r[k + 4] : r[k]) + __shfl_xor_sync(0xffffffffu, b4 ? r[k] : r[k + 4], 16);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) s2[k] = (b3 ? s4[k + 2] : s4[k]) + __shfl_xor_sync(0xffffffffu, b3 ? s4[k] : s4[k + 2], 8);
+      HT s1 = (b2 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? s2[0] : s2[1], 4);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      // lane 16 a + 8 b + 4 c holds value index 4 a + 2 b + c : a selects g over d, (2 b + c) the row of the four
+      if ((lane & 3) == 0) {
+        const int i = i0 + ((lane >> 2) & 3);
+        if (i < rowEnd) atomicAdd(&(b4 ? outG : outD)[i], static_cast<double>(s1));
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < V; ++t)
+      if (cb + t < n) {
+        atomicAdd(&outD[cb + t], static_cast<double>(aD[t]));
+        atomicAdd(&outG[cb + t], static_cast<double>(aG[t]));
+      }
+  }
+}
+
 template <class FF, class HT = double>
 __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWorkT<HT>& w, int n, int maxIters,
                                     double gradTol, bool scaleGrads, int maxRestarts) {
@@ -257,7 +366,6 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       // 2 n^2 read + n^2 written. A fresh H (= I) is never materialised: the first sweep with a pending update writes it.
       B200_T0();
       using AT             = HT;  // arithmetic type of the sweep = storage type
-      constexpr int kSlots = sizeof(HT) == 4 ? 4 : 2;  // column slots a lane keeps in registers per sweep
       AT*           px     = reinterpret_cast<AT*>(w.scratch);  // pending x (step), h (H dGrad), u
       AT*           ph     = px + n;
       AT*           pu     = ph + n;
@@ -288,86 +396,8 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
           hgv[i] = 0.0;
         }
         __syncthreads();
-        const int lane = tid & 31, warp = tid >> 5;
-        const AT  cfac = static_cast<AT>(pfac), cfad = static_cast<AT>(pfad), cfae = static_cast<AT>(pfae);
-        for (int c0 = 0; c0 < n; c0 += 32 * kSlots) {
-          AT aD[kSlots], aG[kSlots], xj[kSlots], hj[kSlots], uj[kSlots], dj[kSlots], gj[kSlots];
-#pragma unroll
-          for (int k = 0; k < kSlots; ++k) {
-            const int  j  = c0 + lane + 32 * k;
-            const bool in = j < n;
-            aD[k] = aG[k] = AT(0);
-            xj[k] = (in && pending) ? px[j] : AT(0);
-            hj[k] = (in && pending) ? ph[j] : AT(0);
-            uj[k] = (in && pending) ? pu[j] : AT(0);
-            dj[k] = in ? vD[j] : AT(0);
-            gj[k] = in ? vG[j] : AT(0);
-          }
-          const int rowEnd = min(n, c0 + 32 * kSlots);  // rows below have no element with j >= i in these columns
-          for (int ib = warp; ib < rowEnd; ib += 2 * kWarps) {
-            AT h[2][kSlots];
-            // all loads of two rows first (independent, in flight together), then the arithmetic and the stores
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const int i  = ib + r * kWarps;
-              const HT* hr = H + static_cast<size_t>(i) * ld + c0 + lane;
-#pragma unroll
-              for (int k = 0; k < kSlots; ++k) {
-                const int j = c0 + lane + 32 * k;
-                h[r][k]     = (j == i) ? AT(1) : AT(0);
-                if (!fresh && i < rowEnd && j >= i && j < n) h[r][k] = hr[32 * k];
-              }
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const int i = ib + r * kWarps;
-              if (i >= rowEnd) break;
-              HT*      hr = H + static_cast<size_t>(i) * ld + c0 + lane;
-              const AT di = vD[i], gi = vG[i];
-              AT       si = AT(0), ti = AT(0), wi = AT(0);
-              if (pending) {
-                si = cfac * px[i];
-                ti = cfad * ph[i];
-                wi = cfae * pu[i];
-              }
-              AT rD = AT(0), rG = AT(0);
-#pragma unroll
-              for (int k = 0; k < kSlots; ++k) {
-                const int j = c0 + lane + 32 * k;
-                if (j >= i && j < n) {
-                  AT v = h[r][k];
-                  if (pending) {
-                    v += (si * xj[k] - ti * hj[k] + wi * uj[k]);
-                    hr[32 * k] = v;
-                  }
-                  aD[k] += v * di;
-                  aG[k] += v * gi;
-                  if (j > i) {
-                    rD += v * dj[k];
-                    rG += v * gj[k];
-                  }
-                }
-              }
-#pragma unroll
-              for (int o = 16; o; o >>= 1) {
-                rD += __shfl_xor_sync(0xffffffffu, rD, o);
-                rG += __shfl_xor_sync(0xffffffffu, rG, o);
-              }
-              if (lane == 0) {
-                atomicAdd(&hdg[i], static_cast<double>(rD));
-                atomicAdd(&hgv[i], static_cast<double>(rG));
-              }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < kSlots; ++k) {
-            const int j = c0 + lane + 32 * k;
-            if (j < n) {
-              atomicAdd(&hdg[j], static_cast<double>(aD[k]));
-              atomicAdd(&hgv[j], static_cast<double>(aG[k]));
-            }
-          }
-        }
+        hessianSweep<HT>(H, ld, n, fresh, pending, static_cast<AT>(pfac), static_cast<AT>(pfad), static_cast<AT>(pfae), px, ph, pu,
+                         vD, vG, hdg, hgv);
         if (pending) fresh = false;
         __syncthreads();
       }
