@@ -15,7 +15,7 @@
 #include "profile.cuh"
 
 namespace b200 {
-int g_bfgsCtasPerSm = 4;  // resident minimisation CTAs per SM (option "bfgs_ctas_per_sm")
+int g_bfgsCtasPerSm = kMinCtas;  // resident minimisation CTAs per SM (option "bfgs_ctas_per_sm")
 namespace {
 
 struct Batch {
@@ -38,7 +38,7 @@ struct Batch {
 };
 
 template <class FF>
-__global__ void __launch_bounds__(kT, 4) bfgsKernel(const typename FF::System sys, const typename FF::Params par, const Batch b) {
+__global__ void __launch_bounds__(kT, kMinCtas) bfgsKernel(const typename FF::System sys, const typename FF::Params par, const Batch b) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kRed];
   __shared__ int                        nextConf;

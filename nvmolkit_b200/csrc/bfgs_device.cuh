@@ -1,11 +1,17 @@
 // Device-side BFGS over a flattened force field for ONE conformer held in shared memory (see bfgs.cu for the design).
 #pragma once
+#include <type_traits>
+
 #include "ff.cuh"
 
 namespace b200 {
 
 constexpr int kT     = 256;  // threads per CTA
 constexpr int kWarps = kT / 32;
+#ifndef B200_BFGS_MIN_CTAS
+#define B200_BFGS_MIN_CTAS 3
+#endif
+constexpr int kMinCtas = B200_BFGS_MIN_CTAS;  // resident CTAs per SM the minimiser kernels are compiled for (register cap)
 constexpr int kRed   = kWarps * 6;  // doubles of shared memory behind `red`
 
 __device__ __forceinline__ double warpSum(double v) {
@@ -141,10 +147,9 @@ static inline void readBfgsClocks(unsigned long long* out) {
 // together by one exchange-halving butterfly (9 shuffles for 8 values instead of 40). Columns [n, ld) hold zeros, so
 // only the chunk that contains the diagonal needs per-element masks. The sweep is issue-bound, not latency-bound
 // (profiles/r01_path_b_summary.md), hence the instruction diet.
-template <class HT>
-__device__ __noinline__ void hessianSweep(HT* __restrict__ H, int ld, int n, bool fresh, bool pending, HT cfac, HT cfad,
-                                             HT cfae, const HT* px, const HT* ph, const HT* pu, const HT* vD, const HT* vG,
-                                             double* outD, double* outG) {
+template <class HT, bool FRESH, bool PENDING>
+__device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT cfac, HT cfad, HT cfae, const HT* px, const HT* ph,
+                                           const HT* pu, const HT* vD, const HT* vG, double* outD, double* outG) {
   constexpr int V  = 16 / static_cast<int>(sizeof(HT));
   constexpr int CW = 32 * V;
   struct alignas(16) Pack {
@@ -159,63 +164,54 @@ __device__ __noinline__ void hessianSweep(HT* __restrict__ H, int ld, int n, boo
     for (int t = 0; t < V; ++t) {
       const bool in = cb + t < n;
       aD[t] = aG[t] = HT(0);
-      xj[t] = (in && pending) ? px[cb + t] : HT(0);
-      hj[t] = (in && pending) ? ph[cb + t] : HT(0);
-      uj[t] = (in && pending) ? pu[cb + t] : HT(0);
+      xj[t] = (in && PENDING) ? px[cb + t] : HT(0);
+      hj[t] = (in && PENDING) ? ph[cb + t] : HT(0);
+      uj[t] = (in && PENDING) ? pu[cb + t] : HT(0);
       dj[t] = in ? vD[cb + t] : HT(0);
       gj[t] = in ? vG[cb + t] : HT(0);
     }
     const int rowEnd = min(n, c0 + CW);  // rows below have no element with j >= i in this chunk
-    for (int i0 = 4 * warp; i0 < rowEnd; i0 += 4 * kWarps) {
-      const bool diag = i0 >= c0;  // the four rows' diagonal elements lie in this chunk (CW is a multiple of 4)
-      HT         r[8];             // row sums: [0..3] with d, [4..7] with g
+    auto      batch  = [&](int i0, auto diagTag) {
+      constexpr bool DIAG = decltype(diagTag)::value;  // the four rows' diagonal elements lie in this chunk
+      Pack           pk[4];
+      // the four rows' loads first: they are independent, and the sweep is bound by memory latency (HBM-resident slabs)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        r[q] = r[q + 4] = HT(0);
-        const int i     = i0 + q;
-        if (i >= rowEnd) continue;
-        Pack* hp = reinterpret_cast<Pack*>(H + static_cast<size_t>(i) * ld + cb);
-        Pack  p;
-        if (!fresh) {
-          if (laneIn) p = *hp;
-        } else {
+        const int i = i0 + q;
 #pragma unroll
-          for (int t = 0; t < V; ++t) p.e[t] = (cb + t == i) ? HT(1) : HT(0);
-        }
-        const HT di = vD[i], gi = vG[i];
-        if (pending) {
-          const HT si = cfac * px[i], ti = cfad * ph[i], wi = cfae * pu[i];
+        for (int t = 0; t < V; ++t) pk[q].e[t] = (FRESH && cb + t == i) ? HT(1) : HT(0);
+        if constexpr (!FRESH)
+          if (laneIn && i < rowEnd) pk[q] = *reinterpret_cast<const Pack*>(H + static_cast<size_t>(i) * ld + cb);
+      }
+      HT r[8];  // row sums: [0..3] with d, [4..7] with g
 #pragma unroll
-          for (int t = 0; t < V; ++t) p.e[t] += (si * xj[t] - ti * hj[t] + wi * uj[t]);
-        }
-        if (diag) {
+      for (int q = 0; q < 4; ++q) {
+        const int  i  = i0 + q;
+        const bool ok = i < rowEnd;  // rows past the end contribute zeros and are not stored
+        const HT   di = ok ? vD[i] : HT(0), gi = ok ? vG[i] : HT(0);
+        if constexpr (PENDING) {
+          const HT si = ok ? cfac * px[i] : HT(0), ti = ok ? cfad * ph[i] : HT(0), wi = ok ? cfae * pu[i] : HT(0);
 #pragma unroll
-          for (int t = 0; t < V; ++t) p.e[t] = (cb + t >= i) ? p.e[t] : HT(0);
+          for (int t = 0; t < V; ++t) pk[q].e[t] += (si * xj[t] - ti * hj[t] + wi * uj[t]);
         }
-        if (pending && laneIn) *hp = p;
-        if (!laneIn) {
+        if constexpr (DIAG) {
 #pragma unroll
-          for (int t = 0; t < V; ++t) p.e[t] = HT(0);
+          for (int t = 0; t < V; ++t) pk[q].e[t] = (cb + t >= i) ? pk[q].e[t] : HT(0);
         }
+        if constexpr (PENDING)
+          if (laneIn && ok) *reinterpret_cast<Pack*>(H + static_cast<size_t>(i) * ld + cb) = pk[q];
+        HT rd = HT(0), rg = HT(0);
 #pragma unroll
         for (int t = 0; t < V; ++t) {
-          aD[t] += p.e[t] * di;
-          aG[t] += p.e[t] * gi;
+          const HT v = pk[q].e[t];
+          aD[t] += v * di;
+          aG[t] += v * gi;
+          const HT vs = (!DIAG || cb + t > i) ? v : HT(0);
+          rd += vs * dj[t];
+          rg += vs * gj[t];
         }
-        if (diag) {
-#pragma unroll
-          for (int t = 0; t < V; ++t) {
-            const HT v = (cb + t > i) ? p.e[t] : HT(0);
-            r[q] += v * dj[t];
-            r[q + 4] += v * gj[t];
-          }
-        } else {
-#pragma unroll
-          for (int t = 0; t < V; ++t) {
-            r[q] += p.e[t] * dj[t];
-            r[q + 4] += p.e[t] * gj[t];
-          }
-        }
+        r[q]     = rd;
+        r[q + 4] = rg;
       }
       // eight sums over the warp: halve the value set at each of the first three exchange steps
       const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
@@ -232,7 +228,11 @@ __device__ __noinline__ void hessianSweep(HT* __restrict__ H, int ld, int n, boo
         const int i = i0 + ((lane >> 2) & 3);
         if (i < rowEnd) atomicAdd(&(b4 ? outG : outD)[i], static_cast<double>(s1));
       }
-    }
+    };
+    // rows above the chunk's diagonal block: no masks; rows inside it (CW is a multiple of 4): masked
+    int i0 = 4 * warp;
+    for (; i0 < min(c0, rowEnd); i0 += 4 * kWarps) batch(i0, std::false_type{});
+    for (; i0 < rowEnd; i0 += 4 * kWarps) batch(i0, std::true_type{});
 #pragma unroll
     for (int t = 0; t < V; ++t)
       if (cb + t < n) {
@@ -240,6 +240,13 @@ __device__ __noinline__ void hessianSweep(HT* __restrict__ H, int ld, int n, boo
         atomicAdd(&outG[cb + t], static_cast<double>(aG[t]));
       }
   }
+}
+template <class HT>
+__device__ __forceinline__ void hessianSweep(HT* H, int ld, int n, bool fresh, bool pending, HT cfac, HT cfad, HT cfae, const HT* px,
+                                             const HT* ph, const HT* pu, const HT* vD, const HT* vG, double* outD, double* outG) {
+  if (!fresh && pending) hessianSweepT<HT, false, true>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG);
+  else if (fresh) hessianSweepT<HT, true, true>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG);  // pending by construction
+  else hessianSweepT<HT, false, false>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG);
 }
 
 template <class FF, class HT = double>

@@ -182,7 +182,7 @@ __device__ unsigned finalChecks(const EmbedArgs& a, int mol, const double* pos, 
   return m;
 }
 
-__global__ void __launch_bounds__(kT, 4) etkdgKernel(const EmbedArgs a) {
+__global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kRed];
   __shared__ int                        nextSlot;
