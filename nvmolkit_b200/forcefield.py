@@ -39,6 +39,17 @@ def _system_struct(kind: str):
 SYSTEM_STRUCT = {k: _system_struct(k) for k in LAYOUT}
 
 
+def _diagonal_order(starts: np.ndarray, idx: np.ndarray, par: np.ndarray):
+    """Order each molecule's pair terms by (|j - i|, min(i, j)): consecutive terms (one warp's worth) then touch
+    distinct atoms, so the shared-memory gradient atomics of a warp do not collide. A pair list sorted by (i, j) makes 32
+    lanes add into the SAME atom and serialises the fp64 CAS loops (profiles/r01_path_b_summary.md). Any order is
+    correct; this one is fast. Energies change only by summation order."""
+    mol = np.repeat(np.arange(len(starts) - 1), np.diff(starts))
+    a, b = idx[:, 0].astype(np.int32), idx[:, 1].astype(np.int32)
+    order = np.lexsort((np.minimum(a, b), np.abs(b - a), mol))
+    return np.ascontiguousarray(idx[order]), np.ascontiguousarray(par[order])
+
+
 @dataclass
 class FlatSystem:
     kind: str
@@ -57,6 +68,8 @@ class FlatSystem:
             par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, p) if p else np.zeros((len(idx), 0))
             if len(starts) != n_mols + 1 or starts[-1] != len(idx) or (p and len(par) != len(idx)):
                 raise ValueError(f"inconsistent term table '{name}'")
+            if k == 2 and len(idx):
+                idx, par = _diagonal_order(starts, idx, par)
             fixed[name] = (starts, idx, par)
         self.tables = fixed
 
