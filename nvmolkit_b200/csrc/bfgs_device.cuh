@@ -164,9 +164,10 @@ __device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT
     for (int t = 0; t < V; ++t) {
       const bool in = cb + t < n;
       aD[t] = aG[t] = HT(0);
-      xj[t] = (in && PENDING) ? px[cb + t] : HT(0);
-      hj[t] = (in && PENDING) ? ph[cb + t] : HT(0);
-      uj[t] = (in && PENDING) ? pu[cb + t] : HT(0);
+      // the three scalars of the rank-2 update ride on the COLUMN values (once per chunk), not on the row values
+      xj[t] = (in && PENDING) ? cfac * px[cb + t] : HT(0);
+      hj[t] = (in && PENDING) ? -cfad * ph[cb + t] : HT(0);
+      uj[t] = (in && PENDING) ? cfae * pu[cb + t] : HT(0);
       dj[t] = in ? vD[cb + t] : HT(0);
       gj[t] = in ? vG[cb + t] : HT(0);
     }
@@ -190,9 +191,21 @@ __device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT
         const bool ok = i < rowEnd;  // rows past the end contribute zeros and are not stored
         const HT   di = ok ? vD[i] : HT(0), gi = ok ? vG[i] : HT(0);
         if constexpr (PENDING) {
-          const HT si = ok ? cfac * px[i] : HT(0), ti = ok ? cfad * ph[i] : HT(0), wi = ok ? cfae * pu[i] : HT(0);
+          const HT si = ok ? px[i] : HT(0), ti = ok ? ph[i] : HT(0), wi = ok ? pu[i] : HT(0);
 #pragma unroll
-          for (int t = 0; t < V; ++t) pk[q].e[t] += (si * xj[t] - ti * hj[t] + wi * uj[t]);
+          for (int t = 0; t < V; ++t) {
+            HT v = pk[q].e[t];
+            if constexpr (sizeof(HT) == 4) {
+              v = __fmaf_rn(si, xj[t], v);
+              v = __fmaf_rn(ti, hj[t], v);
+              v = __fmaf_rn(wi, uj[t], v);
+            } else {
+              v = __fma_rn(si, xj[t], v);
+              v = __fma_rn(ti, hj[t], v);
+              v = __fma_rn(wi, uj[t], v);
+            }
+            pk[q].e[t] = v;
+          }
         }
         if constexpr (DIAG) {
 #pragma unroll
