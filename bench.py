@@ -263,7 +263,7 @@ def run_b200(args) -> None:
     path_b = None
     if args.etkdg_mols > 0:
         flat_b, mmff_b = path_b_pool(args.pool, synthetic.SEED)
-        path_b = run_path_b_gpu(flat_b, mmff_b, args.etkdg_mols, args.confs, dev, max(1, args.steps - 1), 1, world, rank)
+        path_b = run_path_b_gpu(flat_b, mmff_b, args.etkdg_mols, args.confs, dev, max(1, args.steps - 1), 2, world, rank)
         path_b["config"] = {"workload": f"{args.etkdg_mols} drug-like pseudo-mols (20-50 heavy atoms, {args.pool} distinct) x "
                                         f"{args.confs} conformers: ETKDG embed + MMFF94 200-iter BFGS", "data": "synthetic"}
 
@@ -461,7 +461,7 @@ def main() -> None:
     ap.add_argument("--workload", default="butina")
     ap.add_argument("--n-centres", type=int, default=0, help="override the problem size (x50 fingerprints); testing only")
     ap.add_argument("--cross-n", type=int, default=32768, help="rows of the materialised cross-similarity leg (0 = skip)")
-    ap.add_argument("--etkdg-mols", type=int, default=512, help="molecules of the ETKDG+MMFF leg (0 = skip)")
+    ap.add_argument("--etkdg-mols", type=int, default=2048, help="molecules of the ETKDG+MMFF leg (0 = skip)")
     ap.add_argument("--confs", type=int, default=10)
     ap.add_argument("--pool", type=int, default=64, help="distinct pseudo-molecules cycled to fill the batch")
     ap.add_argument("--etkdg-cpu-mols", type=int, default=16, help="molecules of the CPU-baseline sample of that leg")

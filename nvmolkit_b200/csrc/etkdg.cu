@@ -42,7 +42,12 @@ struct EmbedArgs {
   size_t                  hessStride;
   int*                    queue;
   int                     maxN;
+  // attempt-level work stealing (see etkdgKernel): per slot, the next attempt index to hand out, the lowest successful
+  // attempt so far (kNoAttempt = none), a spin lock for the result write, and the number of attempts that have ended
+  int *slotNext, *slotBest, *slotLock, *slotDone;
 };
+constexpr int kNoAttempt      = 0x7f7f7f7f;  // cudaMemset(0x7f) pattern
+constexpr int kMaxSpeculation = 8;           // attempts of one slot in flight at once, at most
 
 constexpr int kNumStages = 11;
 
@@ -185,23 +190,73 @@ __device__ unsigned finalChecks(const EmbedArgs& a, int mol, const double* pos, 
 __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kRed];
-  __shared__ int                        nextSlot;
   const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red);
   double*        ref = sm + kBfgsVectors * a.maxN;  // ETK reference geometry
   const int      tid = threadIdx.x;
+  // Work item = one ATTEMPT of one slot. A CTA first works through the slot queue, retrying its own slot while it fails;
+  // once the queue is dry it helps slots that are still unfinished by running their NEXT attempts speculatively
+  // (attempts are independent: their random streams are functions of (seed, slot, attempt)). The accepted conformer is
+  // always the LOWEST successful attempt index, exactly what the sequential retry loop of the reference yields
+  // (src/etkdg.cpp:339-394), so a small batch no longer waits on one CTA grinding through a hard molecule.
+  __shared__ int                sSlot, sAttempt, sWrite;
+  __shared__ unsigned long long sPick;
+  int                           mySlot = -1;
   for (;;) {
     __syncthreads();
-    if (tid == 0) nextSlot = atomicAdd(a.queue, 1);
+    if (tid == 0) {
+      sSlot = -1;
+      if (mySlot >= 0 && *reinterpret_cast<volatile int*>(a.slotBest + mySlot) == kNoAttempt) {
+        const int at = atomicAdd(a.slotNext + mySlot, 1);
+        if (at < a.par.maxAttempts) {
+          sSlot    = mySlot;
+          sAttempt = at;
+        }
+      }
+      if (sSlot < 0) {
+        const int q = atomicAdd(a.queue, 1);
+        if (q < a.nSlots) {
+          a.ok[q] = 0;
+          if (a.attempts) a.attempts[q] = a.par.maxAttempts;
+          if (a.energy) a.energy[q] = 0.0;
+          __threadfence();
+          sSlot    = q;
+          sAttempt = atomicAdd(a.slotNext + q, 1);  // 0: nobody can have touched it before
+        }
+      }
+      sPick = ~0ull;
+    }
     __syncthreads();
-    const int slot = nextSlot;
-    if (slot >= a.nSlots) break;
+    if (sSlot < 0) {  // queue dry: find an unfinished slot with the fewest attempts handed out
+      for (int s = tid; s < a.nSlots; s += kT) {
+        const int nx = *reinterpret_cast<volatile int*>(a.slotNext + s);
+        if (nx > 0 && nx < a.par.maxAttempts && *reinterpret_cast<volatile int*>(a.slotBest + s) == kNoAttempt &&
+            nx - *reinterpret_cast<volatile int*>(a.slotDone + s) < kMaxSpeculation)
+          atomicMin(&sPick, static_cast<unsigned long long>(nx) << 32 | static_cast<unsigned>(s));
+      }
+      __syncthreads();
+      if (tid == 0 && sPick != ~0ull) {
+        const int s  = static_cast<int>(sPick & 0xffffffffu);
+        const int at = atomicAdd(a.slotNext + s, 1);
+        if (at < a.par.maxAttempts) {
+          sSlot    = s;
+          sAttempt = at;
+        } else {
+          sSlot = -2;  // lost the race for the last attempt: look again
+        }
+      }
+      __syncthreads();
+      if (sSlot == -2) continue;
+      if (sSlot < 0) break;  // nothing left that another attempt could help
+      mySlot = -1;
+    } else {
+      mySlot = sSlot;
+    }
+    const int slot = sSlot, attempt = sAttempt;
     const int mol = a.slotMol[slot];
     const int nA  = a.dg.atomCounts[mol];
     const int n   = 4 * nA;
-    bool      success = false;
-    int       attempt = 0;
     double    eAccepted = 0.0;
-    for (attempt = 0; attempt < a.par.maxAttempts && !success; ++attempt) {
+    {
       int failedStage = -1;
       // 0: random coordinates in a 4-D box
       for (int i = tid; i < n; i += kT) w.pos[i] = (uniform01(a.par.seed, slot, attempt, i) - 0.5) * a.par.boxSize;
@@ -235,18 +290,35 @@ __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
         const unsigned m = finalChecks(a, mol, w.pos, red, true);
         if (m) failedStage = __ffs(m) - 1;
       }
-      if (failedStage < 0) success = true;
-      else if (tid == 0 && a.stageFailures) atomicAdd(a.stageFailures + failedStage, 1ull);
-    }
-    __syncthreads();
-    const int a0 = a.slotAtomStart[slot];
-    if (success) {
-      for (int i = tid; i < nA * 3; i += kT) a.coords[static_cast<size_t>(a0) * 3 + i] = w.pos[(i / 3) * 4 + (i % 3)];
-    }
-    if (tid == 0) {
-      a.ok[slot] = success ? 1 : 0;
-      if (a.attempts) a.attempts[slot] = attempt;
-      if (a.energy) a.energy[slot] = eAccepted;
+      __syncthreads();
+      if (failedStage < 0) {
+        // result write under the slot's lock; only a LOWER attempt index than the one already stored may overwrite
+        if (tid == 0) {
+          while (atomicCAS(a.slotLock + slot, 0, 1) != 0) {}
+          __threadfence();
+          sWrite = attempt < *reinterpret_cast<volatile int*>(a.slotBest + slot);
+        }
+        __syncthreads();
+        if (sWrite) {
+          const int a0 = a.slotAtomStart[slot];
+          for (int i = tid; i < nA * 3; i += kT) a.coords[static_cast<size_t>(a0) * 3 + i] = w.pos[(i / 3) * 4 + (i % 3)];
+          if (tid == 0) {
+            a.ok[slot] = 1;
+            if (a.attempts) a.attempts[slot] = attempt + 1;
+            if (a.energy) a.energy[slot] = eAccepted;
+          }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          if (sWrite) atomicExch(a.slotBest + slot, attempt);
+          __threadfence();
+          atomicExch(a.slotLock + slot, 0);
+        }
+      } else if (tid == 0 && a.stageFailures) {
+        atomicAdd(a.stageFailures + failedStage, 1ull);
+      }
+      if (tid == 0) atomicAdd(a.slotDone + slot, 1);
     }
   }
 }
@@ -314,8 +386,12 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     Scratch<int>    queue(1, s);
     B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));
     if (d_stage_failures) B200_CUDA(cudaMemsetAsync(d_stage_failures, 0, kNumStages * sizeof(uint64_t), s));
+    Scratch<int>    state(static_cast<size_t>(4) * nSlots, s);  // next | best | lock | done
+    B200_CUDA(cudaMemsetAsync(state.get(), 0, sizeof(int) * 4 * nSlots, s));
+    B200_CUDA(cudaMemsetAsync(state.get() + nSlots, 0x7f, sizeof(int) * nSlots, s));
     EmbedArgs a{*dg, *etk, *checks, *params, nSlots, d_slot_mol, d_slot_atom_start, d_coords, d_ok, d_attempts, d_energy,
-                reinterpret_cast<unsigned long long*>(d_stage_failures), hess.get(), stride, queue.get(), maxN};
+                reinterpret_cast<unsigned long long*>(d_stage_failures), hess.get(), stride, queue.get(), maxN,
+                state.get(), state.get() + nSlots, state.get() + 2 * static_cast<size_t>(nSlots), state.get() + 3 * static_cast<size_t>(nSlots)};
     PhaseTimer t("etkdg", s);
     etkdgKernel<<<blocks, kT, smem, s>>>(a);
     B200_LAUNCHED();
