@@ -13,9 +13,9 @@ st0 = np.concatenate([[0], np.cumsum(system.atom_counts)])
 relaxed = [pos0[st0[m]:st0[m + 1]] for m in range(8)]
 b2 = ConformerBatch.from_coords(system, [[r + rng.normal(0, 0.05, r.shape) for _ in range(2)] for r in relaxed])
 pos_o, e_o, conv_o, it_o = oracle.ff_minimize("uff", system.atom_counts, system.tables, b2.conf_mol, b2.atom_starts, b2.positions, 1000, 1e-4)
-for rep in range(3):
+for rep in range(8):
     res = minimize(system, b2, 1000, 1e-4)
     eg, st = res.energies.cpu().numpy(), res.status.cpu().numpy()
-    print("rel", np.abs(eg - e_o) / np.maximum(1, np.abs(e_o)))
-    print("st", st, "conv_o", conv_o, "iters", res.iterations.cpu().numpy() if res.iterations is not None else None, it_o)
+    np.set_printoptions(precision=2, linewidth=200); print("rel", np.abs(eg - e_o) / np.maximum(1, np.abs(e_o)))
+    print("st", st, "conv_o", conv_o)
 print(e_o)
