@@ -7,11 +7,21 @@
 // (tanimoto.cu) emits neighbour counts AND the edge list in one pass, or the dense distance matrix is scanned once —
 // and the greedy loop then runs on the CSR graph inside ONE persistent cooperative kernel: no per-cluster host sync
 // (the reference's fused_butina does three .item() syncs per cluster, nvmolkit/clustering.py:152-169, and its dense
-// path re-reads the N^2 hit matrix every round, src/butina.cu:50-74). Per round: (A) slice-wise arg-max with dirty
-// flags, grid.sync, (B) a warp per neighbour of the centroid assigns it and decrements the counts of ITS neighbours,
-// grid.sync.
+// path re-reads the N^2 hit matrix every round, src/butina.cu:50-74).
+//
+// The greedy order is honoured exactly, but not one cluster at a time. A free point whose key (free-neighbour count,
+// index) is the largest within TWO hops of itself will be chosen by the sequential algorithm with exactly its present
+// free neighbours, whatever happens elsewhere first: every centre chosen before it has a larger key, hence lies more
+// than two hops away and touches none of its neighbours; and taking it out early only LOWERS keys that were already
+// below its own, so it changes no earlier choice. All such local maxima are therefore committed in the same round
+// (butinaRoundsKernel: two passes over the free rows' adjacency for the 2-hop maxima, one to commit). Keys chosen by
+// the sequential algorithm decrease strictly, so the creation order of the clusters - their ids - is the descending
+// order of the keys the centres had when chosen: one radix sort at the end. Rounds that commit only a handful of
+// centres hand over to the one-cluster-per-step loop (butinaLoopKernel): (A) slice-wise arg-max with dirty flags,
+// grid.sync, (B) a warp per neighbour of the centroid assigns it and decrements the counts of ITS neighbours, grid.sync.
 #include <cooperative_groups.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "profile.cuh"
@@ -27,6 +37,9 @@ namespace {
 constexpr int kSliceShift = 10;  // arg-max slices of 1024 points
 constexpr int kSlice      = 1 << kSliceShift;
 constexpr int kLoopThreads = 1024;
+}  // namespace
+int g_butinaMinCommits = 32;  // a parallel round that commits fewer clusters hands over to the stepwise loop (option "butina_min_round_commits")
+namespace {
 
 __global__ void fillAdjacencyKernel(const int2* __restrict__ edges, unsigned long long nEdges,
                                     const long long* __restrict__ offsets, int* __restrict__ fillPos,
@@ -75,11 +88,11 @@ struct LoopState {
   const long long*    offsets;  // [n+1]
   const int*          adj;
   int32_t*            counts;   // free-neighbour counts (live)
-  int32_t*            ids;      // cluster id, -1 = free
-  int32_t*            centroids;
+  int32_t*            ids;      // index of the point's centre while the loops run, -1 = free
+  unsigned long long* selKey;   // [n] key a centre had when it was chosen (0 = not a centre)
   unsigned long long* sliceBest;  // [nSlices] key = count<<32 | idx ; 0 = nothing
   int*                sliceDirty;
-  int*                nClustersOut;  // clusters formed by the loop (non-singletons + isolated leftovers come later)
+  int*                nClustersOut;  // += clusters formed (non-singletons; isolated leftovers come later)
   int                 vecOk;         // ids / counts are 16-byte aligned: full slices use vector loads
 };
 
@@ -174,15 +187,15 @@ __global__ void __launch_bounds__(kLoopThreads, 1) butinaLoopKernel(LoopState st
     // ---- (B) assign: a warp per neighbour of the centre ----
     const long long cBeg = st.offsets[centre], cEnd = st.offsets[centre + 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      st.ids[centre]                        = cluster;
-      st.centroids[cluster]                 = centre;
+      st.ids[centre]                        = centre;
+      st.selKey[centre]                     = best;
       st.sliceDirty[centre >> kSliceShift] = 1;
     }
     for (long long e = cBeg + gWarp; e < cEnd; e += gWarps) {
       const int m = st.adj[e];
       if (st.ids[m] >= 0) continue;  // taken in an earlier round (ids of this round's members are written only here)
       if (lane == 0) {
-        st.ids[m]                         = cluster;
+        st.ids[m]                         = centre;
         st.sliceDirty[m >> kSliceShift] = 1;
       }
       const long long mBeg = st.offsets[m], mEnd = st.offsets[m + 1];
@@ -198,7 +211,116 @@ __global__ void __launch_bounds__(kLoopThreads, 1) butinaLoopKernel(LoopState st
     ++cluster;
     grid.sync();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *st.nClustersOut = cluster;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(st.nClustersOut, cluster);
+}
+
+// ---- many clusters per round: every 2-hop local maximum of the key is committed (see the file header) ----
+constexpr int kRoundThreads = 256;
+__device__ __forceinline__ unsigned long long liveKey(const LoopState& st, int i) {
+  // other SMs change ids / counts between the phases of a round: read through L2
+  return __ldcg(st.ids + i) < 0
+           ? (static_cast<unsigned long long>(static_cast<unsigned>(__ldcg(st.counts + i))) << 32) | static_cast<unsigned>(i)
+           : 0ull;
+}
+__global__ void __launch_bounds__(kRoundThreads) butinaRoundsKernel(LoopState st, unsigned long long* best1, int minCommits) {
+  cg::grid_group grid   = cg::this_grid();
+  const int      lane   = threadIdx.x & 31;
+  const int      gWarp  = (blockIdx.x * kRoundThreads + threadIdx.x) >> 5;
+  const int      gWarps = (gridDim.x * kRoundThreads) >> 5;
+  int            done   = 0, round = 0;
+  for (;;) {
+    // (1) best1[m] = largest key in the closed free neighbourhood of every free row m (0 for taken rows)
+    for (int base = gWarp * 32; base < st.n; base += gWarps * 32) {
+      const int                row  = base + lane;
+      const unsigned long long mine = row < st.n ? liveKey(st, row) : 0ull;
+      if (row < st.n && mine == 0ull) best1[row] = 0ull;
+      unsigned todo = __ballot_sync(0xffffffffu, mine != 0ull);
+      while (todo) {
+        const int          src = __ffs(todo) - 1;
+        const int          m   = base + src;
+        unsigned long long b   = __shfl_sync(0xffffffffu, mine, src);
+        todo &= todo - 1;
+        const long long beg = st.offsets[m], end = st.offsets[m + 1];
+        for (long long e = beg + lane; e < end; e += 32) {
+          const unsigned long long k = liveKey(st, st.adj[e]);
+          b                          = k > b ? k : b;
+        }
+        b = warpMax(b);
+        if (lane == 0) best1[m] = b;
+      }
+    }
+    grid.sync();
+    // (2) a free point with free neighbours whose key tops every best1 of its free neighbours is a 2-hop maximum
+    for (int base = gWarp * 32; base < st.n; base += gWarps * 32) {
+      const int                row  = base + lane;
+      unsigned long long       mine = row < st.n ? liveKey(st, row) : 0ull;
+      if ((mine >> 32) == 0) mine = 0ull;  // no free neighbour left: a singleton, later
+      unsigned todo = __ballot_sync(0xffffffffu, mine != 0ull);
+      while (todo) {
+        const int                src = __ffs(todo) - 1;
+        const int                p   = base + src;
+        const unsigned long long kp  = __shfl_sync(0xffffffffu, mine, src);
+        todo &= todo - 1;
+        unsigned long long b   = 0ull;
+        const long long    beg = st.offsets[p], end = st.offsets[p + 1];
+        for (long long e = beg + lane; e < end; e += 32) {
+          const unsigned long long k = __ldcg(best1 + st.adj[e]);
+          b                          = k > b ? k : b;
+        }
+        b = warpMax(b);
+        if (lane == 0 && b <= kp) st.selKey[p] = kp;  // (b == kp: p itself is in its free neighbours' neighbourhoods)
+      }
+    }
+    grid.sync();
+    // (3) commit the new centres: their neighbourhoods are pairwise disjoint, the count updates are atomic
+    for (int base = gWarp * 32; base < st.n; base += gWarps * 32) {
+      const int  row    = base + lane;
+      const bool fresh  = row < st.n && __ldcg(st.selKey + row) != 0ull && __ldcg(st.ids + row) < 0;
+      unsigned   todo   = __ballot_sync(0xffffffffu, fresh);
+      if (lane == 0 && todo) atomicAdd(st.nClustersOut, __popc(todo));
+      while (todo) {
+        const int p = base + __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (lane == 0) st.ids[p] = p;
+        const long long beg = st.offsets[p], end = st.offsets[p + 1];
+        for (long long e = beg; e < end; ++e) {
+          const int m = st.adj[e];
+          if (__ldcg(st.ids + m) >= 0) continue;  // taken in an earlier round
+          if (lane == 0) st.ids[m] = p;
+          const long long mBeg = st.offsets[m], mEnd = st.offsets[m + 1];
+          for (long long f = mBeg + lane; f < mEnd; f += 32) {
+            const int i = st.adj[f];
+            if (i != p) atomicSub(st.counts + i, 1);  // dead counts (members, taken points) may go anywhere
+          }
+        }
+      }
+    }
+    grid.sync();
+    const int total = __ldcg(st.nClustersOut);
+#ifdef B200_BUTINA_DEBUG
+    if (blockIdx.x == 0 && threadIdx.x == 0) printf("round %d total %d done %d\n", round, total, done);
+#endif
+    if (total - done < (minCommits > 1 ? minCommits : 1)) break;  // (a round without a commit ends the phase in any case)
+    if (++round >= st.n) break;  // cannot happen (every continuing round commits a cluster); a guard against a spin
+    done = total;
+  }
+}
+
+__global__ void iotaKernel(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+// sorted (key descending, point): rank r -> centroids[r], idOf[point] = r
+__global__ void rankCentresKernel(const unsigned long long* __restrict__ keys, const int* __restrict__ pts, int n,
+                                  int32_t* __restrict__ centroids, int* __restrict__ idOf) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || keys[r] == 0ull) return;
+  centroids[r]  = pts[r];
+  idOf[pts[r]]  = r;
+}
+__global__ void remapIdsKernel(int32_t* __restrict__ ids, const int* __restrict__ idOf, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] >= 0) ids[i] = idOf[ids[i]];
 }
 
 // Leftover free points become singletons in descending index order (RDKit sorts (count, idx) descending).
@@ -231,22 +353,59 @@ void clusterFromCsr(int n, const long long* offsets, const int* adj, int32_t* co
   Scratch<unsigned long long> sliceBest(nSlices, s);
   Scratch<int>                sliceDirty(nSlices, s);
   Scratch<int>                nLoop(1, s);
+  Scratch<unsigned long long> selKey(n, s), best1(n, s);
   fillKernel<<<(n + 255) / 256, 256, 0, s>>>(ids, n, -1);
   B200_LAUNCHED();
-  fillKernel<<<(nSlices + 255) / 256, 256, 0, s>>>(sliceDirty.get(), nSlices, 1);
-  B200_LAUNCHED();
+  B200_CUDA(cudaMemsetAsync(selKey.get(), 0, sizeof(unsigned long long) * n, s));
+  B200_CUDA(cudaMemsetAsync(nLoop.get(), 0, sizeof(int), s));
 
   const int vecOk = ((reinterpret_cast<uintptr_t>(ids) | reinterpret_cast<uintptr_t>(counts)) & 15) == 0;
-  LoopState st{n, nSlices, offsets, adj, counts, ids, centroids, sliceBest.get(), sliceDirty.get(), nLoop.get(), vecOk};
-  int       perSm = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, butinaLoopKernel, kLoopThreads, 0));
-  B200_REQUIRE(perSm >= 1, "butina loop kernel does not fit on an SM");
-  // The loop is latency-bound (two grid-wide barriers per cluster): a small grid keeps the barrier cheap, and 32 CTAs x
-  // 32 warps are plenty for the ~100 dirty slices and ~100 member warps of a round.
-  const int blocks = smCount() < 32 ? smCount() : 32;
-  void*     args[] = {&st};
-  B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(butinaLoopKernel), dim3(blocks), dim3(kLoopThreads), args, 0, s));
-  g_launchCount.fetch_add(1);
+  LoopState st{n, nSlices, offsets, adj, counts, ids, selKey.get(), sliceBest.get(), sliceDirty.get(), nLoop.get(), vecOk};
+  {
+    // many clusters per round while a round still commits a few dozen; then one cluster per step
+    PhaseTimer          t("cluster_rounds", s);
+    int                 perSm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, butinaRoundsKernel, kRoundThreads, 0));
+    B200_REQUIRE(perSm >= 1, "butina rounds kernel does not fit on an SM");
+    const int           blocks = smCount() * (perSm > 4 ? 4 : perSm);
+    unsigned long long* b1     = best1.get();
+    int                 minCommits = g_butinaMinCommits;
+    void*               args[] = {&st, &b1, &minCommits};
+    B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(butinaRoundsKernel), dim3(blocks), dim3(kRoundThreads), args, 0, s));
+    g_launchCount.fetch_add(1);
+  }
+  fillKernel<<<(nSlices + 255) / 256, 256, 0, s>>>(sliceDirty.get(), nSlices, 1);
+  B200_LAUNCHED();
+  {
+    PhaseTimer t("cluster_steps", s);
+    int        perSm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, butinaLoopKernel, kLoopThreads, 0));
+    B200_REQUIRE(perSm >= 1, "butina loop kernel does not fit on an SM");
+    // The loop is latency-bound (two grid-wide barriers per cluster): a small grid keeps the barrier cheap, and 32 CTAs x
+    // 32 warps are plenty for the ~100 dirty slices and ~100 member warps of a round.
+    const int blocks = smCount() < 32 ? smCount() : 32;
+    void*     args[] = {&st};
+    B200_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(butinaLoopKernel), dim3(blocks), dim3(kLoopThreads), args, 0, s));
+    g_launchCount.fetch_add(1);
+  }
+  {
+    // cluster ids = rank of the centre's key (descending) = creation order of the sequential algorithm
+    Scratch<unsigned long long> keysOut(n, s);
+    Scratch<int>                ptsIn(n, s), ptsOut(n, s), idOf(n, s);
+    iotaKernel<<<(n + 255) / 256, 256, 0, s>>>(ptsIn.get(), n);
+    B200_LAUNCHED();
+    size_t sortBytes = 0;
+    B200_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, sortBytes, selKey.get(), keysOut.get(), ptsIn.get(), ptsOut.get(), n,
+                                                        0, 64, s));
+    Scratch<uint8_t> sortTmp(sortBytes, s);
+    B200_CUDA(cub::DeviceRadixSort::SortPairsDescending(sortTmp.get(), sortBytes, selKey.get(), keysOut.get(), ptsIn.get(),
+                                                        ptsOut.get(), n, 0, 64, s));
+    g_launchCount.fetch_add(1);
+    rankCentresKernel<<<(n + 255) / 256, 256, 0, s>>>(keysOut.get(), ptsOut.get(), n, centroids, idOf.get());
+    B200_LAUNCHED();
+    remapIdsKernel<<<(n + 255) / 256, 256, 0, s>>>(ids, idOf.get(), n);
+    B200_LAUNCHED();
+  }
 
   Scratch<int> flags(n, s), rank(n, s);
   freeFlagsKernel<<<(n + 255) / 256, 256, 0, s>>>(ids, n, flags.get());

@@ -258,6 +258,28 @@ def test_pack_unpack_roundtrip(cuda):
     assert (pack_fingerprint(unpack_fingerprint(fp)) == fp).all()
 
 
+@pytest.mark.parametrize("min_commits", [0, 32, 10 ** 9])  # rounds to exhaustion | default hybrid | stepwise loop only
+@pytest.mark.parametrize("n,degree", [(60, 3), (400, 10), (1500, 40)])
+def test_butina_parallel_rounds_keep_the_greedy_order(cuda, min_commits, n, degree):
+    """Overlapping neighbourhoods (a random graph, no cluster structure): many rounds whose commits depend on each
+    other. Every mode must reproduce the sequential greedy result - members, centroids AND ids (creation order)."""
+    from nvmolkit_b200 import _lib
+    from nvmolkit_b200.clustering import butina
+
+    rng = np.random.default_rng(n * 7 + degree)
+    d = rng.random((n, n))
+    d = np.minimum(d, d.T)
+    np.fill_diagonal(d, 0.0)
+    cutoff = 1.0 - (1.0 - degree / n) ** 0.5  # P(min(u, v) <= c) = degree / n
+    _lib.set_option("butina_min_round_commits", min_commits)
+    try:
+        ids, cen = butina(torch.from_numpy(d).to(cuda), cutoff, return_centroids=True)
+    finally:
+        _lib.set_option("butina_min_round_commits", 32)
+    ids_cpu, cen_cpu = oracle.butina_dense(d, cutoff)
+    assert (ids.numpy() == ids_cpu).all() and (cen.numpy() == cen_cpu).all()
+
+
 # ------------------------------------------------------------------ tensor-core (tcgen05 int8) path of the count pass
 @pytest.fixture
 def force_tensor_path(cuda):
