@@ -33,6 +33,7 @@ constexpr int kEpiWarps  = 8;    // two warps per TMEM lane quarter, each takes 
 constexpr int kThreadsTC = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kABytes   = kTM * kTK;
 constexpr int kBBytes   = kTN * kTK;
+constexpr int kTNFp4    = 224;  // fp4 count mode: 2 x 224 accumulator columns leave TMEM columns 448..511 for the scale factors
 constexpr int kGroupTC  = 16;  // tile rows per L2 reuse group
 
 struct TcParams {
@@ -57,6 +58,9 @@ struct TcParams {
 };
 
 enum TcMode : int { kTcCount = 0, kTcTanimoto = 1, kTcCosine = 2 };
+}  // namespace
+int g_tensorFp4 = 1;  // count mode on block-scaled fp4 operands (option "similarity_tensor_fp4"; 0 = int8 tile)
+namespace {
 
 __global__ void expandBitsKernel(const uint32_t* __restrict__ fp, size_t nWords, uint4* __restrict__ out) {
   const size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -70,6 +74,24 @@ __global__ void expandBitsKernel(const uint32_t* __restrict__ fp, size_t nWords,
   }
   out[2 * w]     = make_uint4(b[0], b[1], b[2], b[3]);
   out[2 * w + 1] = make_uint4(b[4], b[5], b[6], b[7]);
+}
+
+// bits -> packed E2M1 (fp4): bit = 1 -> 0x2 (1.0), bit = 0 -> 0x0; two elements per byte, 1 KB per 2048-bit row. The
+// contraction is invariant to the order of the K elements as long as both operands use the same one.
+__global__ void expandBitsFp4Kernel(const uint32_t* __restrict__ fp, size_t nWords, uint4* __restrict__ out) {
+  const size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= nWords) return;
+  const uint32_t x = fp[w];
+  uint32_t       b[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // 8 bits -> 8 nibbles
+    uint32_t v = (x >> (8 * q)) & 0xFFu;
+    v          = (v | (v << 12)) & 0x000F000Fu;
+    v          = (v | (v << 6)) & 0x03030303u;
+    v          = (v | (v << 3)) & 0x11111111u;
+    b[q]       = v << 1;
+  }
+  out[w] = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
 __device__ __forceinline__ uint64_t makeSmemDesc(uint32_t smemByteAddr) {
@@ -87,6 +109,29 @@ __device__ __forceinline__ void ummaI8(uint32_t tmemD, uint64_t aDesc, uint64_t 
     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemD),
     "l"(aDesc), "l"(bDesc), "r"(kIdescI8), "r"(accumulate)
     : "memory");
+}
+// Block-scaled fp4 (kind::mxf4, K = 64 elements = 32 bytes per instruction, twice the int8 rate): operands are the
+// packed E2M1 0/1 expansions, every UE8M0 scale factor is 1.0 (0x7F; TMEM columns 448..511 are filled with it, so the
+// scale-factor layout is immaterial), accumulation in fp32 is exact (sums <= 4096).
+// Descriptor bits (cute/arch/mma_sm100_desc.hpp, InstrDescriptorBlockScaled): a/b format E2M1 = 1 at [7,10) / [10,13),
+// N >> 3 at [17,23), scale format UE8M0 = 1 at bit 23, M >> 4 at [24,29), scale-factor ids 0, K = 64 (bit 31 = 0).
+constexpr uint32_t kIdescMxf4 = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTNFp4 >> 3) << 17) | (1u << 23) |
+                                (static_cast<uint32_t>(kTM >> 4) << 24);
+__device__ __forceinline__ void ummaMxf4(uint32_t tmemD, uint64_t aDesc, uint64_t bDesc, uint32_t accumulate, uint32_t tmemSfa,
+                                         uint32_t tmemSfb) {
+  asm volatile(
+    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmemD),
+    "l"(aDesc), "l"(bDesc), "r"(kIdescMxf4), "r"(accumulate), "r"(tmemSfa), "r"(tmemSfb)
+    : "memory");
+}
+__device__ __forceinline__ void tmemStore32Const(uint32_t taddr, uint32_t v) {
+  asm volatile(
+    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+    "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+    "r"(v)
+    : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void ummaCommit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smemAddr(bar)) : "memory");
@@ -108,6 +153,7 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // linear tile index -> (tm, tn): groups of kGroupTC tile-rows sweep the tile-columns
+template <int TN>
 __device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32_t& tm, uint32_t& tn) {
   const uint64_t perGroup = static_cast<uint64_t>(kGroupTC) * p.tilesN;
   const uint32_t group    = static_cast<uint32_t>(t / perGroup);
@@ -119,15 +165,18 @@ __device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32
   tn                   = inGroup / gRows;
   if (tn >= p.tilesN) return false;
   // symmetric: skip tiles whose every column index is <= every row index (no pair with row < col)
-  if (p.symmetric && (tn * kTN + kTN - 1) <= tm * kTM) return false;
+  if (p.symmetric && (tn * TN + TN - 1) <= tm * kTM) return false;
   return true;
 }
 
-template <int MODE>
+template <int MODE, bool FP4>
 __global__ void __launch_bounds__(kThreadsTC, 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                   uint64_t totalTiles) {
   extern __shared__ __align__(1024) uint8_t smemRaw[];
+  constexpr int TN      = FP4 ? kTNFp4 : kTN;  // tile columns; the accumulator stages sit TN TMEM columns apart
+  constexpr int kBBytes = TN * kTK;
+  static_assert(!FP4 || MODE == kTcCount, "the fp4 tile serves the count mode");
   constexpr int kStagesTC = MODE == kTcCount ? kStagesCount : kStagesMat;
   __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
   __shared__ uint32_t tmemBase;
@@ -167,6 +216,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
   __syncthreads();
   tcFenceAfter();
   const uint32_t tmem = tmemBase;
+  if constexpr (FP4) {
+    // every scale factor = 1.0: fill TMEM columns 448..511 of all 128 lanes (a warp reaches its own lane quarter)
+    if (warp >= 2 && warp < 6) {
+      const uint32_t q = static_cast<uint32_t>(warp & 3) * 32u;
+      tmemStore32Const(tmem + 448 + (q << 16), 0x7F7F7F7Fu);
+      tmemStore32Const(tmem + 480 + (q << 16), 0x7F7F7F7Fu);
+    }
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -175,13 +235,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       uint32_t phase = 0;
       for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
         uint32_t tm, tn;
-        if (!tileCoords(p, t, tm, tn)) continue;
+        if (!tileCoords<TN>(p, t, tm, tn)) continue;
         for (int kc = 0; kc < p.kChunks; ++kc) {
           mbarWait(&emptyBar[stage], phase ^ 1);
           uint8_t* dst = smemGen + stage * (kABytes + kBBytes);
           mbarExpectTx(&fullBar[stage], kABytes + kBBytes);
           tmaLoad2D(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
-          tmaLoad2D(dst + kABytes, &tmB, kc * kTK, tn * kTN, &fullBar[stage]);
+          tmaLoad2D(dst + kABytes, &tmB, kc * kTK, tn * TN, &fullBar[stage]);
           if (++stage == kStagesTC) {
             stage = 0;
             phase ^= 1;
@@ -196,11 +256,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       uint32_t phase = 0, local = 0;
       for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
         uint32_t tm, tn;
-        if (!tileCoords(p, t, tm, tn)) continue;
+        if (!tileCoords<TN>(p, t, tm, tn)) continue;
         const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
         mbarWait(&tmemEmpty[as], accPhase ^ 1);
         tcFenceAfter();
-        const uint32_t dAddr = tmem + as * kTN;
+        const uint32_t dAddr = tmem + as * TN;
         for (int kc = 0; kc < p.kChunks; ++kc) {
           mbarWait(&fullBar[stage], phase);
           tcFenceAfter();
@@ -208,7 +268,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
           const uint64_t aDesc = makeSmemDesc(aAddr), bDesc = makeSmemDesc(aAddr + kABytes);
 #pragma unroll
           for (int k = 0; k < kTK / 32; ++k)  // K = 32 bytes per instruction: +32 B = +2 in the 16-byte address field
-            ummaI8(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u);
+          {
+            if constexpr (FP4) ummaMxf4(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u, tmem + 448, tmem + 480);
+            else ummaI8(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u);
+          }
           ummaCommit(&emptyBar[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == kStagesTC) {
             stage = 0;
@@ -228,11 +291,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     uint32_t       local   = 0;
     for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
       uint32_t tm, tn;
-      if (!tileCoords(p, t, tm, tn)) continue;
+      if (!tileCoords<TN>(p, t, tm, tn)) continue;
       const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
       // stage this tile's column popcounts
-      for (int c = et; c < kTN; c += 32 * kEpiWarps) {
-        const uint32_t gc = tn * kTN + c;
+      for (int c = et; c < TN; c += 32 * kEpiWarps) {
+        const uint32_t gc = tn * TN + c;
         popB[as][c]       = gc < p.nY ? __ldg(p.popY + gc) : 0;
         colAcc[as][c]     = 0;
       }
@@ -246,9 +309,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       mbarWait(&tmemFull[as], accPhase);
       tcFenceAfter();
       int rowHits = 0;
-      for (int cb = half * (kTN / 64); cb < (half + 1) * (kTN / 64); ++cb) {
+      constexpr int kCb = TN / 32, kCbHalf = (kCb + 1) / 2;  // column blocks of 32; the two warps of a quarter split them
+      for (int cb = half * kCbHalf; cb < (half ? kCb : kCbHalf); ++cb) {
         uint32_t r[32];
-        tmemLoad32(tmem + as * kTN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+        tmemLoad32(tmem + as * TN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
         if constexpr (MODE != kTcCount) {
           // Transpose the 32 x 32 block in registers (5 butterfly rounds of SHFL) so that lane = column and k = row:
           // every store instruction then writes 32 consecutive doubles of one output row (8 full sectors) instead of
@@ -266,7 +330,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
               }
             }
           }
-          const uint32_t gc = tn * kTN + cb * 32 + lane;
+          const uint32_t gc = tn * TN + cb * 32 + lane;
           const int      pb = popB[as][cb * 32 + lane];
           if (gc < p.nY) {
             const uint32_t row0 = tm * kTM + quarter * 32;
@@ -299,11 +363,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
         uint32_t mask = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const uint32_t gc = tn * kTN + cb * 32 + j;
+          const uint32_t gc = tn * TN + cb * 32 + j;
           bool           ok = gr < p.n && gc < p.nY;
           if (p.symmetric) ok = ok && gr < gc;
           const int th = threshS[pa + popB[as][cb * 32 + j]];
-          if (ok && static_cast<int>(r[j]) >= th) mask |= 1u << j;
+          const int cij = FP4 ? __float2int_rn(__uint_as_float(r[j])) : static_cast<int>(r[j]);
+          if (ok && cij >= th) mask |= 1u << j;
         }
         const unsigned any = __ballot_sync(0xffffffffu, mask != 0);
         if (any) {
@@ -332,7 +397,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             while (m) {
               const int j = __ffs(m) - 1;
               m &= m - 1;
-              if (at < p.edgeCap) p.edges[at] = make_int2(static_cast<int>(gr), static_cast<int>(tn * kTN + cb * 32 + j));
+              if (at < p.edgeCap) p.edges[at] = make_int2(static_cast<int>(gr), static_cast<int>(tn * TN + cb * 32 + j));
               ++at;
             }
           }
@@ -344,9 +409,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       if (MODE == kTcCount && rowHits) atomicAdd(p.counts + gr, p.sign * rowHits);
       if (MODE == kTcCount && p.countsY) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        for (int c = et; c < kTN; c += 32 * kEpiWarps) {
+        for (int c = et; c < TN; c += 32 * kEpiWarps) {
           const int v = colAcc[as][c];
-          if (v) atomicAdd(p.countsY + tn * kTN + c, p.sign * v);
+          if (v) atomicAdd(p.countsY + tn * TN + c, p.sign * v);
         }
       }
       ++local;
@@ -373,12 +438,19 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   const bool same = (q.x == q.y && q.nX == q.nY);
   if (q.symmetric && !same) return false;
 
+  // count mode: block-scaled fp4 operands (twice the int8 MMA rate, half the operand bytes) when the fingerprint is a
+  // whole number of 256-bit chunks; the materialise modes (HBM-bound on the fp64 output) keep the int8 tile
+  const bool count = mode == kCountTanimoto;
+  const bool fp4   = count && g_tensorFp4 && bits % (2 * kTK) == 0;
+  const int  tn    = fp4 ? kTNFp4 : kTN;
+  const int  rowBytes = fp4 ? bits / 2 : bits;  // bytes of one expanded fingerprint
+
   TcParams p{};
   p.n         = static_cast<uint32_t>(q.nX);
   p.nY        = static_cast<uint32_t>(q.nY);
-  p.kChunks   = bits / kTK;
+  p.kChunks   = rowBytes / kTK;
   p.tilesM    = static_cast<uint32_t>((q.nX + kTM - 1) / kTM);
-  p.tilesN    = static_cast<uint32_t>((q.nY + kTN - 1) / kTN);
+  p.tilesN    = static_cast<uint32_t>((q.nY + tn - 1) / tn);
   p.symmetric = q.symmetric ? 1 : 0;
   p.groupOffset = q.groupOffset;
   p.groupStride = q.groupStride < 1 ? 1 : q.groupStride;
@@ -391,18 +463,18 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   p.out       = q.out;
   p.recipLen  = 2 * bits;
 
-  // 0/1 byte expansion of the fingerprints (2 KB per 2048-bit row)
-  Scratch<uint8_t> expX(q.nX * static_cast<size_t>(bits), s);
-  Scratch<uint8_t> expYown(same ? 0 : q.nY * static_cast<size_t>(bits), s);
+  // 0/1 expansion of the fingerprints: bytes (2 KB per 2048-bit row) or packed fp4 (1 KB)
+  Scratch<uint8_t> expX(q.nX * static_cast<size_t>(rowBytes), s);
+  Scratch<uint8_t> expYown(same ? 0 : q.nY * static_cast<size_t>(rowBytes), s);
   {
-    const size_t nw = q.nX * static_cast<size_t>(q.words);
-    expandBitsKernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(q.x, nw, reinterpret_cast<uint4*>(expX.get()));
-    B200_LAUNCHED();
-    if (!same) {
-      const size_t nwy = q.nY * static_cast<size_t>(q.words);
-      expandBitsKernel<<<static_cast<unsigned>((nwy + 255) / 256), 256, 0, s>>>(q.y, nwy, reinterpret_cast<uint4*>(expYown.get()));
+    auto expand = [&](const uint32_t* src, size_t rows, uint8_t* dst) {
+      const size_t nw = rows * static_cast<size_t>(q.words);
+      if (fp4) expandBitsFp4Kernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(src, nw, reinterpret_cast<uint4*>(dst));
+      else expandBitsKernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(src, nw, reinterpret_cast<uint4*>(dst));
       B200_LAUNCHED();
-    }
+    };
+    expand(q.x, q.nX, expX.get());
+    if (!same) expand(q.y, q.nY, expYown.get());
   }
   const uint8_t* expY = same ? expX.get() : expYown.get();
 
@@ -420,17 +492,17 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   p.thresh = thresh.get();
 
   CUtensorMap tmA, tmB;
-  makeTensorMap2D(&tmA, expX.get(), q.nX, bits, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
-  makeTensorMap2D(&tmB, expY, q.nY, bits, kTN, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  makeTensorMap2D(&tmA, expX.get(), q.nX, rowBytes, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  makeTensorMap2D(&tmB, expY, q.nY, rowBytes, tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
-  const bool   count     = mode == kCountTanimoto;
-  const size_t smemBytes = static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + kBBytes) +
+  const size_t smemBytes = static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK) +
                            (count ? static_cast<size_t>(maxS + 1) * 2 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
   static bool  configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     configured = true;
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
@@ -440,13 +512,14 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   if (static_cast<uint64_t>(blocks) > total) blocks = static_cast<int>(total);
   if (mode == kCountTanimoto) {
     PhaseTimer t("neighbor_pass_tc", s);
-    simTensorKernel<kTcCount><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    if (fp4) simTensorKernel<kTcCount, true><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    else simTensorKernel<kTcCount, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcTanimoto><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcTanimoto, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
   } else {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcCosine><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcCosine, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
   }
   B200_LAUNCHED();
   return true;
