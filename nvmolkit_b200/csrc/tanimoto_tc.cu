@@ -94,6 +94,28 @@ __global__ void expandBitsFp4Kernel(const uint32_t* __restrict__ fp, size_t nWor
   out[w] = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
+// lo[S] = min(thresh[S..len-1]): the threshold table need not be monotone (cutoff 0 admits only even |A|+|B|), its
+// lower envelope is, and that is what the epilogue's one-compare pre-filter may use. One block, any len <= 16384.
+__global__ void __launch_bounds__(1024) threshSuffixMinKernel(const uint16_t* __restrict__ thresh, int len, uint16_t* __restrict__ lo) {
+  __shared__ int part[1024];
+  const int      per = (len + 1023) / 1024, beg = threadIdx.x * per, end = min(len, beg + per);
+  int            m   = 0x7fffffff;
+  for (int i = end - 1; i >= beg; --i) m = min(m, static_cast<int>(thresh[i]));
+  part[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // inclusive suffix-min over the chunk minima
+    const int v = threadIdx.x + o < 1024 ? part[threadIdx.x + o] : 0x7fffffff;
+    __syncthreads();
+    part[threadIdx.x] = min(part[threadIdx.x], v);
+    __syncthreads();
+  }
+  int run = threadIdx.x + 1 < 1024 ? part[threadIdx.x + 1] : 0x7fffffff;  // everything to the right of this chunk
+  for (int i = end - 1; i >= beg; --i) {
+    run   = min(run, static_cast<int>(thresh[i]));
+    lo[i] = static_cast<uint16_t>(run);
+  }
+}
+
 __device__ __forceinline__ uint64_t makeSmemDesc(uint32_t smemByteAddr) {
   // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO unused, descriptor version 1 (sm_100), layout type 2
   return static_cast<uint64_t>((smemByteAddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(1024 >> 4) << 32) |
@@ -183,6 +205,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
   __shared__ int      popB[2][kTN];
   __shared__ int      popA[2][kTM];
   __shared__ int      colAcc[2][kTN];
+  __shared__ int      popBMin[2][kEpiWarps];
 
   const uint32_t smemBase = (smemAddr(smemRaw) + 1023u) & ~1023u;
   uint8_t*       smemGen  = smemRaw + (smemBase - smemAddr(smemRaw));
@@ -207,7 +230,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(&tmemBase)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < p.threshLen; i += kThreadsTC) threshS[i] = p.thresh[i];
+  for (int i = threadIdx.x; i < 2 * p.threshLen; i += kThreadsTC) threshS[i] = p.thresh[i];  // table | its suffix-min
+  const uint16_t* threshLoS = threshS + p.threshLen;
   double* recipS = reinterpret_cast<double*>(threshS);  // materialise Tanimoto: RN(1/u), u = |A u B| <= 2 * bits
   if constexpr (MODE == kTcTanimoto) {
     for (int u = threadIdx.x; u <= p.recipLen; u += kThreadsTC) recipS[u] = u ? __drcp_rn(static_cast<double>(u)) : 0.0;
@@ -294,10 +318,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       if (!tileCoords<TN>(p, t, tm, tn)) continue;
       const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
       // stage this tile's column popcounts
+      int minPb = 0x3fffffff;  // smallest |B| among this tile's valid columns (pre-filter of the threshold test)
       for (int c = et; c < TN; c += 32 * kEpiWarps) {
         const uint32_t gc = tn * TN + c;
-        popB[as][c]       = gc < p.nY ? __ldg(p.popY + gc) : 0;
+        const int      pb = gc < p.nY ? __ldg(p.popY + gc) : 0;
+        popB[as][c]       = pb;
         colAcc[as][c]     = 0;
+        if (gc < p.nY) minPb = min(minPb, pb);
+      }
+      if constexpr (MODE == kTcCount) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) minPb = min(minPb, __shfl_xor_sync(0xffffffffu, minPb, o));
+        if (lane == 0) popBMin[as][ew] = minPb;
       }
       if (MODE != kTcCount && et < kTM) {
         const uint32_t ga = tm * kTM + et;
@@ -306,6 +338,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       const uint32_t gr = tm * kTM + quarter * 32 + lane;
       const int      pa = gr < p.n ? __ldg(p.popX + gr) : 0;
+      int thMin = 0;
+      if constexpr (MODE == kTcCount) {
+        int mpb = popBMin[as][0];
+#pragma unroll
+        for (int k = 1; k < kEpiWarps; ++k) mpb = min(mpb, popBMin[as][k]);
+        thMin = (gr < p.n && mpb < 0x3fffffff) ? static_cast<int>(threshLoS[pa + mpb]) : 0x3fffffff;  // no valid pair: all out
+      }
+      const float fThMin = static_cast<float>(thMin);
+      (void)fThMin;
       mbarWait(&tmemFull[as], accPhase);
       tcFenceAfter();
       int rowHits = 0;
@@ -360,15 +401,30 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
           }
           continue;
         }
-        uint32_t mask = 0;
+        // Pre-filter: the threshold grows with |A| + |B|, so c < thresh[|A| + min |B| of the tile] rules a pair out with
+        // one compare; the exact table test (and the bounds / upper-triangle predicates) runs for the survivors only —
+        // a handful per million pairs on fingerprint data.
+        uint32_t maybe = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
+          if constexpr (FP4) maybe |= (__uint_as_float(r[j]) >= fThMin ? 1u : 0u) << j;
+          else maybe |= (static_cast<int>(r[j]) >= thMin ? 1u : 0u) << j;
+        }
+        uint32_t mask = 0;
+        while (maybe) {
+          const int j = __ffs(maybe) - 1;
+          maybe &= maybe - 1;
           const uint32_t gc = tn * TN + cb * 32 + j;
           bool           ok = gr < p.n && gc < p.nY;
           if (p.symmetric) ok = ok && gr < gc;
-          const int th = threshS[pa + popB[as][cb * 32 + j]];
-          const int cij = FP4 ? __float2int_rn(__uint_as_float(r[j])) : static_cast<int>(r[j]);
-          if (ok && cij >= th) mask |= 1u << j;
+          if (ok) {
+            // (dynamic register indexing is avoided: the accumulator is re-read through a shuffle-free select chain)
+            int cij = 0;
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (q == j) cij = FP4 ? __float2int_rn(__uint_as_float(r[q])) : static_cast<int>(r[q]);
+            if (cij >= threshS[pa + popB[as][cb * 32 + j]]) mask |= 1u << j;
+          }
         }
         const unsigned any = __ballot_sync(0xffffffffu, mask != 0);
         if (any) {
@@ -484,9 +540,11 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   p.popX = popX.get();
   p.popY = same ? popX.get() : popYown.get();
   const int         maxS = 2 * bits;
-  Scratch<uint16_t> thresh(maxS + 1, s);
+  Scratch<uint16_t> thresh(2 * static_cast<size_t>(maxS + 1), s);
   if (mode == kCountTanimoto) {
     launchThreshTable(maxS, q.cutoff, thresh.get(), s);
+    threshSuffixMinKernel<<<1, 1024, 0, s>>>(thresh.get(), maxS + 1, thresh.get() + maxS + 1);
+    B200_LAUNCHED();
     p.threshLen = maxS + 1;
   }
   p.thresh = thresh.get();
@@ -496,7 +554,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   makeTensorMap2D(&tmB, expY, q.nY, rowBytes, tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
   const size_t smemBytes = static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK) +
-                           (count ? static_cast<size_t>(maxS + 1) * 2 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
+                           (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
   static bool  configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
