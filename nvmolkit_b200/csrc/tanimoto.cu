@@ -298,6 +298,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s);
 extern int g_bfgsCtasPerSm;
 extern int g_butinaMinCommits;
 extern int g_tensorFp4;
+extern int g_tensorCluster;
 long long g_tensorMinPairs = 1ll << 24;  // pair count from which the count mode runs on tcgen05 (< 0: never)
 
 void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s) {
@@ -412,6 +413,7 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       g_bfgsCtasPerSm = static_cast<int>(value);
     }
     else if (k == "similarity_tensor_fp4") g_tensorFp4 = value != 0;
+    else if (k == "similarity_tensor_cluster") g_tensorCluster = value != 0;
     else if (k == "butina_min_round_commits") {
       B200_REQUIRE(value >= 0, "butina_min_round_commits must be >= 0");
       g_butinaMinCommits = static_cast<int>(value > 1000000000 ? 1000000000 : value);  // huge = stepwise loop only

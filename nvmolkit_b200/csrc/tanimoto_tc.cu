@@ -59,6 +59,7 @@ struct TcParams {
 
 enum TcMode : int { kTcCount = 0, kTcTanimoto = 1, kTcCosine = 2 };
 }  // namespace
+int g_tensorCluster = 1;  // fp4 count tile in clusters of two CTAs with a multicast column operand (option "similarity_tensor_cluster")
 int g_tensorFp4 = 1;  // count mode on block-scaled fp4 operands (option "similarity_tensor_fp4"; 0 = int8 tile)
 namespace {
 
@@ -158,6 +159,11 @@ __device__ __forceinline__ void tmemStore32Const(uint32_t taddr, uint32_t v) {
 __device__ __forceinline__ void ummaCommit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smemAddr(bar)) : "memory");
 }
+__device__ __forceinline__ void ummaCommitMulticast(uint64_t* bar, uint16_t ctaMask) {  // same barrier offset in every CTA of the mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smemAddr(bar)),
+               "h"(ctaMask)
+               : "memory");
+}
 __device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -191,7 +197,29 @@ __device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32
   return true;
 }
 
-template <int MODE, bool FP4>
+// Cluster of two CTAs: one unit = two vertically adjacent tiles (tile rows 2 tp, 2 tp + 1) of the same tile column; the
+// two CTAs share the column operand (each loads half of it and multicasts). Same row-group partition as tileCoords.
+template <int TN>
+__device__ __forceinline__ bool tileCoordsPair(const TcParams& p, uint64_t t, uint32_t rank, uint32_t& tm, uint32_t& tn) {
+  constexpr uint32_t kPairGroup = kGroupTC / 2;
+  const uint32_t     pairRows   = (p.tilesM + 1) / 2;
+  const uint64_t     perGroup   = static_cast<uint64_t>(kPairGroup) * p.tilesN;
+  const uint32_t     group      = static_cast<uint32_t>(t / perGroup);
+  const uint32_t     inGroup    = static_cast<uint32_t>(t % perGroup);
+  if (group * kPairGroup >= pairRows) return false;
+  if (group % p.groupStride != p.groupOffset) return false;
+  const uint32_t gRows = min(kPairGroup, pairRows - group * kPairGroup);
+  const uint32_t tp    = group * kPairGroup + inGroup % gRows;
+  tn                   = inGroup / gRows;
+  if (tn >= p.tilesN) return false;
+  // the upper tile decides for both (if it has no pair with row < col, neither has the lower one); a lower tile that is
+  // past the end or below the diagonal still runs - its loads are zero-filled / its predicates reject everything
+  if (p.symmetric && (tn * TN + TN - 1) <= (2 * tp) * kTM) return false;
+  tm = 2 * tp + rank;
+  return true;
+}
+
+template <int MODE, bool FP4, bool CL>
 __global__ void __launch_bounds__(kThreadsTC, 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                   uint64_t totalTiles) {
@@ -199,6 +227,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
   constexpr int TN      = FP4 ? kTNFp4 : kTN;  // tile columns; the accumulator stages sit TN TMEM columns apart
   constexpr int kBBytes = TN * kTK;
   static_assert(!FP4 || MODE == kTcCount, "the fp4 tile serves the count mode");
+  static_assert(!CL || FP4, "the two-CTA cluster is wired for the fp4 count tile");
+  const uint32_t rank      = CL ? clusterCtaRank() : 0u;
+  const uint64_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
   constexpr int kStagesTC = MODE == kTcCount ? kStagesCount : kStagesMat;
   __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
   __shared__ uint32_t tmemBase;
@@ -218,7 +249,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     tmaPrefetchDesc(&tmB);
     for (int s = 0; s < kStagesTC; ++s) {
       mbarInit(&fullBar[s], 1);
-      mbarInit(&emptyBar[s], 1);
+      mbarInit(&emptyBar[s], CL ? 2 : 1);  // cluster: the MMAs of both CTAs read what the pair's producers overwrite
     }
     for (int s = 0; s < 2; ++s) {
       mbarInit(&tmemFull[s], 1);
@@ -240,6 +271,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
   __syncthreads();
   tcFenceAfter();
   const uint32_t tmem = tmemBase;
+  if constexpr (CL) clusterSync();  // the peer's barriers exist before anything is multicast at them
   if constexpr (FP4) {
     // every scale factor = 1.0: fill TMEM columns 448..511 of all 128 lanes (a warp reaches its own lane quarter)
     if (warp >= 2 && warp < 6) {
@@ -257,15 +289,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     if (lane == 0) {
       int      stage = 0;
       uint32_t phase = 0;
-      for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
+      for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
         uint32_t tm, tn;
-        if (!tileCoords<TN>(p, t, tm, tn)) continue;
+        if (!(CL ? tileCoordsPair<TN>(p, t, rank, tm, tn) : tileCoords<TN>(p, t, tm, tn))) continue;
         for (int kc = 0; kc < p.kChunks; ++kc) {
           mbarWait(&emptyBar[stage], phase ^ 1);
           uint8_t* dst = smemGen + stage * (kABytes + kBBytes);
           mbarExpectTx(&fullBar[stage], kABytes + kBBytes);
           tmaLoad2D(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
-          tmaLoad2D(dst + kABytes, &tmB, kc * kTK, tn * TN, &fullBar[stage]);
+          if constexpr (CL) {
+            // half of the shared column operand each, delivered to both CTAs (their barriers count the bytes)
+            constexpr int kHalfRows = TN / 2;
+            tmaLoad2DMulticast(dst + kABytes + rank * (kHalfRows * kTK), &tmB, kc * kTK, tn * TN + rank * kHalfRows, &fullBar[stage],
+                               static_cast<uint16_t>(3));
+          } else {
+            tmaLoad2D(dst + kABytes, &tmB, kc * kTK, tn * TN, &fullBar[stage]);
+          }
           if (++stage == kStagesTC) {
             stage = 0;
             phase ^= 1;
@@ -278,9 +317,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     if (lane == 0) {
       int      stage = 0;
       uint32_t phase = 0, local = 0;
-      for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
+      for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
         uint32_t tm, tn;
-        if (!tileCoords<TN>(p, t, tm, tn)) continue;
+        if (!(CL ? tileCoordsPair<TN>(p, t, rank, tm, tn) : tileCoords<TN>(p, t, tm, tn))) continue;
         const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
         mbarWait(&tmemEmpty[as], accPhase ^ 1);
         tcFenceAfter();
@@ -296,7 +335,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
             if constexpr (FP4) ummaMxf4(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u, tmem + 448, tmem + 480);
             else ummaI8(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u);
           }
-          ummaCommit(&emptyBar[stage]);  // frees the smem stage when these MMAs retire
+          if constexpr (CL) ummaCommitMulticast(&emptyBar[stage], static_cast<uint16_t>(3));
+          else ummaCommit(&emptyBar[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == kStagesTC) {
             stage = 0;
             phase ^= 1;
@@ -313,9 +353,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     const int      half    = ew >> 2;              // which half of the column blocks this warp takes
     const int      et      = ew * 32 + lane;       // thread index among the epilogue warps
     uint32_t       local   = 0;
-    for (uint64_t t = blockIdx.x; t < totalTiles; t += gridDim.x) {
+    for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
       uint32_t tm, tn;
-      if (!tileCoords<TN>(p, t, tm, tn)) continue;
+      if (!(CL ? tileCoordsPair<TN>(p, t, rank, tm, tn) : tileCoords<TN>(p, t, tm, tn))) continue;
       const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
       // stage this tile's column popcounts
       int minPb = 0x3fffffff;  // smallest |B| among this tile's valid columns (pre-filter of the threshold test)
@@ -475,6 +515,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
   }
   tcFenceBefore();
   __syncthreads();
+  if constexpr (CL) clusterSync();  // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tcFenceAfter();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -551,33 +592,55 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
 
   CUtensorMap tmA, tmB;
   makeTensorMap2D(&tmA, expX.get(), q.nX, rowBytes, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
-  makeTensorMap2D(&tmB, expY, q.nY, rowBytes, tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  const bool cluster = fp4 && g_tensorCluster;  // CTA pairs share the column operand through TMA multicast
+  makeTensorMap2D(&tmB, expY, q.nY, rowBytes, cluster ? tn / 2 : tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
   const size_t smemBytes = static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK) +
                            (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
   static bool  configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     configured = true;
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
   const uint64_t groupsM = (p.tilesM + kGroupTC - 1) / kGroupTC;
-  const uint64_t total   = groupsM * kGroupTC * p.tilesN;
+  const uint64_t total   = groupsM * (cluster ? kGroupTC / 2 : kGroupTC) * p.tilesN;  // tiles, or vertical tile pairs
   int            blocks  = smCount();
   if (static_cast<uint64_t>(blocks) > total) blocks = static_cast<int>(total);
   if (mode == kCountTanimoto) {
     PhaseTimer t("neighbor_pass_tc", s);
-    if (fp4) simTensorKernel<kTcCount, true><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
-    else simTensorKernel<kTcCount, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    if (cluster) {
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute attr[1];
+      attr[0].id               = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.blockDim         = dim3(kThreadsTC);
+      cfg.dynamicSmemBytes = smemBytes;
+      cfg.stream           = s;
+      cfg.attrs            = attr;
+      cfg.numAttrs         = 1;
+      cfg.gridDim          = dim3(2);
+      int maxClusters = 0;
+      B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, true>, &cfg));
+      B200_REQUIRE(maxClusters >= 1, "no CTA pair fits the device");
+      uint64_t pairs = maxClusters;  // persistent: one resident cluster per schedulable SM pair
+      if (pairs > total) pairs = total;
+      cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+      B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, true>, tmA, tmB, p, total));
+    } else if (fp4) simTensorKernel<kTcCount, true, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    else simTensorKernel<kTcCount, false, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcTanimoto, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcTanimoto, false, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
   } else {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcCosine, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcCosine, false, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
   }
   B200_LAUNCHED();
   return true;

@@ -93,6 +93,24 @@ __device__ __forceinline__ void tmaLoad2D(void* smemDst, const CUtensorMap* tm, 
     "l"(reinterpret_cast<uint64_t>(tm)), "r"(smemAddr(bar)), "r"(c0), "r"(c1)
     : "memory");
 }
+// The same load delivered to every CTA of the cluster named in ctaMask, at the same shared-memory offsets (data and
+// mbarrier) in each of them.
+__device__ __forceinline__ void tmaLoad2DMulticast(void* smemDst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar,
+                                                   uint16_t ctaMask) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+    "[%2], %5;" ::"r"(smemAddr(smemDst)),
+    "l"(reinterpret_cast<uint64_t>(tm)), "r"(smemAddr(bar)), "r"(c0), "r"(c1), "h"(ctaMask)
+    : "memory");
+}
+__device__ __forceinline__ uint32_t clusterCtaRank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void clusterSync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmaPrefetchDesc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
