@@ -39,9 +39,17 @@ uint64_t b200mol_launch_count(void);
 /* 0 when device `dev` is compute capability 10.x; B200MOL_ERR_NODEVICE otherwise. */
 int b200mol_check_device(int dev);
 int b200mol_free_async(void* d_ptr, void* stream);
-/* Tuning knobs. "similarity_tensor_min_pairs": pair count (nX * nY) from which the thresholded Tanimoto pass runs on
- * the tcgen05 int8 tensor-core tile instead of the SIMT popcount tile (default 2^24; 0 = always, < 0 = never).
- * "bfgs_ctas_per_sm": resident CTAs per SM of the minimiser / embedder kernels (default 4). */
+/* Tuning knobs (every setting computes the same results; tests/ run the variants against each other and the oracle):
+ *   "similarity_tensor_min_pairs"  pair count (nX * nY) from which the similarity passes run on the tcgen05 tensor-core
+ *                                  tile instead of the SIMT popcount tile (default 2^24; 0 = always, < 0 = never)
+ *   "similarity_tensor_fp4"        1 (default): the thresholded count pass feeds the tensor cores block-scaled fp4
+ *                                  operands (kind::mxf4, fingerprints of a multiple of 256 bits); 0: the int8 tile
+ *   "similarity_tensor_cluster"    1 (default): that tile runs in clusters of two CTAs sharing the column operand
+ *                                  through TMA multicast; 0: one CTA per tile
+ *   "butina_min_round_commits"     a parallel Butina round that commits fewer clusters than this hands over to the
+ *                                  one-cluster-per-step loop (default 32; 0 = rounds only, >= 1e9 = stepwise only)
+ *   "bfgs_ctas_per_sm"             resident CTAs per SM of the minimiser / embedder kernels (default 3 = the register
+ *                                  budget they are compiled for) */
 int b200mol_set_option(const char* key, long long value);
 /* Per-phase CUDA-event timing inside the library (off by default). Phases: "neighbor_pass" (the N^2 tile kernel
  * alone), "csr_build", "cluster_loop", "bfgs". b200mol_profile_read waits for the phase's stop event. */
