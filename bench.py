@@ -124,7 +124,7 @@ def run_reference(args) -> None:
     import oracle
     from nvmolkit_b200 import synthetic
 
-    cores = os.cpu_count() or 1
+    cores = oracle.set_threads(os.cpu_count() or 1)  # (torchrun exports OMP_NUM_THREADS=1 to its workers)
     n, _ = cpu_sample_size()
     if args.n_centres:
         n = min(n, args.n_centres * 50)
@@ -340,6 +340,7 @@ def run_b200(args) -> None:
     # CPU baseline (oracle port, OpenMP on the host cores) on a bounded sample + exact parity on that sample
     import oracle
 
+    cpu_threads = oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1 to its workers
     ns, _ = cpu_sample_size(target_s=12.0)
     if args.n_centres:
         ns = min(ns, n)
@@ -349,7 +350,7 @@ def run_b200(args) -> None:
     dt = time.perf_counter() - t0
     g_ids, g_cen = fused_butina_device(torch.from_numpy(fps.view(np.int32)).to(dev), CUTOFF)
     parity = bool((g_ids.cpu().numpy() == ids_cpu).all() and (g_cen.cpu().numpy() == cen_cpu).all())
-    out["cpu_baseline"] = {"value": unique_pairs(len(fps)) / dt, "unit": UNIT, "cores": os.cpu_count() or 1,
+    out["cpu_baseline"] = {"value": unique_pairs(len(fps)) / dt, "unit": UNIT, "cores": cpu_threads,
                            "kind": "port",
                            "sample": f"{len(fps)}x{len(fps)} clustered 2048-bit fingerprints, cutoff {CUTOFF}, {dt:.1f} s"}
     out["parity_on_sample"] = "bit-exact" if parity else "MISMATCH"
@@ -359,7 +360,7 @@ def run_b200(args) -> None:
         flat_b, mmff_b = path_b_pool(args.pool, synthetic.SEED)
         nb = min(args.etkdg_cpu_mols, path_b["n_mols"])
         v, dt_b, okf = run_path_b_cpu(flat_b, mmff_b, nb, path_b["confs_per_mol"])
-        path_b["cpu_baseline"] = {"value": v, "unit": "mols/s", "cores": os.cpu_count() or 1, "kind": "port",
+        path_b["cpu_baseline"] = {"value": v, "unit": "mols/s", "cores": cpu_threads, "kind": "port",
                                   "sample": f"{nb} mols x {path_b['confs_per_mol']} conformers, {dt_b:.1f} s, embedded {okf:.2f}"}
     print(json.dumps(out))
     if world > 1:

@@ -38,6 +38,14 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def set_threads(n: int = 0) -> int:
+    """Use n OpenMP threads (0 = leave as is); returns the team size the library will use."""
+    L = lib()
+    L.oracle_set_threads.argtypes = [C.c_int]
+    L.oracle_set_threads.restype = C.c_int
+    return int(L.oracle_set_threads(int(n)))
+
+
 def _p(a: np.ndarray, t):
     return a.ctypes.data_as(C.POINTER(t))
 

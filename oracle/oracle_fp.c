@@ -390,3 +390,10 @@ void oracle_morgan(const int32_t* atomStarts, const int32_t* bondStarts, const u
                       bondB + b0, radius, fpBits, out + (size_t)m * (fpBits / 32), NULL);
   }
 }
+
+/* Thread count of the OpenMP teams of this library (bench.py: torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU
+ * baseline must say how many threads it really used). Returns the resulting maximum team size. */
+int oracle_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
