@@ -29,8 +29,10 @@ constexpr int kTN       = 256;
 constexpr int kTK       = 128;  // bytes (= bits of the fingerprint) per K chunk
 constexpr int kStagesCount = 4;  // smem ring depth of the count mode
 constexpr int kStagesMat   = 3;  // materialise modes: one stage less, the space holds the reciprocal table
-constexpr int kEpiWarps  = 8;    // two warps per TMEM lane quarter, each takes half of the 256 columns
-constexpr int kThreadsTC = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kEpiWarpsCount = 8;   // count mode: two warps per TMEM lane quarter share the column blocks
+constexpr int kEpiWarpsMat   = 16;  // materialise modes: four per quarter (the fp64 epilogue is the long pole there)
+constexpr int epiWarps(int mode) { return mode == 0 ? kEpiWarpsCount : kEpiWarpsMat; }
+constexpr int threadsTC(int mode) { return 64 + 32 * epiWarps(mode); }  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kABytes   = kTM * kTK;
 constexpr int kBBytes   = kTN * kTK;
 constexpr int kTNFp4    = 224;  // fp4 count mode: 2 x 224 accumulator columns leave TMEM columns 448..511 for the scale factors
@@ -220,10 +222,11 @@ __device__ __forceinline__ bool tileCoordsPair(const TcParams& p, uint64_t t, ui
 }
 
 template <int MODE, bool FP4, bool CL>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+__global__ void __launch_bounds__(threadsTC(MODE), 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                   uint64_t totalTiles) {
   extern __shared__ __align__(1024) uint8_t smemRaw[];
+  constexpr int kEpiWarps = epiWarps(MODE), kThreadsTC = threadsTC(MODE), kParts = kEpiWarps / 4;
   constexpr int TN      = FP4 ? kTNFp4 : kTN;  // tile columns; the accumulator stages sit TN TMEM columns apart
   constexpr int kBBytes = TN * kTK;
   static_assert(!FP4 || MODE == kTcCount, "the fp4 tile serves the count mode");
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
     // ===================== epilogue (warps 2..5) =====================
     const int      ew      = warp - 2;             // 0..kEpiWarps-1
     const int      quarter = warp & 3;             // TMEM lane quarter this warp may read
-    const int      half    = ew >> 2;              // which half of the column blocks this warp takes
+    const int      part    = ew >> 2;              // which share of the column blocks this warp takes
     const int      et      = ew * 32 + lane;       // thread index among the epilogue warps
     uint32_t       local   = 0;
     for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
@@ -390,8 +393,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
       mbarWait(&tmemFull[as], accPhase);
       tcFenceAfter();
       int rowHits = 0;
-      constexpr int kCb = TN / 32, kCbHalf = (kCb + 1) / 2;  // column blocks of 32; the two warps of a quarter split them
-      for (int cb = half * kCbHalf; cb < (half ? kCb : kCbHalf); ++cb) {
+      constexpr int kCb = TN / 32, kCbPer = (kCb + kParts - 1) / kParts;  // column blocks of 32; the warps of a quarter split them
+      for (int cb = part * kCbPer; cb < min(kCb, (part + 1) * kCbPer); ++cb) {
         uint32_t r[32];
         tmemLoad32(tmem + as * TN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
         if constexpr (MODE != kTcCount) {
@@ -620,7 +623,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
       attr[0].val.clusterDim.x = 2;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
-      cfg.blockDim         = dim3(kThreadsTC);
+      cfg.blockDim         = dim3(threadsTC(kTcCount));
       cfg.dynamicSmemBytes = smemBytes;
       cfg.stream           = s;
       cfg.attrs            = attr;
@@ -633,14 +636,14 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
       if (pairs > total) pairs = total;
       cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
       B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, true>, tmA, tmB, p, total));
-    } else if (fp4) simTensorKernel<kTcCount, true, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
-    else simTensorKernel<kTcCount, false, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    } else if (fp4) simTensorKernel<kTcCount, true, false><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
+    else simTensorKernel<kTcCount, false, false><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcTanimoto, false, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcTanimoto, false, false><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, p, total);
   } else {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcCosine, false, false><<<blocks, kThreadsTC, smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcCosine, false, false><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, p, total);
   }
   B200_LAUNCHED();
   return true;
