@@ -413,7 +413,10 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       g_bfgsCtasPerSm = static_cast<int>(value);
     }
     else if (k == "similarity_tensor_fp4") g_tensorFp4 = value != 0;
-    else if (k == "similarity_tensor_cluster") g_tensorCluster = value != 0;
+    else if (k == "similarity_tensor_cluster") {
+      B200_REQUIRE(value >= 0 && value <= 2, "similarity_tensor_cluster must be 0, 1 or 2");
+      g_tensorCluster = static_cast<int>(value);
+    }
     else if (k == "butina_min_round_commits") {
       B200_REQUIRE(value >= 0, "butina_min_round_commits must be >= 0");
       g_butinaMinCommits = static_cast<int>(value > 1000000000 ? 1000000000 : value);  // huge = stepwise loop only

@@ -28,7 +28,8 @@ constexpr int kTM       = 128;
 constexpr int kTN       = 256;
 constexpr int kTK       = 128;  // bytes (= bits of the fingerprint) per K chunk
 constexpr int kStagesCount = 4;  // smem ring depth of the count mode
-constexpr int kStagesMat   = 3;  // materialise modes: one stage less, the space holds the reciprocal table
+constexpr int kStagesMat   = 3;
+constexpr int kStagesPair  = 6;  // pair-MMA count mode: 30 KB per stage and CTA  // materialise modes: one stage less, the space holds the reciprocal table
 constexpr int kEpiWarpsCount = 8;   // count mode: two warps per TMEM lane quarter share the column blocks
 constexpr int kEpiWarpsMat   = 16;  // materialise modes: four per quarter (the fp64 epilogue is the long pole there)
 constexpr int epiWarps(int mode) { return mode == 0 ? kEpiWarpsCount : kEpiWarpsMat; }
@@ -166,6 +167,23 @@ __device__ __forceinline__ void ummaCommitMulticast(uint64_t* bar, uint16_t ctaM
                "h"(ctaMask)
                : "memory");
 }
+// CTA-pair MMA (cta_group::2): M = 256 (128 rows in each CTA's TMEM), the N x K operand split across the two CTAs'
+// shared memory (N/2 rows each, same offsets), issued by the leader alone.
+constexpr uint32_t kIdescMxf4Pair = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTNFp4 >> 3) << 17) | (1u << 23) |
+                                    (static_cast<uint32_t>((2 * kTM) >> 4) << 24);
+__device__ __forceinline__ void ummaMxf4Pair(uint32_t tmemD, uint64_t aDesc, uint64_t bDesc, uint32_t accumulate, uint32_t tmemSfa,
+                                             uint32_t tmemSfb) {
+  asm volatile(
+    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmemD),
+    "l"(aDesc), "l"(bDesc), "r"(kIdescMxf4Pair), "r"(accumulate), "r"(tmemSfa), "r"(tmemSfb)
+    : "memory");
+}
+__device__ __forceinline__ void ummaCommitPairMulticast(uint64_t* bar, uint16_t ctaMask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smemAddr(bar)),
+               "h"(ctaMask)
+               : "memory");
+}
 __device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -221,7 +239,9 @@ __device__ __forceinline__ bool tileCoordsPair(const TcParams& p, uint64_t t, ui
   return true;
 }
 
-template <int MODE, bool FP4, bool CL>
+// CL: 0 = one CTA per tile; 1 = CTA pair, column operand multicast; 2 = CTA pair with cta_group::2 MMAs (each CTA stages
+// half of the column operand, the leader issues M = 256 instructions for both)
+template <int MODE, bool FP4, int CL>
 __global__ void __launch_bounds__(threadsTC(MODE), 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                   uint64_t totalTiles) {
@@ -233,7 +253,10 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   static_assert(!CL || FP4, "the two-CTA cluster is wired for the fp4 count tile");
   const uint32_t rank      = CL ? clusterCtaRank() : 0u;
   const uint64_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
-  constexpr int kStagesTC = MODE == kTcCount ? kStagesCount : kStagesMat;
+  constexpr bool P2          = CL == 2;
+  constexpr int  kBStage     = P2 ? kBBytes / 2 : kBBytes;  // bytes of the column operand one CTA stages per K chunk
+  constexpr int  kStageBytes = kABytes + kBStage;
+  constexpr int  kStagesTC   = P2 ? kStagesPair : (MODE == kTcCount ? kStagesCount : kStagesMat);
   __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
   __shared__ uint32_t tmemBase;
   __shared__ int      popB[2][kTN];
@@ -243,7 +266,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
 
   const uint32_t smemBase = (smemAddr(smemRaw) + 1023u) & ~1023u;
   uint8_t*       smemGen  = smemRaw + (smemBase - smemAddr(smemRaw));
-  uint16_t*      threshS  = reinterpret_cast<uint16_t*>(smemGen + kStagesTC * (kABytes + kBBytes));
+  uint16_t*      threshS  = reinterpret_cast<uint16_t*>(smemGen + kStagesTC * kStageBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -252,17 +275,22 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     tmaPrefetchDesc(&tmB);
     for (int s = 0; s < kStagesTC; ++s) {
       mbarInit(&fullBar[s], 1);
-      mbarInit(&emptyBar[s], CL ? 2 : 1);  // cluster: the MMAs of both CTAs read what the pair's producers overwrite
+      mbarInit(&emptyBar[s], CL == 1 ? 2 : 1);  // multicast pair: the MMAs of both CTAs read what the pair's producers overwrite
     }
     for (int s = 0; s < 2; ++s) {
       mbarInit(&tmemFull[s], 1);
-      mbarInit(&tmemEmpty[s], kEpiWarps);  // one arrival per epilogue warp
+      mbarInit(&tmemEmpty[s], P2 ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (pair MMA: of both CTAs, at the leader)
     }
     fenceBarrierInit();
   }
   if (warp == 1) {  // TMEM: 512 columns = two 128 x 256 s32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(&tmemBase)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (P2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(&tmemBase)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(&tmemBase)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   for (int i = threadIdx.x; i < 2 * p.threshLen; i += kThreadsTC) threshS[i] = p.thresh[i];  // table | its suffix-min
   const uint16_t* threshLoS = threshS + p.threshLen;
@@ -297,16 +325,25 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         if (!(CL ? tileCoordsPair<TN>(p, t, rank, tm, tn) : tileCoords<TN>(p, t, tm, tn))) continue;
         for (int kc = 0; kc < p.kChunks; ++kc) {
           mbarWait(&emptyBar[stage], phase ^ 1);
-          uint8_t* dst = smemGen + stage * (kABytes + kBBytes);
-          mbarExpectTx(&fullBar[stage], kABytes + kBBytes);
-          tmaLoad2D(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
-          if constexpr (CL) {
-            // half of the shared column operand each, delivered to both CTAs (their barriers count the bytes)
+          uint8_t* dst = smemGen + stage * kStageBytes;
+          if constexpr (P2) {
+            // both CTAs' loads are counted on the LEADER's barrier (it alone issues the MMAs); each CTA stages its own
+            // 128 rows and its half of the tile's columns
             constexpr int kHalfRows = TN / 2;
-            tmaLoad2DMulticast(dst + kABytes + rank * (kHalfRows * kTK), &tmB, kc * kTK, tn * TN + rank * kHalfRows, &fullBar[stage],
-                               static_cast<uint16_t>(3));
+            if (rank == 0) mbarExpectTx(&fullBar[stage], 2 * kStageBytes);
+            tmaLoad2DPair(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
+            tmaLoad2DPair(dst + kABytes, &tmB, kc * kTK, tn * TN + rank * kHalfRows, &fullBar[stage]);
           } else {
-            tmaLoad2D(dst + kABytes, &tmB, kc * kTK, tn * TN, &fullBar[stage]);
+            mbarExpectTx(&fullBar[stage], kABytes + kBBytes);
+            tmaLoad2D(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
+            if constexpr (CL == 1) {
+              // half of the shared column operand each, delivered to both CTAs (their barriers count the bytes)
+              constexpr int kHalfRows = TN / 2;
+              tmaLoad2DMulticast(dst + kABytes + rank * (kHalfRows * kTK), &tmB, kc * kTK, tn * TN + rank * kHalfRows,
+                                 &fullBar[stage], static_cast<uint16_t>(3));
+            } else {
+              tmaLoad2D(dst + kABytes, &tmB, kc * kTK, tn * TN, &fullBar[stage]);
+            }
           }
           if (++stage == kStagesTC) {
             stage = 0;
@@ -317,7 +354,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && !(P2 && rank != 0)) {  // (pair MMA: the leader issues for both CTAs)
       int      stage = 0;
       uint32_t phase = 0, local = 0;
       for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
@@ -330,22 +367,25 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         for (int kc = 0; kc < p.kChunks; ++kc) {
           mbarWait(&fullBar[stage], phase);
           tcFenceAfter();
-          const uint32_t aAddr = smemBase + stage * (kABytes + kBBytes);
+          const uint32_t aAddr = smemBase + stage * kStageBytes;
           const uint64_t aDesc = makeSmemDesc(aAddr), bDesc = makeSmemDesc(aAddr + kABytes);
 #pragma unroll
           for (int k = 0; k < kTK / 32; ++k)  // K = 32 bytes per instruction: +32 B = +2 in the 16-byte address field
           {
-            if constexpr (FP4) ummaMxf4(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u, tmem + 448, tmem + 480);
+            if constexpr (P2) ummaMxf4Pair(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u, tmem + 448, tmem + 480);
+            else if constexpr (FP4) ummaMxf4(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u, tmem + 448, tmem + 480);
             else ummaI8(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u);
           }
-          if constexpr (CL) ummaCommitMulticast(&emptyBar[stage], static_cast<uint16_t>(3));
+          if constexpr (P2) ummaCommitPairMulticast(&emptyBar[stage], static_cast<uint16_t>(3));
+          else if constexpr (CL == 1) ummaCommitMulticast(&emptyBar[stage], static_cast<uint16_t>(3));
           else ummaCommit(&emptyBar[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == kStagesTC) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ummaCommit(&tmemFull[as]);
+        if constexpr (P2) ummaCommitPairMulticast(&tmemFull[as], static_cast<uint16_t>(3));  // both CTAs' epilogues
+        else ummaCommit(&tmemFull[as]);
         ++local;
       }
     }
@@ -504,7 +544,10 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       }
       tcFenceBefore();
       __syncwarp();
-      if (lane == 0) mbarArrive(&tmemEmpty[as]);  // accumulator may be overwritten
+      if (lane == 0) {  // accumulator may be overwritten
+        if (P2 && rank != 0) mbarArriveRemote(&tmemEmpty[as], 0);
+        else mbarArrive(&tmemEmpty[as]);
+      }
       if (MODE == kTcCount && rowHits) atomicAdd(p.counts + gr, p.sign * rowHits);
       if (MODE == kTcCount && p.countsY) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -521,7 +564,8 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   if constexpr (CL) clusterSync();  // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tcFenceAfter();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if constexpr (P2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
 }
 
@@ -595,18 +639,21 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
 
   CUtensorMap tmA, tmB;
   makeTensorMap2D(&tmA, expX.get(), q.nX, rowBytes, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
-  const bool cluster = fp4 && g_tensorCluster;  // CTA pairs share the column operand through TMA multicast
+  const bool cluster = fp4 && g_tensorCluster != 0;  // CTA pairs: 1 = multicast column operand, 2 = cta_group::2 MMAs
+  const bool pairMma = cluster && g_tensorCluster == 2;
   makeTensorMap2D(&tmB, expY, q.nY, rowBytes, cluster ? tn / 2 : tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
-  const size_t smemBytes = static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK) +
+  const size_t smemBytes = (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
+                                    : static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK)) +
                            (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
   static bool  configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     configured = true;
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
@@ -630,20 +677,22 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
       cfg.numAttrs         = 1;
       cfg.gridDim          = dim3(2);
       int maxClusters = 0;
-      B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, true>, &cfg));
+      if (pairMma) B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, 2>, &cfg));
+      else B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, 1>, &cfg));
       B200_REQUIRE(maxClusters >= 1, "no CTA pair fits the device");
       uint64_t pairs = maxClusters;  // persistent: one resident cluster per schedulable SM pair
       if (pairs > total) pairs = total;
       cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-      B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, true>, tmA, tmB, p, total));
-    } else if (fp4) simTensorKernel<kTcCount, true, false><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
-    else simTensorKernel<kTcCount, false, false><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
+      if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, p, total));
+      else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, p, total));
+    } else if (fp4) simTensorKernel<kTcCount, true, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
+    else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcTanimoto, false, false><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcTanimoto, false, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, p, total);
   } else {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcCosine, false, false><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, p, total);
   }
   B200_LAUNCHED();
   return true;

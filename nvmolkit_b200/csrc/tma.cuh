@@ -103,6 +103,24 @@ __device__ __forceinline__ void tmaLoad2DMulticast(void* smemDst, const CUtensor
     "l"(reinterpret_cast<uint64_t>(tm)), "r"(smemAddr(bar)), "r"(c0), "r"(c1), "h"(ctaMask)
     : "memory");
 }
+// CTA-pair (cta_group::2) load: data lands in THIS CTA's shared memory, the bytes are counted on the barrier at the same
+// offset in the pair's LEADER (rank 0): clearing the peer bit of the shared::cluster address names the leader's copy
+// (cute/arch/copy_sm100_tma.hpp, Sm100MmaPeerBitMask).
+__device__ __forceinline__ void tmaLoad2DPair(void* smemDst, const CUtensorMap* tm, int c0, int c1, uint64_t* leaderBar) {
+  asm volatile(
+    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+      smemAddr(smemDst)),
+    "l"(reinterpret_cast<uint64_t>(tm)), "r"(smemAddr(leaderBar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+    : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbarArriveRemote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+    "{\n\t.reg .b32 r;\n\tmapa.shared::cluster.u32 r, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [r];\n\t}" ::"r"(
+      smemAddr(bar)),
+    "r"(rank)
+    : "memory");
+}
 __device__ __forceinline__ uint32_t clusterCtaRank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -285,7 +285,11 @@ def test_butina_parallel_rounds_keep_the_greedy_order(cuda, min_commits, n, degr
 def force_tensor_path(cuda):
     from nvmolkit_b200 import _lib
 
+    import os
+
     _lib.set_option("similarity_tensor_min_pairs", 0)
+    if os.environ.get("B200_TENSOR_CLUSTER"):  # exercise another tile variant with the same tests (0, 1 or 2)
+        _lib.set_option("similarity_tensor_cluster", int(os.environ["B200_TENSOR_CLUSTER"]))
     yield
     _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
 
