@@ -200,12 +200,28 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// linear tile index -> (tm, tn): groups of kGroupTC tile-rows sweep the tile-columns
+// Work units in launch order: groups of kGroupTC tile-rows sweep the tile-columns (L2 reuse of the row operand). A CTA
+// walks its units t, t + step, ... keeping (group, index in group) incrementally: no 64-bit division per tile.
+struct UnitWalk {
+  uint64_t t, total;
+  uint32_t step, group, inGroup, perGroup;
+  __device__ UnitWalk(uint64_t first, uint64_t stepBy, uint64_t totalUnits, uint32_t unitsPerGroup)
+      : t(first), total(totalUnits), step(static_cast<uint32_t>(stepBy)), group(static_cast<uint32_t>(first / unitsPerGroup)),
+        inGroup(static_cast<uint32_t>(first % unitsPerGroup)), perGroup(unitsPerGroup) {}
+  __device__ bool more() const { return t < total; }
+  __device__ void next() {
+    t += step;
+    inGroup += step;
+    while (inGroup >= perGroup) {
+      inGroup -= perGroup;
+      ++group;
+    }
+  }
+};
+
+// (group, index in group) -> (tm, tn), one tile per unit
 template <int TN>
-__device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32_t& tm, uint32_t& tn) {
-  const uint64_t perGroup = static_cast<uint64_t>(kGroupTC) * p.tilesN;
-  const uint32_t group    = static_cast<uint32_t>(t / perGroup);
-  const uint32_t inGroup  = static_cast<uint32_t>(t % perGroup);
+__device__ __forceinline__ bool tileCoords(const TcParams& p, uint32_t group, uint32_t inGroup, uint32_t& tm, uint32_t& tn) {
   if (group * kGroupTC >= p.tilesM) return false;
   if (group % p.groupStride != p.groupOffset) return false;
   const uint32_t gRows = min(static_cast<uint32_t>(kGroupTC), p.tilesM - group * kGroupTC);
@@ -218,14 +234,12 @@ __device__ __forceinline__ bool tileCoords(const TcParams& p, uint64_t t, uint32
 }
 
 // Cluster of two CTAs: one unit = two vertically adjacent tiles (tile rows 2 tp, 2 tp + 1) of the same tile column; the
-// two CTAs share the column operand (each loads half of it and multicasts). Same row-group partition as tileCoords.
+// two CTAs share the column operand. Same row-group partition as tileCoords.
 template <int TN>
-__device__ __forceinline__ bool tileCoordsPair(const TcParams& p, uint64_t t, uint32_t rank, uint32_t& tm, uint32_t& tn) {
+__device__ __forceinline__ bool tileCoordsPair(const TcParams& p, uint32_t group, uint32_t inGroup, uint32_t rank, uint32_t& tm,
+                                               uint32_t& tn) {
   constexpr uint32_t kPairGroup = kGroupTC / 2;
   const uint32_t     pairRows   = (p.tilesM + 1) / 2;
-  const uint64_t     perGroup   = static_cast<uint64_t>(kPairGroup) * p.tilesN;
-  const uint32_t     group      = static_cast<uint32_t>(t / perGroup);
-  const uint32_t     inGroup    = static_cast<uint32_t>(t % perGroup);
   if (group * kPairGroup >= pairRows) return false;
   if (group % p.groupStride != p.groupOffset) return false;
   const uint32_t gRows = min(kPairGroup, pairRows - group * kPairGroup);
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   static_assert(!CL || FP4, "the two-CTA cluster is wired for the fp4 count tile");
   const uint32_t rank      = CL ? clusterCtaRank() : 0u;
   const uint64_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
+  const uint32_t unitsPerGroup = (CL ? kGroupTC / 2 : kGroupTC) * p.tilesN;
   constexpr bool P2          = CL == 2;
   constexpr int  kBStage     = P2 ? kBBytes / 2 : kBBytes;  // bytes of the column operand one CTA stages per K chunk
   constexpr int  kStageBytes = kABytes + kBStage;
@@ -320,9 +335,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     if (lane == 0) {
       int      stage = 0;
       uint32_t phase = 0;
-      for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
+      for (UnitWalk w(firstUnit, unitStep, totalTiles, unitsPerGroup); w.more(); w.next()) {
         uint32_t tm, tn;
-        if (!(CL ? tileCoordsPair<TN>(p, t, rank, tm, tn) : tileCoords<TN>(p, t, tm, tn))) continue;
+        if (!(CL ? tileCoordsPair<TN>(p, w.group, w.inGroup, rank, tm, tn) : tileCoords<TN>(p, w.group, w.inGroup, tm, tn))) continue;
         for (int kc = 0; kc < p.kChunks; ++kc) {
           mbarWait(&emptyBar[stage], phase ^ 1);
           uint8_t* dst = smemGen + stage * kStageBytes;
@@ -357,9 +372,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     if (lane == 0 && !(P2 && rank != 0)) {  // (pair MMA: the leader issues for both CTAs)
       int      stage = 0;
       uint32_t phase = 0, local = 0;
-      for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
+      for (UnitWalk w(firstUnit, unitStep, totalTiles, unitsPerGroup); w.more(); w.next()) {
         uint32_t tm, tn;
-        if (!(CL ? tileCoordsPair<TN>(p, t, rank, tm, tn) : tileCoords<TN>(p, t, tm, tn))) continue;
+        if (!(CL ? tileCoordsPair<TN>(p, w.group, w.inGroup, rank, tm, tn) : tileCoords<TN>(p, w.group, w.inGroup, tm, tn))) continue;
         const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
         mbarWait(&tmemEmpty[as], accPhase ^ 1);
         tcFenceAfter();
@@ -396,19 +411,27 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     const int      part    = ew >> 2;              // which share of the column blocks this warp takes
     const int      et      = ew * 32 + lane;       // thread index among the epilogue warps
     uint32_t       local   = 0;
-    for (uint64_t t = firstUnit; t < totalTiles; t += unitStep) {
+    uint32_t       tnOf[2] = {0, 0};  // tile column each accumulator-side buffer last served
+    for (UnitWalk w(firstUnit, unitStep, totalTiles, unitsPerGroup); w.more(); w.next()) {
       uint32_t tm, tn;
-      if (!(CL ? tileCoordsPair<TN>(p, t, rank, tm, tn) : tileCoords<TN>(p, t, tm, tn))) continue;
+      if (!(CL ? tileCoordsPair<TN>(p, w.group, w.inGroup, rank, tm, tn) : tileCoords<TN>(p, w.group, w.inGroup, tm, tn))) continue;
       const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
       // stage this tile's column popcounts
       int minPb = 0x3fffffff;  // smallest |B| among this tile's valid columns (pre-filter of the threshold test)
       for (int c = et; c < TN; c += 32 * kEpiWarps) {
+        if (MODE == kTcCount && p.countsY && local >= 2) {
+          // column counts this buffer collected two tiles ago: every warp finished that tile before it passed the
+          // staging barrier of the tile in between, so no barrier of its own is needed for the flush
+          const int v = colAcc[as][c];
+          if (v) atomicAdd(p.countsY + tnOf[as] * TN + c, p.sign * v);
+        }
         const uint32_t gc = tn * TN + c;
         const int      pb = gc < p.nY ? __ldg(p.popY + gc) : 0;
         popB[as][c]       = pb;
         colAcc[as][c]     = 0;
         if (gc < p.nY) minPb = min(minPb, pb);
       }
+      tnOf[as] = tn;
       if constexpr (MODE == kTcCount) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) minPb = min(minPb, __shfl_xor_sync(0xffffffffu, minPb, o));
@@ -549,14 +572,17 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         else mbarArrive(&tmemEmpty[as]);
       }
       if (MODE == kTcCount && rowHits) atomicAdd(p.counts + gr, p.sign * rowHits);
-      if (MODE == kTcCount && p.countsY) {
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      ++local;
+    }
+    if (MODE == kTcCount && p.countsY) {  // the last two tiles' column counts
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      for (uint32_t back = 1; back <= 2 && back <= local; ++back) {
+        const uint32_t b = (local - back) & 1;
         for (int c = et; c < TN; c += 32 * kEpiWarps) {
-          const int v = colAcc[as][c];
-          if (v) atomicAdd(p.countsY + tn * TN + c, p.sign * v);
+          const int v = colAcc[b][c];
+          if (v) atomicAdd(p.countsY + tnOf[b] * TN + c, p.sign * v);
         }
       }
-      ++local;
     }
   }
   tcFenceBefore();
