@@ -116,10 +116,10 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   const int    maxN = FF::kDim * maxAtoms;
   const size_t smem = static_cast<size_t>(kBfgsVectors + (FF::kHasRef ? 1 : 0)) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large for the shared-memory BFGS (%d atoms)", maxAtoms);
-  static size_t configured = 0;  // per instantiation
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[kMaxDevices] = {};  // per instantiation and device
+  if (smem > 48 * 1024 && smem > configured[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(bfgsKernel<FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+    configured[currentDeviceSlot()] = 200 * 1024;
   }
   int perSm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, bfgsKernel<FF>, kT, smem));
@@ -147,10 +147,10 @@ void runEnergyGrad(const typename FF::System& sys, const typename FF::Params& pa
   const int    maxN = FF::kDim * maxAtoms;
   const size_t smem = static_cast<size_t>(2) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large (%d atoms)", maxAtoms);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[kMaxDevices] = {};
+  if (smem > 48 * 1024 && smem > configured[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(energyGradKernel<FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+    configured[currentDeviceSlot()] = 200 * 1024;
   }
   int blocks = smCount() * 4;
   if (blocks > nConf) blocks = nConf;

@@ -96,13 +96,25 @@ struct Scratch {
   T* get() const { return p; }
 };
 
-inline int smCount() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
+inline int smCount() {  // of the current device
+  static int cached[64] = {};
+  int        dev        = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = v > 0 ? v : 148;
+  }
+  return cached[dev];
+}
+
+// Function attributes (dynamic shared-memory limits) belong to the device's context: a process that drives several
+// GPUs (HardwareOptions.gpuIds / targetGpu) must set them once per DEVICE, not once per process.
+constexpr int kMaxDevices = 64;
+inline int currentDeviceSlot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
 }
 
 inline cudaStream_t asStream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -370,10 +370,10 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     const int    maxN = 4 * max_atoms;
     const size_t smem = static_cast<size_t>(kBfgsVectors + 1) * maxN * sizeof(double);
     B200_REQUIRE(max_atoms > 0 && smem <= 200 * 1024, "molecule too large for the shared-memory embedder (%d atoms)", max_atoms);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    if (!configured[currentDeviceSlot()]) {
       B200_CUDA(cudaFuncSetAttribute(etkdgKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
+      configured[currentDeviceSlot()] = true;
     }
     int perSm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, etkdgKernel, kT, smem));
@@ -408,10 +408,10 @@ extern "C" int b200mol_etkdg_check(const b200mol_dg_system* dg, const b200mol_et
     B200_REQUIRE(d_slot_mol && d_slot_atom_start && d_pos4 && d_fail_masks, "null pointer");
     const size_t smem = static_cast<size_t>(4) * max_atoms * sizeof(double);
     B200_REQUIRE(max_atoms > 0 && smem <= 200 * 1024, "molecule too large (%d atoms)", max_atoms);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    if (!configured[currentDeviceSlot()]) {
       B200_CUDA(cudaFuncSetAttribute(etkdgCheckKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
+      configured[currentDeviceSlot()] = true;
     }
     int blocks = smCount() * 4;
     if (blocks > nSlots) blocks = nSlots;

@@ -253,10 +253,10 @@ extern "C" int b200mol_morgan(const int32_t* d_atom_starts, const int32_t* d_bon
     int warps = static_cast<int>(budget / 2 / L.total);  // two CTAs per SM when the slab is small
     warps     = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
     const size_t smemBytes = static_cast<size_t>(warps) * L.total;
-    static size_t configured = 0;
-    if (smemBytes > configured) {
+    static size_t configured[kMaxDevices] = {};
+    if (smemBytes > configured[currentDeviceSlot()]) {
       B200_CUDA(cudaFuncSetAttribute(morganKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
-      configured = budget;
+      configured[currentDeviceSlot()] = budget;
     }
     Scratch<int> err(1, s);
     B200_CUDA(cudaMemsetAsync(err.get(), 0, sizeof(int), s));

@@ -278,10 +278,10 @@ __global__ void __launch_bounds__(kThreads, 2)
 
 template <int MODE>
 void launchTile(const CUtensorMap& tmX, const CUtensorMap& tmY, const TileParams& tp, size_t smemBytes, cudaStream_t s) {
-  static bool attrSet = false;
-  if (!attrSet) {
+  static bool attrSet[kMaxDevices] = {};  // per instantiation and device
+  if (!attrSet[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(simTileKernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attrSet = true;
+    attrSet[currentDeviceSlot()] = true;
   }
   const uint64_t groupsM = (tp.tilesM + kGroupM - 1) / kGroupM;
   if (tp.groupOffset >= groupsM) return;

@@ -672,15 +672,15 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   const size_t smemBytes = (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
                                     : static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK)) +
                            (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
-  static bool  configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (!configured[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    configured = true;
+    configured[currentDeviceSlot()] = true;
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
   const uint64_t groupsM = (p.tilesM + kGroupTC - 1) / kGroupTC;
