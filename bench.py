@@ -319,7 +319,7 @@ def run_b200(args) -> None:
     out = {
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u32 popcount + f64 threshold", "data": "synthetic",
+        "vs_baseline": None, "dtype": "e2m1 0/1 x e2m1 0/1 -> f32 (exact integer counts), integer threshold test = the f64 predicate", "data": "synthetic",
         "config": {"workload": "1Mx1M symmetric 2048-bit Tanimoto + Butina (sim>=0.7)" if n == 1_000_000 else
                    f"{n}x{n} symmetric 2048-bit Tanimoto + Butina (sim>=0.7) [reduced size override]",
                    "n_fingerprints": n, "fp_bits": words * 32, "cutoff": CUTOFF, "pairs_counted": "unique n(n-1)/2",
