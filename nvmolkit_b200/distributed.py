@@ -43,3 +43,38 @@ def all_gather_v(t: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tenso
     dist.all_gather_into_tensor(gathered, padded, group=group)
     parts = [gathered[r * mx: r * mx + int(sizes_h[r])] for r in range(world)]
     return torch.cat(parts, dim=0), sizes_h
+
+
+def map_molecule_range(n_items: int, compute, group=None) -> torch.Tensor:
+    """Run `compute(lo, hi) -> tensor[hi - lo, ...]` on this rank's contiguous share of `n_items` independent items
+    (molecules, fingerprint rows) and return the results of all ranks, concatenated in item order, on every rank.
+    The one collective is the all-gather-v of the results (Morgan fingerprints, conformer results)."""
+    rank, world = rank_world(group)
+    lo, hi = molecule_range(n_items, rank, world)
+    part = compute(lo, hi)
+    if part.shape[0] != hi - lo:
+        raise ValueError(f"compute({lo}, {hi}) returned {part.shape[0]} rows")
+    out, _ = all_gather_v(part, group)
+    return out
+
+
+def sharded_fingerprints(generator, graphs, group=None) -> torch.Tensor:
+    """Morgan fingerprints of a MolGraphBatch computed by molecule range on every rank, all-gathered: int32 [n, words]."""
+    import numpy as np
+
+    def compute(lo, hi):
+        if hi == lo:
+            return torch.empty((0, generator.fpSize // 32), dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        return generator.GetFingerprints(graphs.select(np.arange(lo, hi))).torch()
+
+    return map_molecule_range(len(graphs), compute, group)
+
+
+def sharded_cross_similarity(fp_a: torch.Tensor, fp_b: torch.Tensor, metric: str = "tanimoto", group=None):
+    """Rows of A sharded, B replicated; the matrix stays distributed (no collective): returns (rows [hi-lo, m], lo, hi)."""
+    from nvmolkit_b200.similarity import crossCosineSimilarity, crossTanimotoSimilarity
+
+    rank, world = rank_world(group)
+    lo, hi = molecule_range(fp_a.shape[0], rank, world)
+    fn = crossTanimotoSimilarity if metric == "tanimoto" else crossCosineSimilarity
+    return fn(fp_a[lo:hi].contiguous(), fp_b).torch(), lo, hi

@@ -43,6 +43,11 @@ _WORKER = textwrap.dedent("""
     counts = torch.full((4,), rank + 1, dtype=torch.int32)
     dist.all_reduce(counts)
     assert counts.tolist() == [3, 3, 3, 3]
+    from nvmolkit_b200.distributed import map_molecule_range
+    rows = map_molecule_range(11, lambda lo, hi: torch.arange(lo, hi, dtype=torch.int64).reshape(-1, 1) * 10)
+    assert rows.ravel().tolist() == [10 * i for i in range(11)]  # item order preserved, every rank has everything
+    rows = map_molecule_range(1, lambda lo, hi: torch.arange(lo, hi, dtype=torch.int64).reshape(-1, 1))  # one rank gets nothing
+    assert rows.ravel().tolist() == [0]
     dist.destroy_process_group()
     print("rank", rank, "ok")
 """)
