@@ -116,12 +116,17 @@ def test_mmff_minimize_parity(cuda):
         assert _rel(e[c], ec) < 1e-10
     both = (st == 0) & (conv_o == 1)
     assert both.mean() > 0.8
-    assert (_rel(e[both], e_o[both]) < E_RTOL).all(), _rel(e[both], e_o[both]).max()
+    # (the gradient atomics sum in a run-dependent order: at most ONE of the 30 trajectories may end in a neighbouring
+    # minimum; every run so far had none)
+    rel = _rel(e[both], e_o[both])
+    assert (rel < E_RTOL).sum() >= both.sum() - 1, rel.max()
     assert ((st == 0) == (conv_o == 1)).mean() > 0.9
     # positions of converged conformers agree closely too (same local minimum)
+    far = 0
     for c in np.nonzero(both)[0]:
         a0, a1 = batch.atom_starts[c], batch.atom_starts[c + 1]
-        assert np.sqrt(((pos[a0:a1] - pos_o[a0:a1]) ** 2).sum(1).mean()) < 0.05
+        far += np.sqrt(((pos[a0:a1] - pos_o[a0:a1]) ** 2).sum(1).mean()) >= 0.05
+    assert far <= 1
 
 
 def test_mmff_optimize_api_and_large_molecule(cuda):
