@@ -142,10 +142,26 @@ int b200mol_morgan(const int32_t* d_atom_starts, const int32_t* d_bond_starts, c
  * themselves are passed from host memory.
  * ---------------------------------------------------------------------------------------- */
 typedef struct b200mol_term_table {
-  const int32_t* starts; /* [nMols+1] */
-  const int16_t* idx;    /* [n][K] */
-  const double*  par;    /* [n][P] */
+  const int32_t* starts;   /* [nMols+1] */
+  const int16_t* idx;      /* [n][K] */
+  const double*  par;      /* [n][P] */
+  /* Gradient schedule (b200mol_schedule_waves): the terms of molecule m are ordered in WAVES molWaves[m] ..
+   * molWaves[m+1]; wave w holds the terms waves[w] .. waves[w+1] (global term indices), at most 32 of them, no atom
+   * twice. A warp takes a wave at a time and adds the gradient contributions without atomics. Required by every entry
+   * point that evaluates gradients (energy-only calls and the ETKDG check tables ignore it; NULL there is fine). */
+  const int32_t* molWaves; /* [nMols+1] */
+  const int32_t* waves;    /* [nWaves+1] */
 } b200mol_term_table;
+
+/* HOST helper (no device work): orders the terms of one table into atom-disjoint waves of at most 32.
+ *   h_starts[nMols+1], h_idx[n][K]   the table (host memory), K in 1..8
+ *   h_perm[n]        out: new position p holds old term h_perm[p] (apply to idx AND par before the upload)
+ *   h_mol_waves[nMols+1], h_waves[n+1]  out (h_waves gets *n_waves + 1 entries)
+ * Dense pair tables (K = 2, >= 2 terms per atom) take the rounds of a round-robin tournament, (i + j) mod M with M the
+ * odd number >= the atom count: every round is a perfect matching, so all-pairs tables fill their waves; everything
+ * else takes a first-fit colouring. Deterministic. The reference has no counterpart (it scatters with atomics). */
+int b200mol_schedule_waves(int32_t nMols, const int32_t* h_starts, const int16_t* h_idx, int K, int32_t* h_perm,
+                           int32_t* h_mol_waves, int32_t* h_waves, int64_t* n_waves);
 
 /* MMFF94 (term math: src/forcefields/mmff_kernels_device.cuh:241-661; layout source: src/forcefields/mmff.h:37-145)
  *   bond    K2 P2 {r0, kb}                  angle   K3 P3 {theta0, ka, isLinear}

@@ -121,20 +121,27 @@ def fused_butina(x, cutoff: float, return_centroids: bool = False, stream=None, 
     centroid first, cluster_sizes the cumulative sizes starting at 0.
     """
     ids, cen = fused_butina_device(x, cutoff, stream=stream, metric=metric)
-    ids_h = ids.cpu().numpy()
-    cen_h = cen.cpu().numpy()
-    k = len(cen_h)
-    order = ids_h.argsort(kind="stable")
-    counts = [0] * k
-    for c in ids_h:
-        counts[c] += 1
-    clusters, sizes, at = [], [0], 0
-    for c in range(k):
-        members = order[at:at + counts[c]].tolist()
-        at += counts[c]
-        centroid = int(cen_h[c])
-        clusters.append(tuple([centroid] + [m for m in members if m != centroid]))
-        sizes.append(sizes[-1] + counts[c])
+    clusters, sizes = clusters_from_ids(ids.cpu().numpy(), cen.cpu().numpy())
     if return_centroids:
-        return clusters, sizes, [int(c) for c in cen_h]
+        return clusters, sizes, cen.cpu().numpy().tolist()
     return clusters, sizes
+
+
+def clusters_from_ids(ids_h, cen_h):
+    """(cluster ids [N], centroids [K]) -> the reference's output format (nvmolkit/clustering.py:171-189): list of
+    tuples, centroid first then the other members in ascending index order, and the cumulative sizes starting at 0.
+    NumPy only: one stable argsort + one split, no per-point Python loop (1M points: tens of milliseconds)."""
+    import numpy as np
+
+    ids_h = np.asarray(ids_h)
+    cen_h = np.asarray(cen_h)
+    k = len(cen_h)
+    counts = np.bincount(ids_h, minlength=k)
+    sizes = np.concatenate([[0], np.cumsum(counts)])
+    # sort key: (cluster id, not-the-centroid, index) -> the centroid leads its cluster, members follow ascending
+    n = len(ids_h)
+    idx = np.arange(n, dtype=np.int64)
+    is_member = (cen_h[ids_h] != idx).astype(np.int64) if k else np.zeros(0, np.int64)
+    order = np.argsort((ids_h.astype(np.int64) * 2 + is_member) * max(n, 1) + idx)
+    clusters = [tuple(part.tolist()) for part in np.split(order, sizes[1:-1])] if k else []
+    return clusters, sizes.tolist()

@@ -4,13 +4,15 @@
 // backend (src/minimizer/bfgs_minimize.cu:80-918, src/minimizer/bfgs_hessian.cu:37-239), all in fp64.
 //
 // B200 design (differs from the reference's bfgsMinimizeKernel, bfgs_minimize_permol_kernels.cu:426-743):
-//   * persistent grid (2 CTAs per SM) pulling conformers from an atomic queue -> no tail from uneven convergence and no
+//   * persistent grid (3 CTAs per SM) pulling conformers from an atomic queue -> no tail from uneven convergence and no
 //     size buckets / host-driven fallback for molecules above 64 atoms;
 //   * term tables are per MOLECULE with local int16 indices, shared by all conformers of that molecule;
 //   * positions, gradient, direction, trial point, dGrad and H*dGrad live in shared memory for any molecule size;
-//   * the inverse Hessian is a per-CTA slab that stays hot in the 126 MB L2, updated with a fused
-//     "rank-2 update + next direction" pass (H read twice and written once per iteration, warp-per-row, coalesced);
-//   * no global atomics: gradients accumulate with shared-memory fp64 atomics.
+//   * the inverse Hessian is a per-CTA slab, ONE sweep over its upper triangle per iteration with the rank-2 update of the
+//     previous iteration applied on the way (bfgs_device.cuh);
+//   * no atomics at all: gradients are scattered wave by wave (atom-disjoint groups of 32 terms scheduled by the host,
+//     b200mol_schedule_waves) into per-warp shared-memory accumulators and reduced in a fixed order, the sweep's
+//     row / column sums likewise -> a minimisation is bit-reproducible run to run.
 #include "bfgs_device.cuh"
 #include "profile.cuh"
 
@@ -41,9 +43,10 @@ template <class FF>
 __global__ void __launch_bounds__(kT, kMinCtas) bfgsKernel(const typename FF::System sys, const typename FF::Params par, const Batch b) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kRed];
+  __shared__ double                     colBuf[kColBuf];
   __shared__ int                        nextConf;
   constexpr int                         DIM = FF::kDim;
-  const BfgsWork w = carveWork(sm, b.maxN, b.hessWs + static_cast<size_t>(blockIdx.x) * b.hessStride, red);
+  const BfgsWork w = carveWork(sm, b.maxN, b.hessWs + static_cast<size_t>(blockIdx.x) * b.hessStride, red, colBuf);
   const int      tid = threadIdx.x;
   for (;;) {
     __syncthreads();
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kT) energyGradKernel(const typename FF::System
   __shared__ double                     red[kRed];
   constexpr int                         DIM = FF::kDim;
   double*                               pos  = sm;
-  double*                               grad = sm + maxN;
+  double*                               grad = sm + maxN;  // kWarps accumulators; the reduced gradient ends up in the first
   for (int conf = blockIdx.x; conf < nConf; conf += gridDim.x) {
     const int mol = confMol ? confMol[conf] : conf;
     const int a0  = confAtomStart[conf];
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(kT) energyGradKernel(const typename FF::System
     const double e = energyOf<FF>(view, pos, red);
     if (threadIdx.x == 0) energy[conf] = e;
     if (gradOut) {
-      gradOf<FF>(view, pos, grad, n);
+      gradOf<FF>(view, pos, grad, maxN, n);
       for (int i = threadIdx.x; i < n; i += kT) gradOut[static_cast<size_t>(a0) * DIM + i] = grad[i];
     }
   }
@@ -113,6 +116,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   if (nConf == 0) return;
   B200_REQUIRE(nConf > 0 && maxAtoms > 0 && maxIters >= 0, "bad batch arguments");
   B200_REQUIRE(confAtomStart && pos && energy, "null pointer");
+  ff::requireSchedule(sys);
   const int    maxN = FF::kDim * maxAtoms;
   const size_t smem = static_cast<size_t>(kBfgsVectors + (FF::kHasRef ? 1 : 0)) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large for the shared-memory BFGS (%d atoms)", maxAtoms);
@@ -144,8 +148,9 @@ void runEnergyGrad(const typename FF::System& sys, const typename FF::Params& pa
                    cudaStream_t s) {
   if (nConf == 0) return;
   B200_REQUIRE(confAtomStart && pos && energy, "null pointer");
+  if (grad) ff::requireSchedule(sys);
   const int    maxN = FF::kDim * maxAtoms;
-  const size_t smem = static_cast<size_t>(2) * maxN * sizeof(double);
+  const size_t smem = static_cast<size_t>(1 + kWarps) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large (%d atoms)", maxAtoms);
   static size_t configured[kMaxDevices] = {};
   if (smem > 48 * 1024 && smem > configured[currentDeviceSlot()]) {

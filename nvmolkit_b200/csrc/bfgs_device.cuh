@@ -86,25 +86,43 @@ template <class FF>
 __device__ double energyOf(const typename FF::View& v, const double* x, double* red) {
   return blockSum(FF::template eval<false>(v, x, nullptr, threadIdx.x, kT), red);
 }
+// Gradient at x into acc[0..n): every warp scatters its waves' contributions into its own accumulator
+// acc + warp * accStride (plain shared-memory adds, ff.cuh), then the kWarps accumulators are summed in a fixed order.
+// No atomics anywhere: the result does not depend on scheduling, so two runs give the same bits.
 template <class FF>
-__device__ void gradOf(const typename FF::View& v, const double* x, double* grad, int n) {
-  for (int i = threadIdx.x; i < n; i += kT) grad[i] = 0.0;
+__device__ void gradOf(const typename FF::View& v, const double* x, double* acc, int accStride, int n) {
+  for (int w = 0; w < kWarps; ++w)
+    for (int i = threadIdx.x; i < n; i += kT) acc[w * accStride + i] = 0.0;
   __syncthreads();
-  FF::template eval<true>(v, x, grad, threadIdx.x, kT);
+  FF::template eval<true>(v, x, acc + (threadIdx.x >> 5) * accStride, threadIdx.x, kT);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kT) {
+    double g = acc[i];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) g += acc[w * accStride + i];
+    acc[i] = g;
+  }
   __syncthreads();
 }
 
-// Shared-memory working set of one CTA: six vectors of maxN doubles + the per-CTA inverse-Hessian slab (global/L2).
+// Shared-memory working set of one CTA: 6 + kWarps vectors of maxN doubles + the per-CTA inverse-Hessian slab (global/L2).
+//   pos, dir, dGrad, scratch[3] (the pending update's vectors)      - live across iterations
+//   acc[0..kWarps)  the per-warp gradient accumulators; outside a gradient evaluation acc[0] = grad (the reduced
+//                   gradient), acc[1] = hdg (H * dGrad), acc[2] = newPos (trial point / H * grad): each of the three is
+//                   dead while the gradient is being accumulated, so only kWarps - 3 vectors are extra
 // HT = storage type of the inverse Hessian: double (default; bit-for-bit the RDKit recurrence) or float (half the slab
 // traffic, products and sums still accumulate in fp64) for the embedding stages whose trajectories are chaotic anyway.
 template <class HT = double>
 struct BfgsWorkT {
   double *pos, *grad, *dir, *newPos, *dGrad, *hdg;  // shared memory, maxN each
   HT*     H;                                        // [n*n] global slab of this CTA
-  double* red;                                      // kWarps doubles of shared memory
-  double* scratch;                                  // shared memory, 4 * maxN doubles (scaled vectors of the Hessian passes)
+  double* red;                                      // kRed doubles of shared memory
+  double* scratch;                                  // shared memory, 3 * maxN doubles (scaled vectors of the Hessian passes)
+  double* colBuf;                                   // shared memory, kColBuf doubles: per-warp column sums of one sweep chunk
+  int     maxN;                                     // stride of the accumulators
 };
-constexpr int kBfgsVectors = 10;
+constexpr int kBfgsVectors = 6 + kWarps;
+constexpr int kColBuf      = 2 * kWarps * 64;  // doubles: 2 products x kWarps x 64 fp64 (= 128 fp32) columns of a chunk
 template <class HT>
 __host__ __device__ inline int bfgsLd(int n) {
   constexpr int per = 128 / static_cast<int>(sizeof(HT));
@@ -112,8 +130,9 @@ __host__ __device__ inline int bfgsLd(int n) {
 }  // six working vectors + four scratch vectors of maxN doubles
 using BfgsWork = BfgsWorkT<double>;
 template <class HT = double>
-__device__ __forceinline__ BfgsWorkT<HT> carveWork(double* sm, int maxN, HT* H, double* red) {
-  return {sm, sm + maxN, sm + 2 * maxN, sm + 3 * maxN, sm + 4 * maxN, sm + 5 * maxN, H, red, sm + 6 * maxN};
+__device__ __forceinline__ BfgsWorkT<HT> carveWork(double* sm, int maxN, HT* H, double* red, double* colBuf) {
+  double* acc = sm + 6 * maxN;  // accumulators: grad | hdg | newPos | kWarps - 3 more
+  return {sm, acc, sm + maxN, acc + 2 * maxN, sm + 2 * maxN, acc + maxN, H, red, sm + 3 * maxN, colBuf, maxN};
 }
 
 struct BfgsOutcome {
@@ -149,7 +168,7 @@ static inline void readBfgsClocks(unsigned long long* out) {
 // (profiles/r01_path_b_summary.md), hence the instruction diet.
 template <class HT, bool FRESH, bool PENDING>
 __device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT cfac, HT cfad, HT cfae, const HT* px, const HT* ph,
-                                           const HT* pu, const HT* vD, const HT* vG, double* outD, double* outG) {
+                                           const HT* pu, const HT* vD, const HT* vG, double* outD, double* outG, double* colBuf) {
   constexpr int V  = 16 / static_cast<int>(sizeof(HT));
   constexpr int CW = 32 * V;
   struct alignas(16) Pack {
@@ -237,29 +256,46 @@ __device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT
       s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
       // lane 16 a + 8 b + 4 c holds value index 4 a + 2 b + c : a selects g over d, (2 b + c) the row of the four
+      // (row i belongs to this lane in every chunk and the column sums are added between barriers: a plain add)
       if ((lane & 3) == 0) {
         const int i = i0 + ((lane >> 2) & 3);
-        if (i < rowEnd) atomicAdd(&(b4 ? outG : outD)[i], static_cast<double>(s1));
+        if (i < rowEnd) (b4 ? outG : outD)[i] += static_cast<double>(s1);
       }
     };
     // rows above the chunk's diagonal block: no masks; rows inside it (CW is a multiple of 4): masked
     int i0 = 4 * warp;
     for (; i0 < min(c0, rowEnd); i0 += 4 * kWarps) batch(i0, std::false_type{});
     for (; i0 < rowEnd; i0 += 4 * kWarps) batch(i0, std::true_type{});
+    // column sums of the chunk: every warp parks its partials, then one thread per column adds the kWarps of them in a
+    // fixed order (no atomics: bit-reproducible)
+    HT* colD = reinterpret_cast<HT*>(colBuf);
+    HT* colG = colD + kWarps * CW;
 #pragma unroll
-    for (int t = 0; t < V; ++t)
-      if (cb + t < n) {
-        atomicAdd(&outD[cb + t], static_cast<double>(aD[t]));
-        atomicAdd(&outG[cb + t], static_cast<double>(aG[t]));
+    for (int t = 0; t < V; ++t) {
+      colD[warp * CW + V * lane + t] = aD[t];
+      colG[warp * CW + V * lane + t] = aG[t];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < CW && c0 + c < n; c += kT) {
+      double sD = 0.0, sG = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        sD += static_cast<double>(colD[w * CW + c]);
+        sG += static_cast<double>(colG[w * CW + c]);
       }
+      outD[c0 + c] += sD;
+      outG[c0 + c] += sG;
+    }
+    __syncthreads();
   }
 }
 template <class HT>
 __device__ __forceinline__ void hessianSweep(HT* H, int ld, int n, bool fresh, bool pending, HT cfac, HT cfad, HT cfae, const HT* px,
-                                             const HT* ph, const HT* pu, const HT* vD, const HT* vG, double* outD, double* outG) {
-  if (!fresh && pending) hessianSweepT<HT, false, true>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG);
-  else if (fresh) hessianSweepT<HT, true, true>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG);  // pending by construction
-  else hessianSweepT<HT, false, false>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG);
+                                             const HT* ph, const HT* pu, const HT* vD, const HT* vG, double* outD, double* outG,
+                                             double* colBuf) {
+  if (!fresh && pending) hessianSweepT<HT, false, true>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG, colBuf);
+  else if (fresh) hessianSweepT<HT, true, true>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG, colBuf);  // pending by construction
+  else hessianSweepT<HT, false, false>(H, ld, n, cfac, cfad, cfae, px, ph, pu, vD, vG, outD, outG, colBuf);
 }
 
 template <class FF, class HT = double>
@@ -282,7 +318,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
     double pfac = 0.0, pfad = 0.0, pfae = 0.0;
 
     double fp = energyOf<FF>(view, pos, red);
-    gradOf<FF>(view, pos, grad, n);
+    gradOf<FF>(view, pos, grad, w.maxN, n);
     double gradScale = scaleGrad(n, grad, scaleGrads, red);
     double s2        = 0.0;
     for (int i = tid; i < n; i += kT) {
@@ -362,7 +398,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
       }
       {
         B200_T0();
-        gradOf<FF>(view, pos, grad, n);
+        gradOf<FF>(view, pos, grad, w.maxN, n);
         B200_T1(1);
       }
       gradScale = scaleGrad(n, grad, scaleGrads, red);
@@ -417,7 +453,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         }
         __syncthreads();
         hessianSweep<HT>(H, ld, n, fresh, pending, static_cast<AT>(pfac), static_cast<AT>(pfad), static_cast<AT>(pfae), px, ph, pu,
-                         vD, vG, hdg, hgv);
+                         vD, vG, hdg, hgv, w.colBuf);
         if (pending) fresh = false;
         __syncthreads();
       }

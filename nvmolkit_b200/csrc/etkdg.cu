@@ -190,7 +190,8 @@ __device__ unsigned finalChecks(const EmbedArgs& a, int mol, const double* pos, 
 __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kRed];
-  const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red);
+  __shared__ double                     colBuf[kColBuf];
+  const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red, colBuf);
   double*        ref = sm + kBfgsVectors * a.maxN;  // ETK reference geometry
   const int      tid = threadIdx.x;
   // Work item = one ATTEMPT of one slot. A CTA first works through the slot queue, retrying its own slot while it fails;
@@ -364,6 +365,8 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
   return guarded([&] {
     B200_REQUIRE(dg && etk && checks && params, "null system");
     validate(*params);
+    ff::requireSchedule(*dg);
+    ff::requireSchedule(*etk);
     if (nSlots <= 0) return;
     B200_REQUIRE(d_slot_mol && d_slot_atom_start && d_coords && d_ok, "null pointer");
     cudaStream_t s    = asStream(stream);

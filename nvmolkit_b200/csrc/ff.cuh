@@ -1,11 +1,21 @@
 // Flattened force fields, block-cooperative evaluation for ONE conformer held in shared memory (sm_100a).
 //
 // Every force field exposes   View (this molecule's term ranges),
-//                             energy(view, pos, tid, nT)  -> this thread's partial energy,
-//                             grad(view, pos, grad, tid, nT) -> accumulates into shared-memory grad (fp64 atomics).
-// Threads stride over the CSR term ranges; records are [n][K] int16 indices + [n][P] fp64 parameters, so a warp
+//                             eval<false>(view, pos, nullptr, tid, nT) -> this thread's partial energy,
+//                             eval<true>(view, pos, acc, tid, nT)      -> gradient contributions into `acc`.
+// Energy: threads stride over the CSR term ranges; records are [n][K] int16 indices + [n][P] fp64 parameters, so a warp
 // reads one contiguous span per term type. All arithmetic is fp64 (the reference drops to fp32 inside most terms,
 // src/forcefields/mmff_kernels_device.cuh:37-107,196-237; its own acceptance bars are looser than north_star's 1e-4).
+//
+// Gradient: NO atomics. The host orders every table's terms into WAVES: at most 32 consecutive terms that share no atom
+// (b200mol_schedule_waves: round-robin-tournament rounds (i + j) mod M for the dense pair tables, first-fit colouring
+// for the sparse ones). One warp takes one wave at a time - lane = term - and adds the term's contributions with plain
+// shared-memory read-modify-writes into the warp's PRIVATE accumulator (`acc` + warp * accStride); atoms are distinct
+// within a wave, waves of a warp are ordered by __syncwarp, and the accumulators are summed in a fixed order afterwards
+// (bfgs_device.cuh gradOf). So the gradient - hence a whole minimisation - is bit-reproducible run to run, and the
+// gradient pass no longer waits on shared-memory fp64 CAS loops (1.4 per clock and SM measured, 6-8 per pair term:
+// that alone was ~4 SM-clocks per term against ~2.5 for the term's arithmetic, profiles/r01_path_b_summary.md).
+// The reference scatters with global atomicAdd(double) (mmff_kernels_device.cuh, dist_geom_kernels_device.cuh:66-94).
 //
 // Term math follows RDKit as restated by the reference: MMFF src/forcefields/mmff_kernels_device.cuh:28-661,
 // DG/ETK src/forcefields/dist_geom_kernels_device.cuh:37-830 (including RDKit's quirks: chiral/4th-dim gradient
@@ -34,19 +44,41 @@ template <int DIM>
 __device__ __forceinline__ V3 ld(const double* pos, int a) {
   return {pos[a * DIM], pos[a * DIM + 1], pos[a * DIM + 2]};
 }
+// plain read-modify-write: the caller owns atom `a` for the duration of the wave (see the header comment)
 template <int DIM>
 __device__ __forceinline__ void acc(double* grad, int a, const V3& g) {
-  atomicAdd(&grad[a * DIM], g.x);
-  atomicAdd(&grad[a * DIM + 1], g.y);
-  atomicAdd(&grad[a * DIM + 2], g.z);
+  grad[a * DIM] += g.x;
+  grad[a * DIM + 1] += g.y;
+  grad[a * DIM + 2] += g.z;
 }
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(hi, fmax(lo, v)); }
 __device__ __forceinline__ bool   isZero(double v) { return v < 1.0e-10 && v > -1.0e-10; }
 
 struct Range {
-  int beg, end;
+  int beg, end;    // terms
+  int wbeg, wend;  // waves (gradient schedule)
 };
-__device__ __forceinline__ Range range(const b200mol_term_table& t, int mol) { return {t.starts[mol], t.starts[mol + 1]}; }
+__device__ __forceinline__ Range range(const b200mol_term_table& t, int mol) {
+  return {t.starts[mol], t.starts[mol + 1], t.molWaves ? t.molWaves[mol] : 0, t.molWaves ? t.molWaves[mol + 1] : 0};
+}
+__device__ __forceinline__ void emptyRange(Range& r) {
+  r.end  = r.beg;
+  r.wend = r.wbeg;
+}
+// Energy mode: thread-strided over the terms. Gradient mode: warp-strided over the waves, lane = term of the wave.
+template <bool GRAD, class F>
+__device__ __forceinline__ void forTerms(const b200mol_term_table& T, const Range& r, int tid, int nT, F&& f) {
+  if constexpr (!GRAD) {
+    for (int t = r.beg + tid; t < r.end; t += nT) f(t);
+  } else {
+    const int warp = tid >> 5, lane = tid & 31, nW = nT >> 5;
+    for (int w = r.wbeg + warp; w < r.wend; w += nW) {
+      const int t = T.waves[w] + lane;
+      if (t < T.waves[w + 1]) f(t);
+      __syncwarp();
+    }
+  }
+}
 
 // ============================================================================================ MMFF94
 struct Mmff {
@@ -68,7 +100,7 @@ struct Mmff {
     const System& s = *v.s;
     double        e = 0.0;
     // ---- bond stretch ----
-    for (int t = v.bond.beg + tid; t < v.bond.end; t += nT) {
+    forTerms<GRAD>(s.bond, v.bond, tid, nT, [&](int t) {
       const int    i = s.bond.idx[2 * t], j = s.bond.idx[2 * t + 1];
       const double r0 = s.bond.par[2 * t], kb = s.bond.par[2 * t + 1];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
@@ -82,9 +114,9 @@ struct Mmff {
         acc<3>(grad, i, g);
         acc<3>(grad, j, -g);
       }
-    }
+    });
     // ---- angle bend ----
-    for (int t = v.angle.beg + tid; t < v.angle.end; t += nT) {
+    forTerms<GRAD>(s.angle, v.angle, tid, nT, [&](int t) {
       const int    i = s.angle.idx[3 * t], j = s.angle.idx[3 * t + 1], k = s.angle.idx[3 * t + 2];
       const double theta0 = s.angle.par[3 * t], ka = s.angle.par[3 * t + 1];
       const bool   linear = s.angle.par[3 * t + 2] != 0.0;
@@ -97,7 +129,7 @@ struct Mmff {
                     : 0.5 * 143.9325 * kDeg2Rad * kDeg2Rad * ka * dT * dT * (1.0 + (-0.4 * kDeg2Rad) * dT);
       } else {
         const double sinSq = 1.0 - cosT * cosT;
-        if (isZero(sinSq) || isZero(l1sq) || isZero(l2sq)) continue;
+        if (isZero(sinSq) || isZero(l1sq) || isZero(l2sq)) return;
         const double de = linear ? -143.9325 * ka * sqrt(sinSq)
                                  : 143.9325 * kDeg2Rad * ka * dT * (1.0 + (-0.006981317 * 1.5) * dT);
         const double cf = -de / sqrt(sinSq);
@@ -107,9 +139,9 @@ struct Mmff {
         acc<3>(grad, j, -(a + b));
         acc<3>(grad, k, b);
       }
-    }
+    });
     // ---- stretch-bend ----
-    for (int t = v.strbend.beg + tid; t < v.strbend.end; t += nT) {
+    forTerms<GRAD>(s.strbend, v.strbend, tid, nT, [&](int t) {
       const int     i = s.strbend.idx[3 * t], j = s.strbend.idx[3 * t + 1], k = s.strbend.idx[3 * t + 2];
       const double* q = s.strbend.par + 5 * t;
       const V3      d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
@@ -128,9 +160,9 @@ struct Mmff {
         acc<3>(grad, j, ((n1 * q[3] + n2 * q[4]) * (-dT) + (a + b) * bt) * pre);
         acc<3>(grad, k, (n2 * (dT * q[4]) - b * bt) * pre);
       }
-    }
+    });
     // ---- out-of-plane ----
-    for (int t = v.oop.beg + tid; t < v.oop.end; t += nT) {
+    forTerms<GRAD>(s.oop, v.oop, tid, nT, [&](int t) {
       const int    i = s.oop.idx[4 * t], j = s.oop.idx[4 * t + 1], k = s.oop.idx[4 * t + 2], l = s.oop.idx[4 * t + 3];
       const double koop = s.oop.par[t];
       V3           ji = ld<3>(pos, i) - ld<3>(pos, j), jk = ld<3>(pos, k) - ld<3>(pos, j), jl = ld<3>(pos, l) - ld<3>(pos, j);
@@ -160,9 +192,9 @@ struct Mmff {
         acc<3>(grad, k, g3 * de);
         acc<3>(grad, l, g4 * de);
       }
-    }
+    });
     // ---- torsion ----
-    for (int t = v.torsion.beg + tid; t < v.torsion.end; t += nT) {
+    forTerms<GRAD>(s.torsion, v.torsion, tid, nT, [&](int t) {
       const int16_t* ix = s.torsion.idx + 4 * t;
       const double   V1 = s.torsion.par[3 * t], V2 = s.torsion.par[3 * t + 1], V3c = s.torsion.par[3 * t + 2];
       const V3       d1 = ld<3>(pos, ix[0]) - ld<3>(pos, ix[1]), d2 = ld<3>(pos, ix[2]) - ld<3>(pos, ix[1]),
@@ -194,9 +226,9 @@ struct Mmff {
         acc<3>(grad, ix[3],
                V3{b.y * (-d2.z) - b.z * (-d2.y), b.z * (-d2.x) - b.x * (-d2.z), b.x * (-d2.y) - b.y * (-d2.x)} * sinTerm);
       }
-    }
+    });
     // ---- buffered 14-7 van der Waals ----
-    for (int t = v.vdw.beg + tid; t < v.vdw.end; t += nT) {
+    forTerms<GRAD>(s.vdw, v.vdw, tid, nT, [&](int t) {
       const int    i = s.vdw.idx[2 * t], j = s.vdw.idx[2 * t + 1];
       const double R = s.vdw.par[2 * t], eps = s.vdw.par[2 * t + 1];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
@@ -213,9 +245,9 @@ struct Mmff {
         acc<3>(grad, i, g);
         acc<3>(grad, j, -g);
       }
-    }
+    });
     // ---- buffered Coulomb ----
-    for (int t = v.ele.beg + tid; t < v.ele.end; t += nT) {
+    forTerms<GRAD>(s.ele, v.ele, tid, nT, [&](int t) {
       const int    i = s.ele.idx[2 * t], j = s.ele.idx[2 * t + 1];
       const double ct = s.ele.par[3 * t];
       const bool   sq = s.ele.par[3 * t + 1] == 2.0, is14 = s.ele.par[3 * t + 2] != 0.0;
@@ -232,7 +264,7 @@ struct Mmff {
         acc<3>(grad, i, g);
         acc<3>(grad, j, -g);
       }
-    }
+    });
     return e;
   }
 };
@@ -258,7 +290,7 @@ struct Dg {
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
     double        e = 0.0;
-    for (int t = v.dist.beg + tid; t < v.dist.end; t += nT) {
+    forTerms<GRAD>(s.dist, v.dist, tid, nT, [&](int t) {
       const int    i = s.dist.idx[2 * t], j = s.dist.idx[2 * t + 1];
       const double lb2 = s.dist.par[3 * t], ub2 = s.dist.par[3 * t + 1], w = s.dist.par[3 * t + 2];
       double       dd[DIM], d2 = 0.0;
@@ -275,8 +307,8 @@ struct Dg {
           const double pre = w * 4.0 * val / ub2;
 #pragma unroll
           for (int c = 0; c < DIM; ++c) {
-            atomicAdd(&grad[i * DIM + c], pre * dd[c]);
-            atomicAdd(&grad[j * DIM + c], -pre * dd[c]);
+            grad[i * DIM + c] += pre * dd[c];
+            grad[j * DIM + c] -= pre * dd[c];
           }
         }
       } else if (d2 < lb2) {
@@ -288,13 +320,13 @@ struct Dg {
           const double pre = w * 8.0 * lb2 * (1.0 - 2.0 * lb2 / l2d2) / (l2d2 * l2d2);
 #pragma unroll
           for (int c = 0; c < DIM; ++c) {
-            atomicAdd(&grad[i * DIM + c], pre * dd[c]);
-            atomicAdd(&grad[j * DIM + c], -pre * dd[c]);
+            grad[i * DIM + c] += pre * dd[c];
+            grad[j * DIM + c] -= pre * dd[c];
           }
         }
       }
-    }
-    for (int t = v.chiral.beg + tid; t < v.chiral.end; t += nT) {
+    });
+    forTerms<GRAD>(s.chiral, v.chiral, tid, nT, [&](int t) {
       const int16_t* ix = s.chiral.idx + 4 * t;
       const double   ub = s.chiral.par[2 * t], lb = s.chiral.par[2 * t + 1];
       const V3       p1 = ld<DIM>(pos, ix[0]), p2 = ld<DIM>(pos, ix[1]), p3 = ld<DIM>(pos, ix[2]), p4 = ld<DIM>(pos, ix[3]);
@@ -303,7 +335,7 @@ struct Dg {
       double         diff;
       if (vol < lb) diff = vol - lb;
       else if (vol > ub) diff = vol - ub;
-      else continue;
+      else return;
       if (!GRAD) {
         e += v.cw * diff * diff;
       } else {
@@ -316,14 +348,14 @@ struct Dg {
                     p1.x * (p2.z - p3.z) + p2.x * (p3.z - p1.z) + p3.x * (p1.z - p2.z),
                     p1.y * (p2.x - p3.x) + p2.y * (p3.x - p1.x) + p3.y * (p1.x - p2.x)} * pre);
       }
-    }
+    });
     if constexpr (DIM == 4) {
-      for (int t = v.fourth.beg + tid; t < v.fourth.end; t += nT) {
+      forTerms<GRAD>(s.fourth, v.fourth, tid, nT, [&](int t) {
         const int    a  = s.fourth.idx[t];
         const double w4 = pos[a * 4 + 3];
         if (!GRAD) e += v.fw * w4 * w4;
-        else atomicAdd(&grad[a * 4 + 3], v.fw * w4);  // RDKit: no factor 2
-      }
+        else grad[a * 4 + 3] += v.fw * w4;  // RDKit: no factor 2
+      });
     }
     return e;
   }
@@ -345,7 +377,7 @@ struct Etk {
   };
   __device__ static View view(const System& s, int mol, const Params& p) {
     Range imp = range(s.improper, mol);
-    if (p.plain) imp.end = imp.beg;
+    if (p.plain) emptyRange(imp);
     return {&s, range(s.torsion, mol), imp, range(s.dist12, mol), range(s.dist13, mol), range(s.angle13, mol),
             range(s.longrange, mol), nullptr};
   }
@@ -357,7 +389,7 @@ struct Etk {
   __device__ static double distTerms(const b200mol_term_table& T, Range r, const double* pos, double* grad, int tid, int nT,
                                      const double* refPos) {
     double e = 0.0;
-    for (int t = r.beg + tid; t < r.end; t += nT) {
+    forTerms<GRAD>(T, r, tid, nT, [&](int t) {
       const int i = T.idx[2 * t], j = T.idx[2 * t + 1];
       double    mn = T.par[P * t], mx = T.par[P * t + 1];
       const double fk = T.par[P * t + 2];
@@ -372,7 +404,7 @@ struct Etk {
       double       ref;
       if (d2 < mn * mn) ref = mn;
       else if (d2 > mx * mx) ref = mx;
-      else continue;
+      else return;
       const double dist = sqrt(d2);
       if (!GRAD) {
         e += 0.5 * fk * (dist - ref) * (dist - ref);
@@ -381,7 +413,7 @@ struct Etk {
         acc<4>(grad, i, g);
         acc<4>(grad, j, -g);
       }
-    }
+    });
     return e;
   }
 
@@ -389,7 +421,7 @@ struct Etk {
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
     double        e = 0.0;
-    for (int t = v.torsion.beg + tid; t < v.torsion.end; t += nT) {
+    forTerms<GRAD>(s.torsion, v.torsion, tid, nT, [&](int t) {
       const int16_t* ix = s.torsion.idx + 4 * t;
       const double*  fc = s.torsion.par + 12 * t;
       const double*  sg = fc + 6;
@@ -406,7 +438,7 @@ struct Etk {
              fc[4] * (1.0 + sg[4] * (16.0 * c5 - 20.0 * c3 + 5.0 * c)) +
              fc[5] * (1.0 + sg[5] * (32.0 * c6 - 48.0 * c4 + 18.0 * c2 - 1.0));
       } else {
-        if (isZero(d02) || isZero(d12)) continue;
+        if (isZero(d02) || isZero(d12)) return;
         const double i0 = 1.0 / sqrt(d02), i1 = 1.0 / sqrt(d12);
         t0 = t0 * i0;
         t1 = t1 * i1;
@@ -430,8 +462,8 @@ struct Etk {
                   a.x * (-r1.z) + a.z * r1.x + b.x * (r3.z - r4.z) + b.z * (r4.x - r3.x),
                   a.x * r1.y + a.y * (-r1.x) + b.x * (r4.y - r3.y) + b.y * (r3.x - r4.x)} * sinTerm);
       }
-    }
-    for (int t = v.improper.beg + tid; t < v.improper.end; t += nT) {
+    });
+    forTerms<GRAD>(s.improper, v.improper, tid, nT, [&](int t) {
       const int16_t* ix = s.improper.idx + 4 * t;
       const double   C0 = s.improper.par[4 * t], C1 = s.improper.par[4 * t + 1], C2 = s.improper.par[4 * t + 2],
                    fk = s.improper.par[4 * t + 3];
@@ -448,7 +480,7 @@ struct Etk {
         const double sSq = 1.0 - cosY * cosY, sinY = sSq > 0.0 ? sqrt(sSq) : 0.0;
         e += fk * (C0 + C1 * sinY + C2 * (2.0 * sinY * sinY - 1.0));
       } else {
-        if (isZero(l2i) || isZero(l2k) || isZero(l2l)) continue;
+        if (isZero(l2i) || isZero(l2k) || isZero(l2l)) return;
         const double ii = 1.0 / sqrt(l2i), ik = 1.0 / sqrt(l2k), il = 1.0 / sqrt(l2l);
         const V3     a = ji * ii, b = jk * ik, c = jl * il;
         V3           n = cross(-a, b);
@@ -466,17 +498,17 @@ struct Etk {
         acc<4>(grad, ix[2], g3 * dE);
         acc<4>(grad, ix[3], g4 * dE);
       }
-    }
+    });
     e += distTerms<GRAD, 4>(s.dist12, v.d12, pos, grad, tid, nT, v.refPos);
     e += distTerms<GRAD, 4>(s.dist13, v.d13, pos, grad, tid, nT, v.refPos);
     e += distTerms<GRAD, 3>(s.longrange, v.lr, pos, grad, tid, nT, nullptr);
-    for (int t = v.a13.beg + tid; t < v.a13.end; t += nT) {
+    forTerms<GRAD>(s.angle13, v.a13, tid, nT, [&](int t) {
       const int16_t* ix = s.angle13.idx + 3 * t;
       const double   mn = s.angle13.par[2 * t], mx = s.angle13.par[2 * t + 1];
       const V3       r1 = ld<4>(pos, ix[0]) - ld<4>(pos, ix[1]), r2 = ld<4>(pos, ix[2]) - ld<4>(pos, ix[1]);
       const double   l1 = dot(r1, r1), l2 = dot(r2, r2);
       if (!GRAD) {
-        if (isZero(l1 * l2)) continue;
+        if (isZero(l1 * l2)) return;
         const double ang = kRad2Deg * acos(clampd(dot(r1, r2) / sqrt(l1 * l2), -1.0, 1.0));
         const double at  = ang < mn ? ang - mn : (ang > mx ? ang - mx : 0.0);
         e += at * at;
@@ -492,7 +524,7 @@ struct Etk {
         acc<4>(grad, ix[1], -(a + b));
         acc<4>(grad, ix[2], b);
       }
-    }
+    });
     return e;
   }
 };
@@ -515,7 +547,7 @@ struct Uff {
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
     double        e = 0.0;
-    for (int t = v.bond.beg + tid; t < v.bond.end; t += nT) {
+    forTerms<GRAD>(s.bond, v.bond, tid, nT, [&](int t) {
       const int    i = s.bond.idx[2 * t], j = s.bond.idx[2 * t + 1];
       const double r0 = s.bond.par[2 * t], k = s.bond.par[2 * t + 1];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
@@ -527,14 +559,14 @@ struct Uff {
         acc<3>(grad, i, g);
         acc<3>(grad, j, -g);
       }
-    }
-    for (int t = v.angle.beg + tid; t < v.angle.end; t += nT) {
+    });
+    forTerms<GRAD>(s.angle, v.angle, tid, nT, [&](int t) {
       const int     i = s.angle.idx[3 * t], j = s.angle.idx[3 * t + 1], k = s.angle.idx[3 * t + 2];
       const double* q = s.angle.par + 6 * t;  // theta0, k, order, C0, C1, C2
       const int     order = static_cast<int>(q[2]);
       const V3      d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
       const double  l1sq = dot(d1, d1), l2sq = dot(d2, d2);
-      if (l1sq <= 0.0 || l2sq <= 0.0) continue;
+      if (l1sq <= 0.0 || l2sq <= 0.0) return;
       const double l1 = sqrt(l1sq), l2 = sqrt(l2sq);
       const double c  = clampd(dot(d1, d2) / (l1 * l2), -1.0, 1.0);
       const double sSq = 1.0 - c * c;
@@ -556,7 +588,7 @@ struct Uff {
         if (corr) en += exp(-20.0 * (acos(c) - q[0] + 0.25));
         e += en;
       } else {
-        if (isZero(sSq)) continue;
+        if (isZero(sSq)) return;
         const double sn = fmax(sqrt(sSq), 1.0e-8), s2t = 2.0 * sn * c;
         double       dE;
         if (order == 0) {
@@ -577,8 +609,8 @@ struct Uff {
         acc<3>(grad, j, -(a + b));
         acc<3>(grad, k, b);
       }
-    }
-    for (int t = v.torsion.beg + tid; t < v.torsion.end; t += nT) {
+    });
+    forTerms<GRAD>(s.torsion, v.torsion, tid, nT, [&](int t) {
       const int16_t* ix = s.torsion.idx + 4 * t;
       const double   fk = s.torsion.par[3 * t], cosTerm = s.torsion.par[3 * t + 2];
       const int      order = static_cast<int>(s.torsion.par[3 * t + 1]);
@@ -593,10 +625,10 @@ struct Uff {
         if (order == 2) cn = 1.0 - 2.0 * sSq;
         else if (order == 3) cn = c * (c * c - 3.0 * sSq);
         else if (order == 6) cn = 1.0 + sSq * (-32.0 * sSq * sSq + 48.0 * sSq - 18.0);
-        else continue;
+        else return;
         e += fk / 2.0 * (1.0 - cosTerm * cn);
       } else {
-        if (isZero(d0) || isZero(d1)) continue;
+        if (isZero(d0) || isZero(d1)) return;
         t0 = t0 * (1.0 / d0);
         t1 = t1 * (1.0 / d1);
         const double c = clampd(dot(t0, t1), -1.0, 1.0), sSq = 1.0 - c * c, sn = sSq > 0.0 ? sqrt(sSq) : 0.0;
@@ -604,7 +636,7 @@ struct Uff {
         if (order == 2) r = 2.0 * sn * c;
         else if (order == 3) r = sn * (3.0 - 4.0 * sSq);
         else if (order == 6) r = c * sn * (32.0 * sSq * (sSq - 1.0) + 6.0);
-        else continue;
+        else return;
         const double dE = r * fk / 2.0 * cosTerm * -1.0 * static_cast<double>(order);
         const double sinTerm = dE * (isZero(sn) ? (1.0 / fmax(fabs(c), 1.0e-8)) : (1.0 / sn));
         const V3     a = (t1 - t0 * c) * (1.0 / d0), b = (t0 - t1 * c) * (1.0 / d1);
@@ -619,8 +651,8 @@ struct Uff {
                   a.x * r0.y + a.y * (-r0.x) + b.x * (r3.y - r2.y) + b.y * (r2.x - r3.x)} * sinTerm);
         acc<3>(grad, ix[3], V3{b.y * r2.z - b.z * r2.y, b.z * r2.x - b.x * r2.z, b.x * r2.y - b.y * r2.x} * sinTerm);
       }
-    }
-    for (int t = v.inversion.beg + tid; t < v.inversion.end; t += nT) {
+    });
+    forTerms<GRAD>(s.inversion, v.inversion, tid, nT, [&](int t) {
       const int16_t* ix = s.inversion.idx + 4 * t;
       const double   fk = s.inversion.par[4 * t], C0 = s.inversion.par[4 * t + 1], C1 = s.inversion.par[4 * t + 2],
                    C2 = s.inversion.par[4 * t + 3];
@@ -638,11 +670,11 @@ struct Uff {
         e += fk * (C0 + C1 * sinY + C2 * (2.0 * sinY * sinY - 1.0));
       } else {
         const double dI = sqrt(l2i), dK = sqrt(l2k), dL = sqrt(l2l);
-        if (isZero(dI) || isZero(dK) || isZero(dL)) continue;
+        if (isZero(dI) || isZero(dK) || isZero(dL)) return;
         const V3 a = ji * (1.0 / dI), b = jk * (1.0 / dK), c = jl * (1.0 / dL);
         V3       n = cross(-a, b);
         const double nn = sqrt(dot(n, n));
-        if (nn <= 0.0) continue;
+        if (nn <= 0.0) return;
         n = n * (1.0 / nn);
         const double cY = clampd(dot(n, c), -1.0, 1.0), sY = fmax(sqrt(1.0 - cY * cY), 1.0e-8);
         const double cT = clampd(dot(a, b), -1.0, 1.0), sTsq = 1.0 - cT * cT, sT = fmax(sqrt(sTsq), 1.0e-8);
@@ -657,15 +689,15 @@ struct Uff {
         acc<3>(grad, ix[2], g3 * dE);
         acc<3>(grad, ix[3], g4 * dE);
       }
-    }
-    for (int t = v.vdw.beg + tid; t < v.vdw.end; t += nT) {
+    });
+    forTerms<GRAD>(s.vdw, v.vdw, tid, nT, [&](int t) {
       const int    i = s.vdw.idx[2 * t], j = s.vdw.idx[2 * t + 1];
       const double x = s.vdw.par[3 * t], eps = s.vdw.par[3 * t + 1], thr = s.vdw.par[3 * t + 2];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
       const double dist = sqrt(dot(d, d));
-      if (dist > thr) continue;
+      if (dist > thr) return;
       if (!GRAD) {
-        if (dist <= 0.0) continue;
+        if (dist <= 0.0) return;
         const double r = x / dist, r2 = r * r, r6 = r2 * r2 * r2;
         e += eps * (r6 * r6 - 2.0 * r6);
       } else {
@@ -679,7 +711,7 @@ struct Uff {
         acc<3>(grad, i, g);
         acc<3>(grad, j, -g);
       }
-    }
+    });
     return e;
   }
 };
@@ -710,15 +742,36 @@ struct Poly {
       const double d = x[i] - v.c[i];
       if (v.power == 2) {
         if (!GRAD) e += v.w[i] * d * d;
-        else atomicAdd(&grad[i], 2.0 * v.w[i] * d);
+        else grad[i] += 2.0 * v.w[i] * d;
       } else {
         if (!GRAD) e += v.w[i] * d * d * d * d;
-        else atomicAdd(&grad[i], 4.0 * v.w[i] * d * d * d);
+        else grad[i] += 4.0 * v.w[i] * d * d * d;
       }
     }
     return e;
   }
 };
+
+// Host-side check: every table with terms must carry its wave schedule before a gradient is evaluated.
+inline void needWaves(const b200mol_term_table& t, const char* what) {
+  B200_REQUIRE(!t.idx || (t.molWaves && t.waves), "term table '%s' has no gradient schedule (see b200mol_schedule_waves)", what);
+}
+inline void requireSchedule(const b200mol_mmff_system& s) {
+  needWaves(s.bond, "bond"), needWaves(s.angle, "angle"), needWaves(s.strbend, "strbend"), needWaves(s.oop, "oop");
+  needWaves(s.torsion, "torsion"), needWaves(s.vdw, "vdw"), needWaves(s.ele, "ele");
+}
+inline void requireSchedule(const b200mol_uff_system& s) {
+  needWaves(s.bond, "bond"), needWaves(s.angle, "angle"), needWaves(s.torsion, "torsion");
+  needWaves(s.inversion, "inversion"), needWaves(s.vdw, "vdw");
+}
+inline void requireSchedule(const b200mol_dg_system& s) {
+  needWaves(s.dist, "dist"), needWaves(s.chiral, "chiral"), needWaves(s.fourth, "fourth");
+}
+inline void requireSchedule(const b200mol_etk_system& s) {
+  needWaves(s.torsion, "torsion"), needWaves(s.improper, "improper"), needWaves(s.dist12, "dist12");
+  needWaves(s.dist13, "dist13"), needWaves(s.angle13, "angle13"), needWaves(s.longrange, "longrange");
+}
+inline void requireSchedule(const Poly::System&) {}
 
 }  // namespace ff
 }  // namespace b200

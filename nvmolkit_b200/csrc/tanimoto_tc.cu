@@ -200,65 +200,95 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Work units in launch order: groups of kGroupTC tile-rows sweep the tile-columns (L2 reuse of the row operand). A CTA
-// walks its units t, t + step, ... keeping (group, index in group) incrementally: no 64-bit division per tile.
+// Work units. A unit = one tile (CL = 0) or two vertically adjacent tiles of one tile column (CTA pairs: unit row r
+// holds tile rows 2 r and 2 r + 1, the two CTAs share the column operand). Unit rows come in groups of G (= kGroupTC
+// tile rows), a group sweeps the tile columns row-fastest (L2 reuse of the row operand). Only units that can hold a pair
+// are enumerated: a rank walks the groups it OWNS, and a group starts at the first tile column that reaches past the
+// diagonal for its top tile row (closed form), so that neither the other ranks' groups nor the lower triangle cost
+// loop iterations (round 1 walked all of them: 215 ns per skipped unit, the 1 -> 8 GPU limiter).
+// Ownership is serpentine over cycles of `groupStride` groups (even cycles: group = cycle * stride + offset, odd
+// cycles mirrored), which balances the triangle's shrinking rows across ranks to < 0.1 %.
+// A CTA walks units first, first + step, ... of the concatenated owned groups; (cycle, index in group) are kept
+// incrementally, the only divisions are by compile-time constants and happen once per group.
+template <int TN, bool PAIR>
 struct UnitWalk {
-  uint64_t t, total;
-  uint32_t step, group, inGroup, perGroup;
-  __device__ UnitWalk(uint64_t first, uint64_t stepBy, uint64_t totalUnits, uint32_t unitsPerGroup)
-      : t(first), total(totalUnits), step(static_cast<uint32_t>(stepBy)), group(static_cast<uint32_t>(first / unitsPerGroup)),
-        inGroup(static_cast<uint32_t>(first % unitsPerGroup)), perGroup(unitsPerGroup) {}
-  __device__ bool more() const { return t < total; }
-  __device__ void next() {
-    t += step;
-    inGroup += step;
-    while (inGroup >= perGroup) {
-      inGroup -= perGroup;
-      ++group;
+  static constexpr uint32_t G = PAIR ? kGroupTC / 2 : kGroupTC;
+  uint32_t cycle, inGroup, units, gRows, tn0, group, step;
+  bool     done;
+  __device__ UnitWalk(const TcParams& p, uint32_t first, uint32_t stepBy) : cycle(0), inGroup(first), units(0), gRows(G), tn0(0), group(0), step(stepBy), done(false) {
+    settle(p);
+  }
+  __device__ void settle(const TcParams& p) {  // make (cycle, inGroup) point at an existing unit, or set done
+    const uint32_t unitRows = PAIR ? (p.tilesM + 1) / 2 : p.tilesM;
+    for (;;) {
+      if (cycle * p.groupStride * G >= unitRows) {
+        done = true;
+        return;
+      }
+      group = cycle * p.groupStride + ((cycle & 1u) ? p.groupStride - 1 - p.groupOffset : p.groupOffset);
+      units = 0;
+      if (group * G < unitRows) {
+        gRows = min(G, unitRows - group * G);
+        // first tile column holding a pair with row < col for the group's top tile row tm0 = group * kGroupTC:
+        // (tn + 1) * TN - 1 > tm0 * kTM
+        tn0   = p.symmetric ? (group * static_cast<uint32_t>(kGroupTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
+        if (tn0 < p.tilesN) units = gRows * (p.tilesN - tn0);
+      }
+      if (inGroup < units) return;
+      inGroup -= units;
+      ++cycle;
     }
+  }
+  __device__ void next(const TcParams& p) {
+    inGroup += step;
+    if (inGroup >= units) {
+      inGroup -= units;
+      ++cycle;
+      settle(p);
+    }
+  }
+  // tile of this unit for CTA `rank` of the pair (0 when unpaired); false = nothing to do (below the diagonal)
+  __device__ bool coords(const TcParams& p, uint32_t rank, uint32_t& tm, uint32_t& tn) const {
+    uint32_t row, col;
+    if (gRows == G) {
+      row = inGroup % G;  // G is a power of two
+      col = inGroup / G;
+    } else {  // the last, partial group
+      row = inGroup % gRows;
+      col = inGroup / gRows;
+    }
+    tn                = tn0 + col;
+    const uint32_t tr = group * G + row;  // unit row
+    const uint32_t top = PAIR ? 2 * tr : tr;
+    // the upper tile decides for both CTAs of a pair (if it has no pair with row < col, neither has the lower one); a
+    // lower tile past the end or below the diagonal still runs - its loads are zero-filled / its predicates reject all
+    if (p.symmetric && (tn * TN + TN - 1) <= top * kTM) return false;
+    tm = top + (PAIR ? rank : 0u);
+    return true;
   }
 };
 
-// (group, index in group) -> (tm, tn), one tile per unit
-template <int TN>
-__device__ __forceinline__ bool tileCoords(const TcParams& p, uint32_t group, uint32_t inGroup, uint32_t& tm, uint32_t& tn) {
-  if (group * kGroupTC >= p.tilesM) return false;
-  if (group % p.groupStride != p.groupOffset) return false;
-  const uint32_t gRows = min(static_cast<uint32_t>(kGroupTC), p.tilesM - group * kGroupTC);
-  tm                   = group * kGroupTC + inGroup % gRows;
-  tn                   = inGroup / gRows;
-  if (tn >= p.tilesN) return false;
-  // symmetric: skip tiles whose every column index is <= every row index (no pair with row < col)
-  if (p.symmetric && (tn * TN + TN - 1) <= tm * kTM) return false;
-  return true;
-}
-
-// Cluster of two CTAs: one unit = two vertically adjacent tiles (tile rows 2 tp, 2 tp + 1) of the same tile column; the
-// two CTAs share the column operand. Same row-group partition as tileCoords.
-template <int TN>
-__device__ __forceinline__ bool tileCoordsPair(const TcParams& p, uint32_t group, uint32_t inGroup, uint32_t rank, uint32_t& tm,
-                                               uint32_t& tn) {
-  constexpr uint32_t kPairGroup = kGroupTC / 2;
-  const uint32_t     pairRows   = (p.tilesM + 1) / 2;
-  if (group * kPairGroup >= pairRows) return false;
-  if (group % p.groupStride != p.groupOffset) return false;
-  const uint32_t gRows = min(kPairGroup, pairRows - group * kPairGroup);
-  const uint32_t tp    = group * kPairGroup + inGroup % gRows;
-  tn                   = inGroup / gRows;
-  if (tn >= p.tilesN) return false;
-  // the upper tile decides for both (if it has no pair with row < col, neither has the lower one); a lower tile that is
-  // past the end or below the diagonal still runs - its loads are zero-filled / its predicates reject everything
-  if (p.symmetric && (tn * TN + TN - 1) <= (2 * tp) * kTM) return false;
-  tm = 2 * tp + rank;
-  return true;
+// host twin of the walk's unit count (sizes the grid)
+template <int TN, bool PAIR>
+uint64_t countUnits(const TcParams& p) {
+  constexpr uint32_t G = PAIR ? kGroupTC / 2 : kGroupTC;
+  const uint32_t     unitRows = PAIR ? (p.tilesM + 1) / 2 : p.tilesM;
+  uint64_t           total = 0;
+  for (uint32_t cycle = 0; cycle * p.groupStride * G < unitRows; ++cycle) {
+    const uint32_t group = cycle * p.groupStride + ((cycle & 1u) ? p.groupStride - 1 - p.groupOffset : p.groupOffset);
+    if (group * G >= unitRows) continue;
+    const uint32_t gRows = std::min(G, unitRows - group * G);
+    const uint32_t tn0   = p.symmetric ? (group * static_cast<uint32_t>(kGroupTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
+    if (tn0 < p.tilesN) total += static_cast<uint64_t>(gRows) * (p.tilesN - tn0);
+  }
+  return total;
 }
 
 // CL: 0 = one CTA per tile; 1 = CTA pair, column operand multicast; 2 = CTA pair with cta_group::2 MMAs (each CTA stages
 // half of the column operand, the leader issues M = 256 instructions for both)
 template <int MODE, bool FP4, int CL>
 __global__ void __launch_bounds__(threadsTC(MODE), 1)
-  simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
-                  uint64_t totalTiles) {
+  simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smemRaw[];
   constexpr int kEpiWarps = epiWarps(MODE), kThreadsTC = threadsTC(MODE), kParts = kEpiWarps / 4;
   constexpr int TN      = FP4 ? kTNFp4 : kTN;  // tile columns; the accumulator stages sit TN TMEM columns apart
@@ -266,8 +296,8 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   static_assert(!FP4 || MODE == kTcCount, "the fp4 tile serves the count mode");
   static_assert(!CL || FP4, "the two-CTA cluster is wired for the fp4 count tile");
   const uint32_t rank      = CL ? clusterCtaRank() : 0u;
-  const uint64_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
-  const uint32_t unitsPerGroup = (CL ? kGroupTC / 2 : kGroupTC) * p.tilesN;
+  const uint32_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
+  using Walk               = UnitWalk<TN, CL != 0>;
   constexpr bool P2          = CL == 2;
   constexpr int  kBStage     = P2 ? kBBytes / 2 : kBBytes;  // bytes of the column operand one CTA stages per K chunk
   constexpr int  kStageBytes = kABytes + kBStage;
@@ -335,9 +365,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     if (lane == 0) {
       int      stage = 0;
       uint32_t phase = 0;
-      for (UnitWalk w(firstUnit, unitStep, totalTiles, unitsPerGroup); w.more(); w.next()) {
+      for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
         uint32_t tm, tn;
-        if (!(CL ? tileCoordsPair<TN>(p, w.group, w.inGroup, rank, tm, tn) : tileCoords<TN>(p, w.group, w.inGroup, tm, tn))) continue;
+        if (!w.coords(p, rank, tm, tn)) continue;
         for (int kc = 0; kc < p.kChunks; ++kc) {
           mbarWait(&emptyBar[stage], phase ^ 1);
           uint8_t* dst = smemGen + stage * kStageBytes;
@@ -372,9 +402,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     if (lane == 0 && !(P2 && rank != 0)) {  // (pair MMA: the leader issues for both CTAs)
       int      stage = 0;
       uint32_t phase = 0, local = 0;
-      for (UnitWalk w(firstUnit, unitStep, totalTiles, unitsPerGroup); w.more(); w.next()) {
+      for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
         uint32_t tm, tn;
-        if (!(CL ? tileCoordsPair<TN>(p, w.group, w.inGroup, rank, tm, tn) : tileCoords<TN>(p, w.group, w.inGroup, tm, tn))) continue;
+        if (!w.coords(p, rank, tm, tn)) continue;
         const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
         mbarWait(&tmemEmpty[as], accPhase ^ 1);
         tcFenceAfter();
@@ -412,9 +442,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     const int      et      = ew * 32 + lane;       // thread index among the epilogue warps
     uint32_t       local   = 0;
     uint32_t       tnOf[2] = {0, 0};  // tile column each accumulator-side buffer last served
-    for (UnitWalk w(firstUnit, unitStep, totalTiles, unitsPerGroup); w.more(); w.next()) {
+    for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
       uint32_t tm, tn;
-      if (!(CL ? tileCoordsPair<TN>(p, w.group, w.inGroup, rank, tm, tn) : tileCoords<TN>(p, w.group, w.inGroup, tm, tn))) continue;
+      if (!w.coords(p, rank, tm, tn)) continue;
       const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
       // stage this tile's column popcounts
       int minPb = 0x3fffffff;  // smallest |B| among this tile's valid columns (pre-filter of the threshold test)
@@ -683,8 +713,9 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
     configured[currentDeviceSlot()] = true;
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
-  const uint64_t groupsM = (p.tilesM + kGroupTC - 1) / kGroupTC;
-  const uint64_t total   = groupsM * (cluster ? kGroupTC / 2 : kGroupTC) * p.tilesN;  // tiles, or vertical tile pairs
+  // units this call owns: tiles, or vertical tile pairs (same enumeration as the kernel's UnitWalk)
+  const uint64_t total = cluster ? countUnits<kTNFp4, true>(p) : (fp4 ? countUnits<kTNFp4, false>(p) : countUnits<kTN, false>(p));
+  if (total == 0) return true;  // nothing owned by this rank (more ranks than row groups)
   int            blocks  = smCount();
   if (static_cast<uint64_t>(blocks) > total) blocks = static_cast<int>(total);
   if (mode == kCountTanimoto) {
@@ -709,16 +740,16 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
       uint64_t pairs = maxClusters;  // persistent: one resident cluster per schedulable SM pair
       if (pairs > total) pairs = total;
       cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-      if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, p, total));
-      else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, p, total));
-    } else if (fp4) simTensorKernel<kTcCount, true, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
-    else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p, total);
+      if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, p));
+      else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, p));
+    } else if (fp4) simTensorKernel<kTcCount, true, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p);
+    else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcTanimoto, false, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcTanimoto, false, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, p);
   } else {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, p, total);
+    simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, p);
   }
   B200_LAUNCHED();
   return true;

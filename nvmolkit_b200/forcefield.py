@@ -28,7 +28,8 @@ CHECK_LAYOUT = (("tetrahedral", 5, 1), ("chiral", 5, 2), ("chiralDist", 2, 2), (
 
 
 class TermTableC(C.Structure):
-    _fields_ = [("starts", C.c_void_p), ("idx", C.c_void_p), ("par", C.c_void_p)]
+    _fields_ = [("starts", C.c_void_p), ("idx", C.c_void_p), ("par", C.c_void_p), ("molWaves", C.c_void_p),
+                ("waves", C.c_void_p)]
 
 
 def _system_struct(kind: str):
@@ -39,15 +40,24 @@ def _system_struct(kind: str):
 SYSTEM_STRUCT = {k: _system_struct(k) for k in LAYOUT}
 
 
-def _diagonal_order(starts: np.ndarray, idx: np.ndarray, par: np.ndarray):
-    """Order each molecule's pair terms by (|j - i|, min(i, j)): consecutive terms (one warp's worth) then touch
-    distinct atoms, so the shared-memory gradient atomics of a warp do not collide. A pair list sorted by (i, j) makes 32
-    lanes add into the SAME atom and serialises the fp64 CAS loops (profiles/r01_path_b_summary.md). Any order is
-    correct; this one is fast. Energies change only by summation order."""
-    mol = np.repeat(np.arange(len(starts) - 1), np.diff(starts))
-    a, b = idx[:, 0].astype(np.int32), idx[:, 1].astype(np.int32)
-    order = np.lexsort((np.minimum(a, b), np.abs(b - a), mol))
-    return np.ascontiguousarray(idx[order]), np.ascontiguousarray(par[order])
+def schedule_waves(starts: np.ndarray, idx: np.ndarray, par: np.ndarray):
+    """Order every molecule's terms into atom-disjoint waves of <= 32 (the gradient schedule of the kernels: one warp
+    per wave, lane = term, plain shared-memory adds instead of atomics; include/b200mol.h b200mol_schedule_waves).
+    Returns (idx, par, mol_waves [nMols+1], waves [nWaves+1]). Any order of the terms is correct; energies change
+    only by summation order."""
+    from nvmolkit_b200 import _lib
+
+    starts = np.ascontiguousarray(starts, dtype=np.int32)
+    idx = np.ascontiguousarray(idx, dtype=np.int16)
+    n, k = idx.shape
+    perm = np.empty(n, dtype=np.int32)
+    mol_waves = np.empty(len(starts), dtype=np.int32)
+    waves = np.empty(n + 1, dtype=np.int32)
+    n_waves = C.c_int64(0)
+    _lib.call("b200mol_schedule_waves", len(starts) - 1, starts.ctypes.data, idx.ctypes.data if n else None, int(k),
+              perm.ctypes.data, mol_waves.ctypes.data, waves.ctypes.data, C.byref(n_waves))
+    return (np.ascontiguousarray(idx[perm]), np.ascontiguousarray(par[perm]), mol_waves,
+            np.ascontiguousarray(waves[: n_waves.value + 1]))
 
 
 @dataclass
@@ -56,6 +66,7 @@ class FlatSystem:
     atom_counts: np.ndarray  # int32 [nMols]
     tables: Dict[str, Tuple[np.ndarray, np.ndarray, np.ndarray]]  # name -> (starts, idx [n,K], par [n,P])
     _device: dict = field(default_factory=dict, repr=False)
+    waves: Dict[str, Tuple[np.ndarray, np.ndarray]] = field(default_factory=dict, repr=False)  # name -> (molWaves, waves)
 
     def __post_init__(self):
         self.atom_counts = np.ascontiguousarray(self.atom_counts, dtype=np.int32)
@@ -68,8 +79,8 @@ class FlatSystem:
             par = np.ascontiguousarray(par, dtype=np.float64).reshape(-1, p) if p else np.zeros((len(idx), 0))
             if len(starts) != n_mols + 1 or starts[-1] != len(idx) or (p and len(par) != len(idx)):
                 raise ValueError(f"inconsistent term table '{name}'")
-            if k == 2 and len(idx):
-                idx, par = _diagonal_order(starts, idx, par)
+            idx, par, mol_waves, waves = schedule_waves(starts, idx, par)
+            self.waves[name] = (mol_waves, waves)
             fixed[name] = (starts, idx, par)
         self.tables = fixed
 
@@ -110,7 +121,9 @@ class FlatSystem:
         st.atomCounts = self.atom_counts.ctypes.data
         for name, _, p in LAYOUT[self.kind]:
             starts, idx, par = self.tables[name]
-            setattr(st, name, TermTableC(starts.ctypes.data, idx.ctypes.data, par.ctypes.data if p else None))
+            mw, wv = self.waves[name]
+            setattr(st, name, TermTableC(starts.ctypes.data, idx.ctypes.data, par.ctypes.data if p else None,
+                                         mw.ctypes.data, wv.ctypes.data))
         return st
 
     def to_device(self, device=None):
@@ -132,7 +145,9 @@ class FlatSystem:
             st.atomCounts = up(self.atom_counts)
             for name, _, p in LAYOUT[self.kind]:
                 starts, idx, par = self.tables[name]
-                setattr(st, name, TermTableC(up(starts), up(idx) if len(idx) else None, up(par) if p and len(par) else None))
+                mw, wv = self.waves[name]
+                setattr(st, name, TermTableC(up(starts), up(idx) if len(idx) else None, up(par) if p and len(par) else None,
+                                             up(mw), up(wv)))
             self._device[key] = (st, keep)
         return self._device[key]
 
@@ -206,7 +221,7 @@ class CheckTables:
         st = ChecksC()
         for name, _, p in CHECK_LAYOUT:
             starts, idx, par = self.tables[name]
-            setattr(st, name, TermTableC(starts.ctypes.data, idx.ctypes.data, par.ctypes.data if p else None))
+            setattr(st, name, TermTableC(starts.ctypes.data, idx.ctypes.data, par.ctypes.data if p else None, None, None))
         st.numImpropers = self.num_impropers.ctypes.data
         return st
 
@@ -226,7 +241,8 @@ class CheckTables:
             st = ChecksC()
             for name, _, p in CHECK_LAYOUT:
                 starts, idx, par = self.tables[name]
-                setattr(st, name, TermTableC(up(starts), up(idx) if len(idx) else None, up(par) if p and len(par) else None))
+                setattr(st, name, TermTableC(up(starts), up(idx) if len(idx) else None, up(par) if p and len(par) else None,
+                                             None, None))
             st.numImpropers = up(self.num_impropers)
             self._device[key] = (st, keep)
         return self._device[key]

@@ -3,36 +3,91 @@ import numpy as np
 
 import oracle
 from nvmolkit_b200 import synthetic as S
-from nvmolkit_b200.forcefield import FlatSystem, _diagonal_order
+from nvmolkit_b200.forcefield import LAYOUT, FlatSystem, schedule_waves
 
 
-def test_diagonal_order_spreads_atoms_and_keeps_energies():
+def _check_waves(system):
+    """Every table: waves tile the molecule's term range, hold <= 32 terms, and never name an atom twice."""
+    for name, k, _ in LAYOUT[system.kind]:
+        starts, idx, _par = system.tables[name]
+        mol_waves, waves = system.waves[name]
+        assert len(mol_waves) == system.n_mols + 1 and waves[-1] == starts[-1]
+        for m in range(system.n_mols):
+            w0, w1 = mol_waves[m], mol_waves[m + 1]
+            if starts[m] == starts[m + 1]:
+                assert w0 == w1
+                continue
+            assert waves[w0] == starts[m] and waves[w1] == starts[m + 1]
+            for w in range(w0, w1):
+                t0, t1 = waves[w], waves[w + 1]
+                assert 0 < t1 - t0 <= 32
+                atoms = idx[t0:t1].ravel().tolist()
+                assert len(set(atoms)) == len(atoms), (name, m, w)
+
+
+def test_wave_schedule_is_conflict_free_and_keeps_energies():
     system, xyz, _ = S.random_mmff_system(3, 20, 30, seed=5)
-    starts, idx, par = system.tables["vdw"]
-    for m in range(system.n_mols):
-        pairs = idx[starts[m]:starts[m + 1]].astype(int)
-        d = np.abs(pairs[:, 1] - pairs[:, 0])
-        assert (np.diff(d) >= 0).all()  # sorted by |j - i| ...
-        for a in range(0, len(pairs) - 32, 32):  # ... so a warp's worth of terms touches (almost) only distinct atoms
-            blk = pairs[a:a + 32]
-            if d[a] == d[a + 31] and d[a] >= 32:
-                assert len(set(blk.ravel().tolist())) == 64
-    # any order gives the same energies up to summation order: shuffle the pair tables and compare through the oracle
+    _check_waves(system)
+    flat, _ = S.random_embed_molecules(3, 6, 14, seed=9)
+    _check_waves(flat.dg)
+    _check_waves(flat.etk)
+    # an all-pairs table fills its waves: rounds of a round-robin tournament, (M - 1) / 2 pairs each
+    starts, idx, _ = flat.dg.tables["dist"]
+    mol_waves, waves = flat.dg.waves["dist"]
+    for m in range(flat.dg.n_mols):
+        a = int(flat.dg.atom_counts[m])
+        n_waves = mol_waves[m + 1] - mol_waves[m]
+        rounds = a if a % 2 else a + 1
+        assert n_waves <= rounds * -(-(rounds // 2) // 32)
+    # any order gives the same energies up to summation order: shuffle every table and compare through the oracle
     rng = np.random.default_rng(0)
     tables = {}
     for name, (st, ix, pr) in system.tables.items():
-        if ix.shape[1] == 2:
-            perm = np.concatenate([st[m] + rng.permutation(st[m + 1] - st[m]) for m in range(system.n_mols)]).astype(int)
-            ix, pr = ix[perm], pr[perm]
-        tables[name] = (st, ix, pr)
+        perm = np.concatenate([st[m] + rng.permutation(st[m + 1] - st[m]) for m in range(system.n_mols)]).astype(int)
+        tables[name] = (st, ix[perm], pr[perm])
     for m, x in enumerate(xyz):
-        e0 = oracle.ff_energy_grad("mmff", system.atom_counts, system.tables, m, x)[0]
-        e1 = oracle.ff_energy_grad("mmff", system.atom_counts, tables, m, x)[0]
+        e0, g0, _ = oracle.ff_energy_grad("mmff", system.atom_counts, system.tables, m, x)
+        e1, g1, _ = oracle.ff_energy_grad("mmff", system.atom_counts, tables, m, x)
         assert abs(e0 - e1) <= 1e-11 * max(1.0, abs(e0))
-    # idempotent
-    i2, p2 = _diagonal_order(starts, idx, par)
-    assert (i2 == idx).all() and (p2 == par).all()
+        assert np.abs(g0 - g1).max() <= 1e-10 * max(1.0, np.abs(g0).max())
+    # deterministic
+    st, ix, pr = system.tables["vdw"]
+    i2, p2, mw2, w2 = schedule_waves(st, ix, pr)
+    i3, p3, mw3, w3 = schedule_waves(st, ix, pr)
+    assert (i2 == i3).all() and (p2 == p3).all() and (w2 == w3).all() and (mw2 == mw3).all()
     assert isinstance(system, FlatSystem)
+
+
+def test_wave_schedule_edge_cases():
+    # empty table, a single term, a molecule without terms between two with terms, a star graph (one hub atom)
+    z = np.zeros((0, 2), np.int16)
+    ix, pr, mw, wv = schedule_waves(np.array([0, 0, 0]), z, np.zeros((0, 3)))
+    assert mw.tolist() == [0, 0, 0] and wv.tolist() == [0]
+    star = np.array([[0, k] for k in range(1, 41)], np.int16)
+    one = np.array([[3, 1]], np.int16)
+    idx = np.concatenate([one, star])
+    par = np.arange(len(idx), dtype=np.float64).reshape(-1, 1)
+    ix, pr, mw, wv = schedule_waves(np.array([0, 1, 1, 41]), idx, par)
+    assert mw.tolist() == [0, 1, 1, 41]  # the hub is in every star term: 40 waves of one term
+    assert (np.diff(wv) == 1).all() and sorted(pr.ravel().tolist()) == list(range(41))
+    assert ix[0].tolist() == [3, 1]
+    # four-body terms
+    rng = np.random.default_rng(3)
+    quad = np.array([rng.permutation(12)[:4] for _ in range(200)], np.int16)
+    ix, pr, mw, wv = schedule_waves(np.array([0, 200]), quad, np.zeros((200, 1)))
+    for w in range(len(wv) - 1):
+        atoms = ix[wv[w]:wv[w + 1]].ravel().tolist()
+        assert len(set(atoms)) == len(atoms)
+
+
+def test_clusters_from_ids_matches_the_reference_output_format():
+    from nvmolkit_b200.clustering import clusters_from_ids
+
+    ids = np.array([1, 0, 0, 2, 0, 1], np.int32)
+    cen = np.array([4, 5, 3])
+    clusters, sizes = clusters_from_ids(ids, cen)
+    assert clusters == [(4, 1, 2), (5, 0), (3,)] and sizes == [0, 3, 5, 6]
+    assert clusters_from_ids(np.zeros(0, np.int32), np.zeros(0, np.int32)) == ([], [0])
 
 
 def _butina_rounds(adj, n):

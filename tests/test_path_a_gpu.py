@@ -281,16 +281,17 @@ def test_butina_parallel_rounds_keep_the_greedy_order(cuda, min_commits, n, degr
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05 int8) path of the count pass
-@pytest.fixture
-def force_tensor_path(cuda):
+@pytest.fixture(params=[1, 0, 2], ids=["multicast_pair", "single_cta", "pair_mma"])
+def force_tensor_path(cuda, request):
+    """Every test that takes this fixture runs on all three tile variants of the fp4 count pass:
+    similarity_tensor_cluster = 1 (CTA pair, multicast column operand; the default), 0 (one CTA per tile),
+    2 (CTA pair with tcgen05 cta_group::2 MMAs)."""
     from nvmolkit_b200 import _lib
 
-    import os
-
     _lib.set_option("similarity_tensor_min_pairs", 0)
-    if os.environ.get("B200_TENSOR_CLUSTER"):  # exercise another tile variant with the same tests (0, 1 or 2)
-        _lib.set_option("similarity_tensor_cluster", int(os.environ["B200_TENSOR_CLUSTER"]))
-    yield
+    _lib.set_option("similarity_tensor_cluster", request.param)
+    yield request.param
+    _lib.set_option("similarity_tensor_cluster", 1)
     _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
 
 
@@ -341,3 +342,67 @@ def test_tensor_cross_similarity_bit_exact(cuda, force_tensor_path, bits, n, m):
     assert (crossTanimotoSimilarity(da, db).numpy() == oracle.similarity_cross(a, b)).all()
     assert (crossCosineSimilarity(da, db).numpy() == oracle.similarity_cross(a, b, metric="cosine")).all()
     assert (crossTanimotoSimilarity(da).numpy() == oracle.similarity_cross(a)).all()
+
+
+# ------------------------------------------------------------------ sharded pair pass (the multi-GPU path, on ONE GPU)
+def _sharded_butina_one_gpu(fp, cutoff, world, cuda):
+    """What fused_butina_sharded does over `world` ranks, replayed on one device: every "rank" runs
+    b200mol_neighbor_edges with (group_offset, group_stride) = (r, world); counts are summed (the all-reduce), edge
+    lists concatenated (the all-gather-v), then b200mol_butina_from_edges clusters the full graph."""
+    import ctypes as C
+
+    from nvmolkit_b200 import _lib
+
+    d = _dev(fp, cuda)
+    n, words = d.shape
+    sptr = torch.cuda.current_stream().cuda_stream
+    total = torch.zeros(n, dtype=torch.int32, device=cuda)
+    parts, per_rank = [], []
+    for r in range(world):
+        cap = 1 << 20
+        while True:
+            counts = torch.zeros(n, dtype=torch.int32, device=cuda)
+            edges = torch.empty((cap, 2), dtype=torch.int32, device=cuda)
+            found = C.c_uint64(0)
+            _lib.call("b200mol_neighbor_edges", d.data_ptr(), n, words, 0, float(cutoff), r, world, counts.data_ptr(),
+                      edges.data_ptr(), cap, C.byref(found), sptr)
+            if found.value <= cap:
+                break
+            cap = int(found.value)
+        total += counts
+        parts.append(edges[: found.value])
+        per_rank.append(int(found.value))
+    all_edges = torch.cat(parts).contiguous()
+    ids = torch.empty(n, dtype=torch.int32, device=cuda)
+    cen = torch.empty(max(n, 1), dtype=torch.int32, device=cuda)
+    ncl = torch.zeros(1, dtype=torch.int32, device=cuda)
+    deg = total.clone()
+    _lib.call("b200mol_butina_from_edges", n, total.data_ptr(), all_edges.data_ptr(), all_edges.shape[0], ids.data_ptr(),
+              cen.data_ptr(), ncl.data_ptr(), None, sptr)
+    k = int(ncl.item())
+    return ids.cpu().numpy(), cen[:k].cpu().numpy(), all_edges.cpu().numpy(), deg.cpu().numpy(), per_rank
+
+
+@pytest.mark.parametrize("tensor", [False, True], ids=["simt_tile", "tensor_tile"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("centres,members", [(30, 20), (130, 50)])  # 600 and 6500 points: 5 and 51 tile rows
+def test_sharded_neighbor_pass_equals_oracle(cuda, world, centres, members, tensor):
+    """Parity of the multi-GPU fused Butina path: the union of the ranks' tiles must be every
+    unordered pair exactly once - same edge set, same degrees, same clusters as the single-pass CPU definition."""
+    from nvmolkit_b200 import _lib
+
+    fp = S.clustered_fingerprints(centres, members, seed=centres + world)
+    _lib.set_option("similarity_tensor_min_pairs", 0 if tensor else -1)
+    try:
+        ids, cen, edges, deg, per_rank = _sharded_butina_one_gpu(fp, 0.3, world, cuda)
+    finally:
+        _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
+    ids_cpu, cen_cpu = oracle.butina_fp(fp, 0.3)
+    want_deg = oracle.count_ge(fp, fp, 0.3) - 1  # neighbours other than the point itself
+    assert (deg == want_deg).all()
+    assert (edges[:, 0] < edges[:, 1]).all()
+    key = edges[:, 0].astype(np.int64) * len(fp) + edges[:, 1]
+    assert len(np.unique(key)) == len(key) == int(want_deg.sum()) // 2  # every neighbour pair exactly once
+    assert (ids == ids_cpu).all() and (cen == cen_cpu).all()
+    if len(fp) >= 16 * 128 * world:  # enough tile-row groups for every rank to own one
+        assert all(c > 0 for c in per_rank)
