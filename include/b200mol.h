@@ -56,6 +56,13 @@ int b200mol_set_option(const char* key, long long value);
  * alone), "csr_build", "cluster_loop", "bfgs". b200mol_profile_read waits for the phase's stop event. */
 int b200mol_profile_enable(int on);
 int b200mol_profile_read(const char* phase, float* ms);
+/* Work counters of the conformer kernels on the current device since the last reset: two banks of 8,
+ * h_out16[0..7] the embedder (b200mol_etkdg_embed), h_out16[8..15] the stand-alone minimisers (b200mol_*_minimize):
+ *   [0] BFGS iterations  [1] energy evaluations  [2] gradient evaluations
+ *   [3] ALGORITHMIC bytes of those iterations by the reference's scheme (per iteration 3 n^2 x 8 B of
+ *       inverse Hessian + (1 + line-search evaluations) x the molecule's term-record bytes) - bench.py's roofline
+ *   [4] minimisations  [5] ETKDG attempts  [6..7] reserved.   Synchronises `stream`. */
+int b200mol_stats_read(uint64_t* h_out16, int reset, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fingerprint similarity.

@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200mol_set_option": (C.c_int, [C.c_char_p, C.c_longlong]),
     "b200mol_profile_enable": (C.c_int, [C.c_int]),
     "b200mol_profile_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_float)]),
+    "b200mol_stats_read": (C.c_int, [_vp, C.c_int, _vp]),
     "b200mol_tanimoto_cross": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, _vp, _vp]),
     "b200mol_cosine_cross": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, _vp, _vp]),
     "b200mol_similarity_cross_host": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, C.c_int, C.c_int, _vp, C.c_size_t]),
@@ -111,6 +112,14 @@ def profile_read(phase: str) -> float:
     ms = C.c_float(0.0)
     check(load().b200mol_profile_read(phase.encode(), C.byref(ms)))
     return float(ms.value)
+
+
+def stats_read(reset: bool = True) -> dict:
+    """Work counters of the conformer kernels on the current device (include/b200mol.h b200mol_stats_read)."""
+    out = (C.c_uint64 * 16)()
+    check(load().b200mol_stats_read(C.cast(out, C.c_void_p), 1 if reset else 0, None))
+    keys = ("bfgs_iterations", "energy_evals", "gradient_evals", "algorithmic_bytes", "minimisations", "etkdg_attempts")
+    return {bank: {k: int(out[8 * b + i]) for i, k in enumerate(keys)} for b, bank in enumerate(("embed", "minimize"))}
 
 
 def set_option(key: str, value: int) -> None:

@@ -18,6 +18,18 @@
 
 namespace b200 {
 int g_bfgsCtasPerSm = kMinCtas;  // resident minimisation CTAs per SM (option "bfgs_ctas_per_sm")
+
+// Device-side work counters of the conformer kernels, one small buffer per device, allocated on first use: two banks of
+// kStatCount, [0] the embedder (etkdgKernel), [1] the stand-alone minimisers (bfgsKernel<FF>).
+unsigned long long* pathBStats() {
+  static unsigned long long* buf[kMaxDevices] = {};
+  const int                  d               = currentDeviceSlot();
+  if (!buf[d]) {
+    B200_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf[d]), 2 * kStatCount * sizeof(unsigned long long)));
+    B200_CUDA(cudaMemset(buf[d], 0, 2 * kStatCount * sizeof(unsigned long long)));
+  }
+  return buf[d];
+}
 namespace {
 
 struct Batch {
@@ -37,6 +49,7 @@ struct Batch {
   size_t         hessStride;
   int*           queue;
   int            maxN;
+  unsigned long long* stats;
 };
 
 template <class FF>
@@ -46,7 +59,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) bfgsKernel(const typename FF::Sy
   __shared__ double                     colBuf[kColBuf];
   __shared__ int                        nextConf;
   constexpr int                         DIM = FF::kDim;
-  const BfgsWork w = carveWork(sm, b.maxN, b.hessWs + static_cast<size_t>(blockIdx.x) * b.hessStride, red, colBuf);
+  const BfgsWork w = carveWork(sm, b.maxN, b.hessWs + static_cast<size_t>(blockIdx.x) * b.hessStride, red, colBuf, b.stats);
   const int      tid = threadIdx.x;
   for (;;) {
     __syncthreads();
@@ -136,7 +149,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   Scratch<int>       queue(1, s);
   B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));
   Batch b{nConf, confMol, confAtomStart, pos, maxIters, gradTol, scaleGrads, 0, active, energy, status, iters,
-          hess.get(), stride, queue.get(), maxN};
+          hess.get(), stride, queue.get(), maxN, pathBStats() + kStatCount};
   PhaseTimer t("bfgs", s);
   bfgsKernel<FF><<<blocks, kT, smem, s>>>(sys, par, b);
   B200_LAUNCHED();
@@ -286,6 +299,17 @@ extern "C" int b200mol_poly_minimize(int32_t nSys, const int32_t* d_starts, int 
     ff::Poly::System sys{power, d_w, d_c, d_starts};
     runMinimize<ff::Poly>(sys, {}, nSys, nullptr, d_starts, max_dim, d_x, max_iters, grad_tol, scale_grads, nullptr, d_energy,
                           d_status, d_iters, asStream(stream));
+  });
+}
+
+extern "C" int b200mol_stats_read(uint64_t* h_out16, int reset, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h_out16, "null pointer");
+    cudaStream_t        s = asStream(stream);
+    unsigned long long* d = pathBStats();
+    B200_CUDA(cudaMemcpyAsync(h_out16, d, 2 * kStatCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (reset) B200_CUDA(cudaMemsetAsync(d, 0, 2 * kStatCount * sizeof(unsigned long long), s));
+    B200_CUDA(cudaStreamSynchronize(s));
   });
 }
 

@@ -120,7 +120,10 @@ struct BfgsWorkT {
   double* scratch;                                  // shared memory, 3 * maxN doubles (scaled vectors of the Hessian passes)
   double* colBuf;                                   // shared memory, kColBuf doubles: per-warp column sums of one sweep chunk
   int     maxN;                                     // stride of the accumulators
+  unsigned long long* stats;                        // device counters (kStat*), may be nullptr
 };
+// Work counters of the conformer kernels (b200mol_stats_read): what bench.py's roofline of this path is computed from.
+enum : int { kStatIters = 0, kStatEnergyEvals = 1, kStatGradEvals = 2, kStatAlgoBytes = 3, kStatMinimisations = 4, kStatAttempts = 5, kStatCount = 8 };
 constexpr int kBfgsVectors = 6 + kWarps;
 constexpr int kColBuf      = 2 * kWarps * 64;  // doubles: 2 products x kWarps x 64 fp64 (= 128 fp32) columns of a chunk
 template <class HT>
@@ -130,9 +133,10 @@ __host__ __device__ inline int bfgsLd(int n) {
 }  // six working vectors + four scratch vectors of maxN doubles
 using BfgsWork = BfgsWorkT<double>;
 template <class HT = double>
-__device__ __forceinline__ BfgsWorkT<HT> carveWork(double* sm, int maxN, HT* H, double* red, double* colBuf) {
+__device__ __forceinline__ BfgsWorkT<HT> carveWork(double* sm, int maxN, HT* H, double* red, double* colBuf,
+                                                    unsigned long long* stats = nullptr) {
   double* acc = sm + 6 * maxN;  // accumulators: grad | hdg | newPos | kWarps - 3 more
-  return {sm, acc, sm + maxN, acc + 2 * maxN, sm + 2 * maxN, acc + maxN, H, red, sm + 3 * maxN, colBuf, maxN};
+  return {sm, acc, sm + maxN, acc + 2 * maxN, sm + 2 * maxN, acc + maxN, H, red, sm + 3 * maxN, colBuf, maxN, stats};
 }
 
 struct BfgsOutcome {
@@ -308,6 +312,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
   // leading dimension of the slab: rows padded to 128 bytes so that every warp access is whole, aligned cache lines
   const int ld = bfgsLd<HT>(n);
   int       status = 1, iter = 0;
+  unsigned  nEvals = 0, nIters = 0, nGrads = 0;  // work counters (thread 0 publishes them)
 #ifdef B200_BFGS_TIMING
   long long tim[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long tAll = clock64();
@@ -319,6 +324,8 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
 
     double fp = energyOf<FF>(view, pos, red);
     gradOf<FF>(view, pos, grad, w.maxN, n);
+    ++nEvals;
+    ++nGrads;
     double gradScale = scaleGrad(n, grad, scaleGrads, red);
     double s2        = 0.0;
     for (int i = tid; i < n; i += kT) {
@@ -354,6 +361,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
           newVal = energyOf<FF>(view, newPos, red);
           B200_T1(0);
         }
+        ++nEvals;
         if (newVal - fp <= FUNCTOL * lambda * slope) {
           accepted = true;
           break;
@@ -401,6 +409,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
         gradOf<FF>(view, pos, grad, w.maxN, n);
         B200_T1(1);
       }
+      ++nGrads;
       gradScale = scaleGrad(n, grad, scaleGrads, red);
       tst       = 0.0;
       for (int i = tid; i < n; i += kT) {
@@ -496,9 +505,19 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
 #endif
       __syncthreads();
     }
+    nIters += iter < maxIters ? iter + 1 : iter;
     if (status == 0 || restart >= maxRestarts) break;
   }
   __syncthreads();
+  if (w.stats && tid == 0) {
+    // per iteration 3 n^2 x 8 B of inverse Hessian + (1 + k_ls) x T bytes of term records
+    const unsigned long long T = FF::termBytes(view);
+    atomicAdd(w.stats + kStatIters, static_cast<unsigned long long>(nIters));
+    atomicAdd(w.stats + kStatEnergyEvals, static_cast<unsigned long long>(nEvals + 1));
+    atomicAdd(w.stats + kStatGradEvals, static_cast<unsigned long long>(nGrads));
+    atomicAdd(w.stats + kStatAlgoBytes, 24ull * n * n * nIters + T * (nEvals + 1 + nGrads));
+    atomicAdd(w.stats + kStatMinimisations, 1ull);
+  }
   BfgsOutcome out;
   out.status = status;
   out.iters  = iter;

@@ -21,6 +21,7 @@
 
 namespace b200 {
 extern int g_bfgsCtasPerSm;
+unsigned long long* pathBStats();
 namespace {
 
 using ff::V3;
@@ -45,6 +46,7 @@ struct EmbedArgs {
   // attempt-level work stealing (see etkdgKernel): per slot, the next attempt index to hand out, the lowest successful
   // attempt so far (kNoAttempt = none), a spin lock for the result write, and the number of attempts that have ended
   int *slotNext, *slotBest, *slotLock, *slotDone;
+  unsigned long long* stats;
 };
 constexpr int kNoAttempt      = 0x7f7f7f7f;  // cudaMemset(0x7f) pattern
 constexpr int kMaxSpeculation = 8;           // attempts of one slot in flight at once, at most
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kRed];
   __shared__ double                     colBuf[kColBuf];
-  const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red, colBuf);
+  const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red, colBuf, a.stats);
   double*        ref = sm + kBfgsVectors * a.maxN;  // ETK reference geometry
   const int      tid = threadIdx.x;
   // Work item = one ATTEMPT of one slot. A CTA first works through the slot queue, retrying its own slot while it fails;
@@ -319,7 +321,10 @@ __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
       } else if (tid == 0 && a.stageFailures) {
         atomicAdd(a.stageFailures + failedStage, 1ull);
       }
-      if (tid == 0) atomicAdd(a.slotDone + slot, 1);
+      if (tid == 0) {
+        atomicAdd(a.slotDone + slot, 1);
+        if (a.stats) atomicAdd(a.stats + kStatAttempts, 1ull);
+      }
     }
   }
 }
@@ -394,7 +399,8 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     B200_CUDA(cudaMemsetAsync(state.get() + nSlots, 0x7f, sizeof(int) * nSlots, s));
     EmbedArgs a{*dg, *etk, *checks, *params, nSlots, d_slot_mol, d_slot_atom_start, d_coords, d_ok, d_attempts, d_energy,
                 reinterpret_cast<unsigned long long*>(d_stage_failures), hess.get(), stride, queue.get(), maxN,
-                state.get(), state.get() + nSlots, state.get() + 2 * static_cast<size_t>(nSlots), state.get() + 3 * static_cast<size_t>(nSlots)};
+                state.get(), state.get() + nSlots, state.get() + 2 * static_cast<size_t>(nSlots), state.get() + 3 * static_cast<size_t>(nSlots),
+                pathBStats()};
     PhaseTimer t("etkdg", s);
     etkdgKernel<<<blocks, kT, smem, s>>>(a);
     B200_LAUNCHED();
@@ -419,7 +425,7 @@ extern "C" int b200mol_etkdg_check(const b200mol_dg_system* dg, const b200mol_et
     int blocks = smCount() * 4;
     if (blocks > nSlots) blocks = nSlots;
     EmbedArgs a{*dg, *etk, *checks, *params, nSlots, d_slot_mol, d_slot_atom_start, nullptr, nullptr, nullptr, nullptr,
-                nullptr, nullptr, 0, nullptr, 4 * max_atoms};
+                nullptr, nullptr, 0, nullptr, 4 * max_atoms, nullptr, nullptr, nullptr, nullptr, nullptr};
     etkdgCheckKernel<<<blocks, kT, smem, asStream(stream)>>>(a, d_pos4, d_fail_masks);
     B200_LAUNCHED();
   });

@@ -95,6 +95,12 @@ struct Mmff {
             range(s.oop, mol), range(s.torsion, mol), range(s.vdw, mol),   range(s.ele, mol)};
   }
 
+  // bytes of this molecule's term records (K int16 + P fp64 each): the T of SURVEY.md 8d's per-iteration figure
+  __device__ static unsigned termBytes(const View& v) {
+    return (v.bond.end - v.bond.beg) * 20u + (v.angle.end - v.angle.beg) * 30u + (v.strbend.end - v.strbend.beg) * 46u +
+           (v.oop.end - v.oop.beg) * 16u + (v.torsion.end - v.torsion.beg) * 32u + (v.vdw.end - v.vdw.beg) * 20u +
+           (v.ele.end - v.ele.beg) * 28u;
+  }
   template <bool GRAD>
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
@@ -286,6 +292,9 @@ struct Dg {
   __device__ static View view(const System& s, int mol, const Params& p) {
     return {&s, range(s.dist, mol), range(s.chiral, mol), range(s.fourth, mol), p.chiralWeight, p.fourthWeight};
   }
+  __device__ static unsigned termBytes(const View& v) {
+    return (v.dist.end - v.dist.beg) * 28u + (v.chiral.end - v.chiral.beg) * 24u + (v.fourth.end - v.fourth.beg) * 2u;
+  }
   template <bool GRAD>
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
@@ -380,6 +389,10 @@ struct Etk {
     if (p.plain) emptyRange(imp);
     return {&s, range(s.torsion, mol), imp, range(s.dist12, mol), range(s.dist13, mol), range(s.angle13, mol),
             range(s.longrange, mol), nullptr};
+  }
+  __device__ static unsigned termBytes(const View& v) {
+    return (v.torsion.end - v.torsion.beg) * 104u + (v.improper.end - v.improper.beg) * 40u + (v.d12.end - v.d12.beg) * 36u +
+           (v.d13.end - v.d13.beg) * 36u + (v.a13.end - v.a13.beg) * 22u + (v.lr.end - v.lr.beg) * 28u;
   }
 
   // Flat-bottom distance terms. P = 4 {min, max, k, fixed}: with a reference geometry the window of every term whose
@@ -542,6 +555,10 @@ struct Uff {
   };
   __device__ static View view(const System& s, int mol, const Params&) {
     return {&s, range(s.bond, mol), range(s.angle, mol), range(s.torsion, mol), range(s.inversion, mol), range(s.vdw, mol)};
+  }
+  __device__ static unsigned termBytes(const View& v) {
+    return (v.bond.end - v.bond.beg) * 20u + (v.angle.end - v.angle.beg) * 54u + (v.torsion.end - v.torsion.beg) * 32u +
+           (v.inversion.end - v.inversion.beg) * 40u + (v.vdw.end - v.vdw.beg) * 28u;
   }
   template <bool GRAD>
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
@@ -735,6 +752,7 @@ struct Poly {
   __device__ static View view(const System& s, int sys, const Params&) {
     return {s.w + s.starts[sys], s.c + s.starts[sys], s.starts[sys + 1] - s.starts[sys], s.power};
   }
+  __device__ static unsigned termBytes(const View& v) { return v.n * 16u; }
   template <bool GRAD>
   __device__ static double eval(const View& v, const double* x, double* grad, int tid, int nT) {
     double e = 0.0;

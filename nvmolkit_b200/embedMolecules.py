@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from nvmolkit_b200 import _lib
+from nvmolkit_b200._hostutil import rows_of, running_index
 from nvmolkit_b200._interop import require_cuda, stream_ctx, stream_ptr
 from nvmolkit_b200.forcefield import CheckTables, FlatSystem
 from nvmolkit_b200.types import AsyncGpuResult, CoordinateOutput, Device3DResult, HardwareOptions
@@ -58,6 +59,20 @@ class FlatEmbedMolecules:
     @property
     def atom_counts(self) -> np.ndarray:
         return self.dg.atom_counts
+
+    @classmethod
+    def concat(cls, parts: "List[FlatEmbedMolecules]") -> "FlatEmbedMolecules":
+        return cls(FlatSystem.concat([p.dg for p in parts]), FlatSystem.concat([p.etk for p in parts]),
+                   CheckTables.concat([p.checks for p in parts]))
+
+    def nbytes(self) -> int:
+        return self.dg.nbytes() + self.etk.nbytes() + self.checks.nbytes()
+
+    def drop_device(self) -> None:
+        """Forget the uploaded copies (the next call uploads the tables again: bench.py's end-to-end leg)."""
+        self.dg._device.clear()
+        self.etk._device.clear()
+        self.checks._device.clear()
 
 
 def _params_struct(params, max_attempts: int, seed_fallback: int = 0xB200) -> EmbedParamsC:
@@ -125,18 +140,11 @@ def _to_device_result(raw: EmbedRaw, n_mols: int, gpu_id: int) -> Device3DResult
     # present results in input molecule order, conformer order within a molecule
     keep = keep[np.argsort(raw.slot_mol[keep], kind="stable")]
     dev = raw.coords.device
-    if len(keep):
-        rows = np.concatenate([np.arange(raw.slot_atom_start[s], raw.slot_atom_start[s + 1]) for s in keep])
-    else:
-        rows = np.zeros(0, dtype=np.int64)
-    values = raw.coords[torch.from_numpy(rows.astype(np.int64)).to(dev)]
+    rows = rows_of(raw.slot_atom_start, keep)
+    values = raw.coords[torch.from_numpy(rows).to(dev)]
     starts = np.concatenate([[0], np.cumsum(sizes[keep])]).astype(np.int32)
     mol_idx = raw.slot_mol[keep].astype(np.int32)
-    conf_idx = np.zeros(len(keep), dtype=np.int32)
-    seen: dict = {}
-    for k, m in enumerate(mol_idx):
-        conf_idx[k] = seen.get(int(m), 0)
-        seen[int(m)] = conf_idx[k] + 1
+    conf_idx = running_index(mol_idx)
     t = lambda a: AsyncGpuResult(torch.from_numpy(a).to(dev))  # noqa: E731
     return Device3DResult(AsyncGpuResult(values), t(starts), t(mol_idx), t(conf_idx), gpu_id, n_mols)
 

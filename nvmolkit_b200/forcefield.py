@@ -70,6 +70,8 @@ class FlatSystem:
 
     def __post_init__(self):
         self.atom_counts = np.ascontiguousarray(self.atom_counts, dtype=np.int32)
+        if self.waves:  # already scheduled (concat of scheduled systems)
+            return
         n_mols = len(self.atom_counts)
         fixed = {}
         for name, k, p in LAYOUT[self.kind]:
@@ -104,6 +106,35 @@ class FlatSystem:
                             np.concatenate(idxs) if idxs else np.zeros((0, k), np.int16),
                             np.concatenate(pars) if pars else np.zeros((0, p)))
         return cls(kind, np.asarray(atom_counts, dtype=np.int32), tables)
+
+    @classmethod
+    def concat(cls, parts: "Sequence[FlatSystem]") -> "FlatSystem":
+        """The molecules of several systems of one kind, in order; the wave schedules are spliced, not recomputed."""
+        kind = parts[0].kind
+        tables, waves = {}, {}
+        for name, _k, _p in LAYOUT[kind]:
+            starts, mol_waves, wave_list = [np.zeros(1, np.int32)], [np.zeros(1, np.int32)], []
+            t_off = w_off = 0
+            for part in parts:
+                st, _ix, _pr = part.tables[name]
+                mw, wv = part.waves[name]
+                starts.append(st[1:] + t_off)
+                mol_waves.append(mw[1:] + w_off)
+                wave_list.append(wv[:-1] + t_off)
+                t_off += int(st[-1])
+                w_off += len(wv) - 1
+            wave_list.append(np.array([t_off], np.int32))
+            tables[name] = (np.concatenate(starts).astype(np.int32), np.concatenate([p.tables[name][1] for p in parts]),
+                            np.concatenate([p.tables[name][2] for p in parts]))
+            waves[name] = (np.concatenate(mol_waves).astype(np.int32), np.concatenate(wave_list).astype(np.int32))
+        return cls(kind, np.concatenate([p.atom_counts for p in parts]), tables, waves=waves)
+
+    def nbytes(self) -> int:
+        """Bytes of the tables as uploaded (starts, indices, parameters, wave schedule)."""
+        total = self.atom_counts.nbytes
+        for name, (st, ix, pr) in self.tables.items():
+            total += st.nbytes + ix.nbytes + pr.nbytes + sum(a.nbytes for a in self.waves[name])
+        return int(total)
 
     def tile(self, reps: int) -> "FlatSystem":
         """The same molecules repeated `reps` times as distinct table entries (bench workloads)."""
@@ -216,6 +247,22 @@ class CheckTables:
             tables[name] = (np.array(starts, dtype=np.int32), np.ascontiguousarray(np.concatenate(idxs)),
                             np.ascontiguousarray(np.concatenate(pars)))
         return cls(tables, np.ascontiguousarray(num_impropers, dtype=np.int32))
+
+    @classmethod
+    def concat(cls, parts: "Sequence[CheckTables]") -> "CheckTables":
+        tables = {}
+        for name, _k, _p in CHECK_LAYOUT:
+            starts, off = [np.zeros(1, np.int32)], 0
+            for part in parts:
+                st = part.tables[name][0]
+                starts.append(st[1:] + off)
+                off += int(st[-1])
+            tables[name] = (np.concatenate(starts).astype(np.int32), np.concatenate([p.tables[name][1] for p in parts]),
+                            np.concatenate([p.tables[name][2] for p in parts]))
+        return cls(tables, np.concatenate([p.num_impropers for p in parts]))
+
+    def nbytes(self) -> int:
+        return int(self.num_impropers.nbytes + sum(a.nbytes for t in self.tables.values() for a in t))
 
     def host_struct(self):
         st = ChecksC()

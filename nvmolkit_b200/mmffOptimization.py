@@ -8,6 +8,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
+from nvmolkit_b200._hostutil import rows_of, running_index
 from nvmolkit_b200.forcefield import ConformerBatch, FlatSystem
 from nvmolkit_b200.minimizer import minimize
 from nvmolkit_b200.types import AsyncGpuResult, CoordinateOutput, Device3DResult, HardwareOptions
@@ -23,11 +24,7 @@ class FlatMMFFMolecules:
 
 def _device_result(system: FlatSystem, batch: ConformerBatch, res, gpu: int) -> Device3DResult:
     dev = res.positions.device
-    conf_idx = np.zeros(batch.n_conf, dtype=np.int32)
-    seen: dict = {}
-    for k, m in enumerate(batch.conf_mol):
-        conf_idx[k] = seen.get(int(m), 0)
-        seen[int(m)] = conf_idx[k] + 1
+    conf_idx = running_index(batch.conf_mol)
     t = lambda a: AsyncGpuResult(torch.from_numpy(np.ascontiguousarray(a)).to(dev))  # noqa: E731
     return Device3DResult(AsyncGpuResult(res.positions.reshape(-1, 3)), t(batch.atom_starts), t(batch.conf_mol), t(conf_idx),
                           gpu, system.n_mols, energies=AsyncGpuResult(res.energies),
@@ -44,15 +41,15 @@ def _optimize(kind_system: FlatSystem, batch: ConformerBatch, max_iters: int, ha
         order = np.argsort(-np.diff(batch.atom_starts), kind="stable")
         sizes = np.diff(batch.atom_starts)[order]
         starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
-        rows = np.concatenate([np.arange(batch.atom_starts[c], batch.atom_starts[c + 1]) for c in order]) if len(order) else np.zeros(0, np.int64)
+        rows = rows_of(batch.atom_starts, order)
         sorted_batch = ConformerBatch(batch.conf_mol[order], starts, batch.positions[rows])
         res = minimize(kind_system, sorted_batch, max_iters, grad_tol)
         # back to input order
         inv = np.argsort(order, kind="stable")
         pos_sorted = res.positions
         dev = pos_sorted.device
-        back_rows = np.concatenate([np.arange(starts[k], starts[k + 1]) for k in inv]) if len(inv) else np.zeros(0, np.int64)
-        res.positions = pos_sorted[torch.from_numpy(back_rows.astype(np.int64)).to(dev)]
+        back_rows = rows_of(starts, inv)
+        res.positions = pos_sorted[torch.from_numpy(back_rows).to(dev)]
         inv_t = torch.from_numpy(inv.astype(np.int64)).to(dev)
         res.energies, res.status, res.iters = res.energies[inv_t], res.status[inv_t], res.iters[inv_t]
         if output == CoordinateOutput.DEVICE:
