@@ -211,6 +211,53 @@ typedef struct b200mol_uff_system {
   b200mol_term_table bond, angle, torsion, inversion, vdw;
 } b200mol_uff_system;
 
+/* ------------------------------------------------------------------------------------------
+ * Term construction on the HOST from a smoothed bounds matrix (pure arithmetic, no RDKit): the seam just below
+ * RDKit's setTopolBounds / getExperimentalTorsions. h_bounds = RDKit BoundsMatrix layout, nAtoms x nAtoms row-major,
+ * upper bound at [min][max], lower bound at [max][min]. Outputs are caller-allocated at their maximum sizes:
+ * pairs nAtoms*(nAtoms-1)/2, chiral nChiral, fourth nAtoms.
+ * Replaces constructForceFieldContribs (rdkit_extensions/dist_geom_flattened_builder.cpp:472-491, :56-122):
+ * every pair with ub - lb <= basinSizeTol becomes a distance term {lb^2, ub^2, weight 1} (the pipeline passes 1e8: all
+ * pairs), the chiral sets (h_chiral_atoms[n][4], h_chiral_bounds[n][2] = {lower, upper}) become chiral terms, dim = 4
+ * adds one fourth-dimension term per atom. h_counts3 = {nDist, nChiral, nFourth}. */
+int b200mol_dg_terms_from_bounds(int32_t nAtoms, const double* h_bounds, int32_t nChiral, const int32_t* h_chiral_atoms,
+                                 const double* h_chiral_bounds, int dim, double basinSizeTol, int16_t* h_dist_idx,
+                                 double* h_dist_par, int16_t* h_chiral_idx, double* h_chiral_par, int16_t* h_fourth_idx,
+                                 int32_t* h_counts3);
+/* RDKit ForceFields::CrystalFF::CrystalFFDetails as plain arrays (host memory). */
+typedef struct b200mol_crystalff_details {
+  int32_t        nTorsions;
+  const int32_t* torsionAtoms; /* [n][4] expTorsionAtoms */
+  const double*  torsionV;     /* [n][6] expTorsionAngles[.].second (force constants), zero-padded */
+  const int32_t* torsionSigns; /* [n][6] expTorsionAngles[.].first, zero-padded */
+  int32_t        nImpropers;
+  const int32_t* improperAtoms; /* [n][6] {a0, centre, a2, a3, Z of the centre, isCBoundToO} */
+  int32_t        nBonds;
+  const int32_t* bonds; /* [n][2] */
+  int32_t        nAngles;
+  const int32_t* angles; /* [n][4] {a, centre, b, isTripleBond} */
+  double         boundsMatForceScaling;
+} b200mol_crystalff_details;
+/* Output buffers of b200mol_etk_terms_from_details, sized by the caller: torsion nTorsions, improper 3 * nImpropers,
+ * dist12 nBonds, dist13 and angle13 nAngles each, longrange nAtoms*(nAtoms-1)/2 (record layouts: b200mol_etk_system). */
+typedef struct b200mol_etk_term_buffers {
+  int16_t* torsion_idx;   double* torsion_par;
+  int16_t* improper_idx;  double* improper_par;
+  int16_t* dist12_idx;    double* dist12_par;
+  int16_t* dist13_idx;    double* dist13_par;
+  int16_t* angle13_idx;   double* angle13_par;
+  int16_t* longrange_idx; double* longrange_par;
+} b200mol_etk_term_buffers;
+/* Replaces construct3DForceFieldContribs (dist_geom_flattened_builder.cpp:493-541, :124-470): experimental torsions,
+ * improper terms (3 permutations per centre, inversion coefficients by element, x10 force scaling; only with
+ * useBasicKnowledge), 1-2 windows (+-0.01, k 100), 1-3 windows (triple bond: angle 179..180; improper-constrained
+ * centre: the bounds, fixed; else +-0.01), long-range terms for every other pair (the bounds, k = 10 x
+ * boundsMatForceScaling). h_counts6 = terms written per table in b200mol_etk_system order; *h_num_impropers = the
+ * planarity check's count (improper centres, not terms). */
+int b200mol_etk_terms_from_details(int32_t nAtoms, const double* h_bounds, const b200mol_crystalff_details* details,
+                                   int useBasicKnowledge, b200mol_etk_term_buffers* out, int32_t* h_counts6,
+                                   int32_t* h_num_impropers);
+
 /* Energies (d_energy[nConf]) and, when d_grad != NULL, gradients (d_grad[totalAtoms*dim], overwritten) of a
  * conformer batch. Replaces launch*EnergyKernel / launch*GradientKernel + combinedEnergies/GradKernel
  * (src/forcefields/mmff_kernels.h, mmff_kernels.cu:1067-1125; dist_geom_kernels.cu). */

@@ -133,10 +133,10 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   const int    maxN = FF::kDim * maxAtoms;
   const size_t smem = static_cast<size_t>(kBfgsVectors + (FF::kHasRef ? 1 : 0)) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large for the shared-memory BFGS (%d atoms)", maxAtoms);
-  static size_t configured[kMaxDevices] = {};  // per instantiation and device
-  if (smem > 48 * 1024 && smem > configured[currentDeviceSlot()]) {
+  static bool configured[kMaxDevices] = {};  // per instantiation and device; static + dynamic may pass 48 KB together
+  if (!configured[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(bfgsKernel<FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured[currentDeviceSlot()] = 200 * 1024;
+    configured[currentDeviceSlot()] = true;
   }
   int perSm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, bfgsKernel<FF>, kT, smem));
@@ -165,10 +165,10 @@ void runEnergyGrad(const typename FF::System& sys, const typename FF::Params& pa
   const int    maxN = FF::kDim * maxAtoms;
   const size_t smem = static_cast<size_t>(1 + kWarps) * maxN * sizeof(double);
   B200_REQUIRE(smem <= 200 * 1024, "molecule too large (%d atoms)", maxAtoms);
-  static size_t configured[kMaxDevices] = {};
-  if (smem > 48 * 1024 && smem > configured[currentDeviceSlot()]) {
+  static bool configured[kMaxDevices] = {};
+  if (!configured[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(energyGradKernel<FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured[currentDeviceSlot()] = 200 * 1024;
+    configured[currentDeviceSlot()] = true;
   }
   int blocks = smCount() * 4;
   if (blocks > nConf) blocks = nConf;

@@ -417,3 +417,55 @@ def etkdg_embed_batch(dg, etk, checks, num_impropers, params: dict, slot_mol, sl
     L.oracle_etkdg_embed_batch(C.addressof(d), C.addressof(e), C.addressof(ck), C.addressof(pr), n, slot_mol.ctypes.data,
                                starts.ctypes.data, coords.ctypes.data, ok.ctypes.data, att.ctypes.data, en.ctypes.data)
     return coords, ok, att, en
+
+
+# ------------------------------------------------------------------------------------------------ term construction
+def dg_dist_terms(bounds: np.ndarray, basin: float = 1e8):
+    """(idx [n,2] int32 with i > j, par [n,3] = lb^2, ub^2, weight) — oracle_build.c oracle_dg_dist_terms."""
+    L = lib()
+    b = np.ascontiguousarray(bounds, np.float64)
+    n = b.shape[0]
+    idx = np.empty((n * (n - 1) // 2, 2), np.int32)
+    par = np.empty((n * (n - 1) // 2, 3))
+    L.oracle_dg_dist_terms.restype = C.c_int
+    L.oracle_dg_dist_terms.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    k = L.oracle_dg_dist_terms(n, b.ctypes.data, float(basin), idx.ctypes.data, par.ctypes.data)
+    return idx[:k], par[:k]
+
+
+def inversion_coefficients(z: int, c_bound_to_o: bool):
+    """(k / 3, C0, C1, C2) of an improper centre of atomic number z."""
+    L = lib()
+    out = (C.c_double * 4)()
+    L.oracle_inversion_coefficients.restype = None
+    L.oracle_inversion_coefficients.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.oracle_inversion_coefficients(int(z), 1 if c_bound_to_o else 0, out)
+    return tuple(out)
+
+
+def etk_terms(bounds, torsion_atoms, improper_atoms, bond_atoms, angle_atoms, scaling: float, basic: bool):
+    """ETK tables other than the torsions (which are copied through) as dict name -> (idx int32, par)."""
+    L = lib()
+    b = np.ascontiguousarray(bounds, np.float64)
+    n = b.shape[0]
+    ta = np.ascontiguousarray(torsion_atoms, np.int32).reshape(-1, 4)
+    ia = np.ascontiguousarray(improper_atoms, np.int32).reshape(-1, 6)
+    ba = np.ascontiguousarray(bond_atoms, np.int32).reshape(-1, 2)
+    aa = np.ascontiguousarray(angle_atoms, np.int32).reshape(-1, 4)
+    npair = n * (n - 1) // 2
+    imp_i, imp_p = np.empty((3 * len(ia), 4), np.int32), np.empty((3 * len(ia), 4))
+    d12_p = np.empty((len(ba), 4))
+    d13_i, d13_p = np.empty((len(aa), 2), np.int32), np.empty((len(aa), 4))
+    a13_i, a13_p = np.empty((len(aa), 3), np.int32), np.empty((len(aa), 2))
+    lr_i, lr_p = np.empty((npair, 2), np.int32), np.empty((npair, 3))
+    counts = (C.c_int32 * 5)()
+    L.oracle_etk_terms.restype = None
+    L.oracle_etk_terms.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 10
+    L.oracle_etk_terms(n, b.ctypes.data, len(ta), ta.ctypes.data, len(ia), ia.ctypes.data, len(ba), ba.ctypes.data, len(aa),
+                       aa.ctypes.data, float(scaling), 1 if basic else 0, imp_i.ctypes.data, imp_p.ctypes.data,
+                       d12_p.ctypes.data, d13_i.ctypes.data, d13_p.ctypes.data, a13_i.ctypes.data, a13_p.ctypes.data,
+                       lr_i.ctypes.data, lr_p.ctypes.data, counts)
+    return {"improper": (imp_i[: counts[0]], imp_p[: counts[0]]), "dist12": (ba.copy(), d12_p),
+            "dist13": (d13_i[: counts[1]], d13_p[: counts[1]]), "angle13": (a13_i[: counts[2]], a13_p[: counts[2]]),
+            "longrange": (lr_i[: counts[3]], lr_p[: counts[3]])}, int(counts[4])
