@@ -489,7 +489,15 @@ def _conformer_roofline(stats, phases, peak, peak_src, traffic):
         if not ms or not st["bfgs_iterations"]:
             continue
         ach = st["algorithmic_bytes"] / (ms * 1e-3) / 1e9
+        # what THIS design has to move for the same iterations: one read + one write of the upper triangle of the inverse
+        # Hessian (f32 in the embedder, f64 in MMFF) instead of three passes over the full f64 matrix, same term bytes
+        own = st["algorithmic_bytes"] - 24 * st["n2_iterations"] + (4 if bank == "embed" else 8) * st["n2_iterations"]
         out[bank] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "own_scheme_bytes": own, "own_scheme_GBps": own / (ms * 1e-3) / 1e9,
+                     "own_scheme_frac": own / (ms * 1e-3) / 1e9 / peak,
+                     "note": "achieved = the reference scheme's bytes (SURVEY.md 8d: 3 n^2 x 8 B + term records per iteration) / "
+                             "time, so frac > 1 means: faster than that scheme could run at the HBM roof; own_scheme_* = the bytes "
+                             "this kernel's one-sweep triangular update needs",
                      "traffic": traffic.get(kernel), "kernel": kernel, "kernel_ms": ms,
                      "algorithmic_bytes": st["algorithmic_bytes"], "bfgs_iterations": st["bfgs_iterations"],
                      "energy_evals": st["energy_evals"], "gradient_evals": st["gradient_evals"],

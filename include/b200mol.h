@@ -61,7 +61,8 @@ int b200mol_profile_read(const char* phase, float* ms);
  *   [0] BFGS iterations  [1] energy evaluations  [2] gradient evaluations
  *   [3] ALGORITHMIC bytes of those iterations by the reference's scheme (per iteration 3 n^2 x 8 B of
  *       inverse Hessian + (1 + line-search evaluations) x the molecule's term-record bytes) - bench.py's roofline
- *   [4] minimisations  [5] ETKDG attempts  [6..7] reserved.   Synchronises `stream`. */
+ *   [4] minimisations  [5] ETKDG attempts  [6] sum over iterations of n^2 (n = BFGS variables)  [7] reserved.
+ * Synchronises `stream`. */
 int b200mol_stats_read(uint64_t* h_out16, int reset, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -330,6 +331,9 @@ typedef struct b200mol_embed_params {
   int32_t  maxAttempts;       /* per conformer slot (reference: maxIterations) */
   int32_t  dgIters, fourthIters, etkIters; /* 400, 200, 300 */
   int32_t  maxRestarts;       /* cap on "repeat until converged" of the first minimisation */
+  int32_t  useMetricStart;    /* 0: random 4-D box (RDKit useRandomCoords = true, the reference's only mode, src/etkdg.cpp:
+                                 99-101). 1: RDKit's useRandomCoords = false start - random distance matrix inside the bounds ->
+                                 metric matrix -> top-4 eigenpairs (power iteration) -> coordinates, on the device, per attempt */
 } b200mol_embed_params;
 
 /* One conformer per slot: slot s embeds molecule d_slot_mol[s] into d_coords[d_slot_atom_start[s]*3 ...] (xyz fp64).
@@ -339,6 +343,13 @@ int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_etk_system* e
                         const b200mol_embed_params* params, int32_t nSlots, const int32_t* d_slot_mol,
                         const int32_t* d_slot_atom_start, int max_atoms, double* d_coords, int8_t* d_ok,
                         int32_t* d_attempts, double* d_energy, uint64_t* d_stage_failures, void* stream);
+/* Stage 0 alone: the 4-D start coordinates of attempt `attempt` of every slot, d_pos4[d_slot_atom_start[s]*4 ...];
+ * d_ok[s] = 0 when the metric-matrix start fails (degenerate metric matrix, eigensolver not converged, zero eigenvalue).
+ * Replaces ETKDGCoordGenStage (src/etkdg_stage_coordgen.cu:100-122, the random box) and adds the eigen start the
+ * reference leaves to RDKit (InitialCoordinateGenerator, src/forcefields/coord_gen.cu:133-216, is off the production path). */
+int b200mol_etkdg_initial_coords(const b200mol_dg_system* dg, const b200mol_embed_params* params, int32_t nSlots,
+                                 const int32_t* d_slot_mol, const int32_t* d_slot_atom_start, int max_atoms, int32_t attempt,
+                                 double* d_pos4, int8_t* d_ok, void* stream);
 /* The acceptance checks alone on given 4-D coordinates d_pos4[atom*4 ...]: bit s of d_fail_masks[slot] = stage s fails
  * (1 energy/atom, 2 tetrahedral, 3 chirality, 5 planarity, 6 double-bond geometry, 7 chirality, 8 chiral distances,
  * 9 centre-in-volume, 10 double-bond stereo). Replaces the kernels of src/etkdg_stage_stereochem_checks.cu:52-440. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "b200mol_poly_minimize": (C.c_int, [C.c_int32, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int,
                                         _vp, _vp, _vp, _vp]),
     "b200mol_etkdg_embed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_etkdg_initial_coords": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, C.c_int, C.c_int32, _vp, _vp, _vp]),
     "b200mol_etkdg_check": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "b200mol_triangle_smooth": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, _vp, _vp]),
     "b200mol_eig_topk": (C.c_int, [_vp, _vp, C.c_int32, C.c_int, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
@@ -120,7 +121,8 @@ def stats_read(reset: bool = True) -> dict:
     """Work counters of the conformer kernels on the current device (include/b200mol.h b200mol_stats_read)."""
     out = (C.c_uint64 * 16)()
     check(load().b200mol_stats_read(C.cast(out, C.c_void_p), 1 if reset else 0, None))
-    keys = ("bfgs_iterations", "energy_evals", "gradient_evals", "algorithmic_bytes", "minimisations", "etkdg_attempts")
+    keys = ("bfgs_iterations", "energy_evals", "gradient_evals", "algorithmic_bytes", "minimisations", "etkdg_attempts",
+            "n2_iterations")
     return {bank: {k: int(out[8 * b + i]) for i, k in enumerate(keys)} for b, bank in enumerate(("embed", "minimize"))}
 
 

@@ -123,7 +123,7 @@ struct BfgsWorkT {
   unsigned long long* stats;                        // device counters (kStat*), may be nullptr
 };
 // Work counters of the conformer kernels (b200mol_stats_read): what bench.py's roofline of this path is computed from.
-enum : int { kStatIters = 0, kStatEnergyEvals = 1, kStatGradEvals = 2, kStatAlgoBytes = 3, kStatMinimisations = 4, kStatAttempts = 5, kStatCount = 8 };
+enum : int { kStatIters = 0, kStatEnergyEvals = 1, kStatGradEvals = 2, kStatAlgoBytes = 3, kStatMinimisations = 4, kStatAttempts = 5, kStatN2Iters = 6, kStatCount = 8 };
 constexpr int kBfgsVectors = 6 + kWarps;
 constexpr int kColBuf      = 2 * kWarps * 64;  // doubles: 2 products x kWarps x 64 fp64 (= 128 fp32) columns of a chunk
 template <class HT>
@@ -517,6 +517,7 @@ __device__ BfgsOutcome bfgsMinimize(const typename FF::View& view, const BfgsWor
     atomicAdd(w.stats + kStatGradEvals, static_cast<unsigned long long>(nGrads));
     atomicAdd(w.stats + kStatAlgoBytes, 24ull * n * n * nIters + T * (nEvals + 1 + nGrads));
     atomicAdd(w.stats + kStatMinimisations, 1ull);
+    atomicAdd(w.stats + kStatN2Iters, static_cast<unsigned long long>(n) * n * nIters);
   }
   BfgsOutcome out;
   out.status = status;

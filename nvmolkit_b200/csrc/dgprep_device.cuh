@@ -25,7 +25,7 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {  // counter-based start
 
 // mat: n x n symmetric (destroyed by deflation); v, z: n doubles of shared memory; red: 16 doubles.
 // Returns (to all threads) the number of converged eigenpairs. eigvecs: [numEigs][n].
-__device__ int powerEigen(double* mat, int n, int numEigs, const double* v0, uint32_t seed, double* v, double* z,
+__device__ inline int powerEigen(double* mat, int n, int numEigs, const double* v0, uint32_t seed, double* v, double* z,
                           double* red, double* eigvals, double* eigvecs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = kEigT / 32;
   int       done = 0;

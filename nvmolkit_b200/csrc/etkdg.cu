@@ -5,6 +5,9 @@
 //
 // Stage list and constants = the reference's production pipeline (src/etkdg.cpp:325-394):
 //   0 coordinates: (u - 0.5) * boxSize in all four dimensions           (src/etkdg_stage_coordgen.cu:100-122; on the CPU there)
+//     or, useRandomCoords = 0 (the reference refuses it, src/etkdg.cpp:99-101): RDKit's metric-matrix
+//     start - a random distance matrix inside the bounds, its metric matrix, the top four eigenpairs by power iteration
+//     (the matrix lives in this CTA's inverse-Hessian slab, which is idle at that point), coordinates sqrt(lambda) v
 //   1 DG minimise  chiral 1.0 / 4th-dim 0.1, 400 iterations, repeated until converged; fail if E/atom >= 0.05
 //                                                                        (src/etkdg_stage_distgeom_minimize.cu:177-249, .h:34)
 //   2 tetrahedral check (volume >= 0.5, x0.25 in fused small rings; centre inside, tol 0.3)   (stereochem_checks.cu:52-168)
@@ -17,6 +20,7 @@
 // The reference launches each stage as separate kernels over a 500-conformer batch, generates coordinates on the CPU,
 // and lets a host Scheduler re-dispatch failures (src/etkdg_impl.cpp:111-159,286-312).
 #include "bfgs_device.cuh"
+#include "dgprep_device.cuh"
 #include "profile.cuh"
 
 namespace b200 {
@@ -66,6 +70,86 @@ __device__ __forceinline__ double uniform01(uint64_t seed, uint32_t slot, uint32
 }
 
 __device__ __forceinline__ V3 p3(const double* pos, int a) { return {pos[4 * a], pos[4 * a + 1], pos[4 * a + 2]}; }
+
+__device__ bool anyFail(bool mine);
+
+// Stage 0 of one attempt: 4-D start coordinates pos[4 * nA]. Returns false (block-uniform) when the metric-matrix start
+// fails (the attempt is then spent, like RDKit's embedPoints). Random streams are functions of (seed, slot, attempt,
+// element): elements [0, 4 nA) the box coordinates; 4 nA + i nA + j (i < j) the distance of pair (i, j);
+// 4 nA + nA^2 + e nA + i the start vector of eigenpair e; 8 nA + nA^2 + k nA + i the replacement coordinate of a
+// dimension with a negative eigenvalue.
+//   work: shared memory, >= 11 nA + 8 doubles.   mat: nA x nA doubles of global scratch (metric start only).
+// Metric start = RDKit DistGeom::pickRandomDistMat + computeInitialCoords (Code/DistGeom/DistGeomUtils.cpp of the
+// un-vendored RDKit 2025.03, restated: EIGVAL_TOL 1e-3, randNegEig = true, numZeroFail = 1) with the reference's power
+// eigensolver (src/symmetric_eigensolver.cu:62-247, dgprep_device.cuh).
+__device__ bool initialCoords(const b200mol_embed_params& par, const b200mol_dg_system& dg, int mol, int nA, int slot,
+                              int attempt, double* pos, double* work, double* mat, double* red) {
+  const int tid = threadIdx.x, n = 4 * nA;
+  if (!par.useMetricStart) {
+    for (int i = tid; i < n; i += kT) pos[i] = (uniform01(par.seed, slot, attempt, i) - 0.5) * par.boxSize;
+    __syncthreads();
+    return true;
+  }
+  double* v = work;                    // nA
+  double* z = v + nA;                  // nA
+  double* vecs = z + nA;               // 4 nA
+  double* v0 = vecs + 4 * nA;          // 4 nA
+  double* sq0 = v0 + 4 * nA;           // nA
+  double* vals = sq0 + nA;             // 4
+  const uint32_t base = static_cast<uint32_t>(n);
+  for (int e = tid; e < nA * nA; e += kT) mat[e] = 0.0;
+  __syncthreads();
+  // squared random distances inside the bounds (every pair is a DG distance term: basinThresh = 1e8)
+  for (int t = dg.dist.starts[mol] + tid; t < dg.dist.starts[mol + 1]; t += kT) {
+    int i = dg.dist.idx[2 * t], j = dg.dist.idx[2 * t + 1];
+    if (i > j) {
+      const int k = i;
+      i           = j;
+      j           = k;
+    }
+    const double lb = sqrt(dg.dist.par[3 * t]), ub = sqrt(dg.dist.par[3 * t + 1]);
+    const double d  = lb + uniform01(par.seed, slot, attempt, base + static_cast<uint32_t>(i * nA + j)) * (ub - lb);
+    mat[i * nA + j] = mat[j * nA + i] = d * d;
+  }
+  __syncthreads();
+  double tot = 0.0;
+  for (int i = tid; i < nA; i += kT) {
+    double s = 0.0;
+    for (int j = 0; j < nA; ++j) s += mat[i * nA + j];
+    sq0[i] = s;
+    tot += s;
+  }
+  const double sumSq = blockSum(tot, red) / (static_cast<double>(nA) * nA * 2.0);
+  bool         bad   = false;
+  for (int i = tid; i < nA; i += kT) {
+    sq0[i] = sq0[i] / nA - sumSq;
+    if (sq0[i] < 1.0e-3 && nA > 3) bad = true;
+  }
+  if (anyFail(bad)) return false;
+  for (int e = tid; e < nA * nA; e += kT) mat[e] = 0.5 * (sq0[e / nA] + sq0[e % nA] - mat[e]);
+  const int nEigs = nA < 4 ? nA : 4;
+  for (int e = tid; e < nEigs * nA; e += kT) v0[e] = uniform01(par.seed, slot, attempt, base + static_cast<uint32_t>(nA * nA + e));
+  __syncthreads();
+  const int done = powerEigen(mat, nA, nEigs, v0, 0u, v, z, red, vals, vecs);
+  if (done < nEigs) return false;
+  int zeroEigs = 0;
+  for (int k = 0; k < nEigs; ++k)  // (every thread evaluates the same four numbers)
+    if (fabs(vals[k]) < 1.0e-3) ++zeroEigs;
+  if (zeroEigs >= 1 && nA > 3) return false;
+  for (int e = tid; e < n; e += kT) {
+    const int i = e >> 2, k = e & 3;
+    double    x = 0.0;
+    if (k < nEigs) {
+      const double lam = vals[k];
+      if (lam > 1.0e-3) x = sqrt(lam) * vecs[k * nA + i];
+      else if (fabs(lam) < 1.0e-3) x = 0.0;
+      else x = 1.0 - 2.0 * uniform01(par.seed, slot, attempt, 2u * base + static_cast<uint32_t>(nA * nA + k * nA + i));
+    }
+    pos[e] = x;
+  }
+  __syncthreads();
+  return true;
+}
 
 __device__ __forceinline__ bool sameSide(double tol, const V3& v1, const V3& v2, const V3& v3, const V3& v4, const V3& p0) {
   const V3     c  = ff::cross(v2 - v1, v3 - v1);
@@ -261,11 +345,10 @@ __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
     double    eAccepted = 0.0;
     {
       int failedStage = -1;
-      // 0: random coordinates in a 4-D box
-      for (int i = tid; i < n; i += kT) w.pos[i] = (uniform01(a.par.seed, slot, attempt, i) - 0.5) * a.par.boxSize;
-      __syncthreads();
+      // 0: start coordinates (random box, or the metric-matrix start with the matrix in this CTA's idle Hessian slab)
+      if (!initialCoords(a.par, a.dg, mol, nA, slot, attempt, w.pos, sm + a.maxN, reinterpret_cast<double*>(w.H), red)) failedStage = 0;
       // 1: first minimisation
-      {
+      if (failedStage < 0) {
         const auto        v = ff::Dg<4>::view(a.dg, mol, {1.0, 0.1});
         const BfgsOutcome o = bfgsMinimize<ff::Dg<4>, float>(v, w, n, a.par.dgIters, a.par.optimizerForceTol, true, a.par.maxRestarts);
         eAccepted           = o.energy;
@@ -351,6 +434,22 @@ __global__ void __launch_bounds__(kT) etkdgCheckKernel(const EmbedArgs a, const 
   }
 }
 
+// Stage 0 alone (tests, and callers that want the start geometry): one CTA per slot.
+__global__ void __launch_bounds__(kT) initialCoordsKernel(const b200mol_dg_system dg, const b200mol_embed_params par, int nSlots,
+                                                        const int32_t* slotMol, const int32_t* slotAtomStart, int attempt,
+                                                        double* pos4, int8_t* ok, double* matWs, size_t matStride) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double                     red[kRed];
+  for (int slot = blockIdx.x; slot < nSlots; slot += gridDim.x) {
+    const int mol = slotMol[slot], nA = dg.atomCounts[mol];
+    __syncthreads();
+    const bool good = initialCoords(par, dg, mol, nA, slot, attempt, sm, sm + 4 * nA, matWs + blockIdx.x * matStride, red);
+    double*    out  = pos4 + static_cast<size_t>(slotAtomStart[slot]) * 4;
+    for (int i = threadIdx.x; i < 4 * nA; i += kT) out[i] = good ? sm[i] : 0.0;
+    if (threadIdx.x == 0) ok[slot] = good ? 1 : 0;
+  }
+}
+
 void validate(const b200mol_embed_params& p) {
   B200_REQUIRE(p.maxAttempts >= 1, "maxAttempts must be >= 1");
   B200_REQUIRE(p.boxSize > 0.0, "boxSize must be positive");
@@ -427,6 +526,33 @@ extern "C" int b200mol_etkdg_check(const b200mol_dg_system* dg, const b200mol_et
     EmbedArgs a{*dg, *etk, *checks, *params, nSlots, d_slot_mol, d_slot_atom_start, nullptr, nullptr, nullptr, nullptr,
                 nullptr, nullptr, 0, nullptr, 4 * max_atoms, nullptr, nullptr, nullptr, nullptr, nullptr};
     etkdgCheckKernel<<<blocks, kT, smem, asStream(stream)>>>(a, d_pos4, d_fail_masks);
+    B200_LAUNCHED();
+  });
+}
+
+extern "C" int b200mol_etkdg_initial_coords(const b200mol_dg_system* dg, const b200mol_embed_params* params, int32_t nSlots,
+                                            const int32_t* d_slot_mol, const int32_t* d_slot_atom_start, int max_atoms,
+                                            int32_t attempt, double* d_pos4, int8_t* d_ok, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(dg && params, "null system");
+    validate(*params);
+    if (nSlots <= 0) return;
+    B200_REQUIRE(d_slot_mol && d_slot_atom_start && d_pos4 && d_ok, "null pointer");
+    B200_REQUIRE(attempt >= 0, "negative attempt index");
+    cudaStream_t s    = asStream(stream);
+    const size_t smem = (static_cast<size_t>(15) * max_atoms + 8) * sizeof(double);
+    B200_REQUIRE(max_atoms > 0 && smem <= 200 * 1024, "molecule too large (%d atoms)", max_atoms);
+    static bool configured[kMaxDevices] = {};
+    if (!configured[currentDeviceSlot()]) {
+      B200_CUDA(cudaFuncSetAttribute(initialCoordsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured[currentDeviceSlot()] = true;
+    }
+    int blocks = smCount() * 2;
+    if (blocks > nSlots) blocks = nSlots;
+    const size_t    stride = static_cast<size_t>(max_atoms) * max_atoms;
+    Scratch<double> mats(params->useMetricStart ? stride * blocks : 0, s);
+    initialCoordsKernel<<<blocks, kT, smem, s>>>(*dg, *params, nSlots, d_slot_mol, d_slot_atom_start, attempt, d_pos4, d_ok,
+                                                  mats.get(), stride);
     B200_LAUNCHED();
   });
 }

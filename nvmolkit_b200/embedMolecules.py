@@ -28,7 +28,7 @@ class EmbedParamsC(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("boxSize", C.c_double), ("optimizerForceTol", C.c_double),
                 ("enforceChirality", C.c_int32), ("useExpTorsions", C.c_int32), ("useBasicKnowledge", C.c_int32),
                 ("maxAttempts", C.c_int32), ("dgIters", C.c_int32), ("fourthIters", C.c_int32), ("etkIters", C.c_int32),
-                ("maxRestarts", C.c_int32)]
+                ("maxRestarts", C.c_int32), ("useMetricStart", C.c_int32)]
 
 
 class EmbedParameters:
@@ -83,7 +83,8 @@ def _params_struct(params, max_attempts: int, seed_fallback: int = 0xB200) -> Em
                         enforceChirality=int(bool(params.enforceChirality)),
                         useExpTorsions=int(bool(params.useExpTorsionAnglePrefs)),
                         useBasicKnowledge=int(bool(params.useBasicKnowledge)), maxAttempts=int(max_attempts),
-                        dgIters=400, fourthIters=200, etkIters=300, maxRestarts=20)
+                        dgIters=400, fourthIters=200, etkIters=300, maxRestarts=20,
+                        useMetricStart=0 if bool(getattr(params, "useRandomCoords", True)) else 1)
 
 
 @dataclass
@@ -167,8 +168,7 @@ def EmbedMolecules(molecules, params, confsPerMolecule: int = 1, maxIterations: 
         for i, mol in enumerate(molecules):
             if mol is None:
                 raise ValueError(f"Molecule at index {i} is None")
-    if not params.useRandomCoords:
-        raise ValueError("ETKDG requires useRandomCoords=True in EmbedParameters")
+    # useRandomCoords=False (refused by the reference, src/etkdg.cpp:99-101) selects the on-device metric-matrix start
     if output == CoordinateOutput.DEVICE and float(getattr(params, "pruneRmsThresh", -1.0)) > 0:
         raise ValueError("DEVICE output is incompatible with pruneRmsThresh > 0")
     if hardwareOptions is None:

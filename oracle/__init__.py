@@ -296,7 +296,7 @@ class _EmbedParamsC(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("boxSize", C.c_double), ("optimizerForceTol", C.c_double),
                 ("enforceChirality", C.c_int32), ("useExpTorsions", C.c_int32), ("useBasicKnowledge", C.c_int32),
                 ("maxAttempts", C.c_int32), ("dgIters", C.c_int32), ("fourthIters", C.c_int32), ("etkIters", C.c_int32),
-                ("maxRestarts", C.c_int32)]
+                ("maxRestarts", C.c_int32), ("useMetricStart", C.c_int32)]
 
 
 def _checks_struct(tables: dict, num_impropers: np.ndarray):
@@ -387,6 +387,19 @@ def etkdg_embed(dg, etk, checks, num_impropers, params: dict, slot_mol):
         attempts.append(att.value)
         energies.append(en.value)
     return out, np.array(attempts), np.array(energies), fails
+
+
+def etkdg_initial_coords(dg, params: dict, slot: int, mol: int, attempt: int):
+    """Stage 0 of one attempt: (pos4 [nAtoms, 4], ok)."""
+    L = _ensure_ff()
+    d = _host_system("dg", np.ascontiguousarray(dg[0], dtype=np.int32), dg[1])
+    pr = _embed_params(params)
+    n = int(np.asarray(dg[0])[mol])
+    pos = np.zeros((n, 4))
+    L.oracle_etkdg_initial_coords.restype = C.c_int
+    L.oracle_etkdg_initial_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    ok = L.oracle_etkdg_initial_coords(C.addressof(d), C.addressof(pr), int(slot), int(mol), int(attempt), pos.ctypes.data)
+    return pos, bool(ok)
 
 
 def uniform01(seed: int, slot: int, attempt: int, element: int) -> float:

@@ -37,7 +37,11 @@ typedef struct {
   uint64_t seed;
   double   boxSize, optimizerForceTol;
   int32_t  enforceChirality, useExpTorsions, useBasicKnowledge, maxAttempts, dgIters, fourthIters, etkIters, maxRestarts;
+  int32_t  useMetricStart;
 } EmbedParams;
+
+void oracle_metric_matrix(const double* dist, int n, double* T);
+int  oracle_power_eigen(double* m, int n, int numEigs, const double* v0, double* eigvals, double* eigvecs);
 
 double oracle_dg_energy_grad(const DgSystem* s, int mol, int dim, double cw, double fw, const double* pos, double* grad);
 double oracle_etk_energy_grad_ref(const EtkSystem* s, int mol, const double* pos, double* grad, int plain, const double* ref);
@@ -214,6 +218,74 @@ unsigned oracle_etkdg_check(const DgSystem* dg, const EtkSystem* etk, const Chec
   return m;
 }
 
+/* Stage 0 of one attempt: 4-D start coordinates. Random box (src/etkdg_stage_coordgen.cu:100-122), or with useMetricStart
+ * RDKit's useRandomCoords = false start: DistGeom::pickRandomDistMat (d = lb + u (ub - lb)) and computeInitialCoords
+ * (Code/DistGeom/DistGeomUtils.cpp of the un-vendored RDKit, restated: sqD0i < 1e-3 fails when N > 3; eigenvalues > 1e-3
+ * -> sqrt, |.| < 1e-3 -> zero (one zero fails, numZeroFail = 1, when N > 3), negative -> random coordinate 1 - 2u
+ * (randNegEig)) on the reference's power eigensolver (oracle_dg.c). Same random-stream elements as csrc/etkdg.cu.
+ * Returns 1 on success. */
+int oracle_etkdg_initial_coords(const DgSystem* dg, const EmbedParams* p, int slot, int mol, int attempt, double* pos) {
+  const int nA = dg->atomCounts[mol], n = 4 * nA;
+  if (!p->useMetricStart) {
+    for (int i = 0; i < n; ++i) pos[i] = (oracle_uniform01(p->seed, slot, attempt, i) - 0.5) * p->boxSize;
+    return 1;
+  }
+  double* dist = (double*)calloc((size_t)nA * nA, sizeof(double));
+  double* T    = (double*)malloc(sizeof(double) * nA * nA);
+  for (int t = dg->dist.starts[mol]; t < dg->dist.starts[mol + 1]; ++t) {
+    int i = dg->dist.idx[2 * t], j = dg->dist.idx[2 * t + 1];
+    if (i > j) {
+      const int k = i;
+      i = j;
+      j = k;
+    }
+    const double lb = sqrt(dg->dist.par[3 * t]), ub = sqrt(dg->dist.par[3 * t + 1]);
+    const double d  = lb + oracle_uniform01(p->seed, slot, attempt, (uint32_t)(n + i * nA + j)) * (ub - lb);
+    dist[i * nA + j] = dist[j * nA + i] = d;
+  }
+  int ok = 1;
+  /* the degenerate-centre test of computeInitialCoords on the same sqD0i the metric matrix is built from */
+  double sumSq = 0.0;
+  for (int e = 0; e < nA * nA; ++e) sumSq += dist[e] * dist[e];
+  sumSq /= (double)nA * nA * 2.0;
+  for (int i = 0; i < nA && ok; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < nA; ++j) s += dist[i * nA + j] * dist[i * nA + j];
+    if (s / nA - sumSq < 1.0e-3 && nA > 3) ok = 0;
+  }
+  const int nEigs = nA < 4 ? nA : 4;
+  double    vals[4] = {0, 0, 0, 0};
+  double*   vecs = (double*)calloc((size_t)4 * nA, sizeof(double));
+  double*   v0   = (double*)malloc(sizeof(double) * 4 * nA);
+  if (ok) {
+    oracle_metric_matrix(dist, nA, T);
+    for (int e = 0; e < nEigs * nA; ++e) v0[e] = oracle_uniform01(p->seed, slot, attempt, (uint32_t)(n + nA * nA + e));
+    if (oracle_power_eigen(T, nA, nEigs, v0, vals, vecs) < nEigs) ok = 0;
+  }
+  if (ok) {
+    int zero = 0;
+    for (int k = 0; k < nEigs; ++k)
+      if (fabs(vals[k]) < 1.0e-3) ++zero;
+    if (zero >= 1 && nA > 3) ok = 0;
+  }
+  if (ok)
+    for (int i = 0; i < nA; ++i)
+      for (int k = 0; k < 4; ++k) {
+        double x = 0.0;
+        if (k < nEigs) {
+          if (vals[k] > 1.0e-3) x = sqrt(vals[k]) * vecs[k * nA + i];
+          else if (fabs(vals[k]) < 1.0e-3) x = 0.0;
+          else x = 1.0 - 2.0 * oracle_uniform01(p->seed, slot, attempt, (uint32_t)(2 * n + nA * nA + k * nA + i));
+        }
+        pos[4 * i + k] = x;
+      }
+  free(dist);
+  free(T);
+  free(vecs);
+  free(v0);
+  return ok;
+}
+
 /* One slot. coords3[nAtoms*3] written on success. Returns 1 on success; *attemptsOut attempts used; failStages[11]
  * (optional) incremented per failed attempt. */
 int oracle_etkdg_embed_one(const DgSystem* dg, const EtkSystem* etk, const Checks* ck, const EmbedParams* p, int slot,
@@ -225,9 +297,11 @@ int oracle_etkdg_embed_one(const DgSystem* dg, const EtkSystem* etk, const Check
   for (attempt = 0; attempt < p->maxAttempts && !ok; ++attempt) {
     int    failed = -1;
     double e = 0.0, e2 = 0.0;
-    for (int i = 0; i < n; ++i) pos[i] = (oracle_uniform01(p->seed, slot, attempt, i) - 0.5) * p->boxSize;
-    oracle_dg_minimize_one(dg, mol, 4, 1.0, 0.1, pos, p->dgIters, p->optimizerForceTol, p->maxRestarts, &e);
-    if (e / nA >= 0.05) failed = 1;
+    if (!oracle_etkdg_initial_coords(dg, p, slot, mol, attempt, pos)) failed = 0;
+    if (failed < 0) {
+      oracle_dg_minimize_one(dg, mol, 4, 1.0, 0.1, pos, p->dgIters, p->optimizerForceTol, p->maxRestarts, &e);
+      if (e / nA >= 0.05) failed = 1;
+    }
     if (failed < 0 && tetrahedral_fails(&ck->tetrahedral, mol, pos, 0.3, 1)) failed = 2;
     if (failed < 0 && p->enforceChirality && chirality_fails(&ck->chiral, mol, pos)) failed = 3;
     if (failed < 0) oracle_dg_minimize_one(dg, mol, 4, 0.2, 1.0, pos, p->fourthIters, p->optimizerForceTol, 0, &e2);

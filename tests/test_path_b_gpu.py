@@ -333,8 +333,74 @@ def test_etkdg_embed_produces_conformers_the_cpu_accepts(cuda):
     assert res.num_conformers == int(ok.sum()) and res.n_mols == 16
     per = EmbedMolecules(flat, params, confsPerMolecule=3, maxIterations=30)
     assert sum(len(c) for c in per) == int(ok.sum()) and len(per) == 16
-    with pytest.raises(ValueError):
-        EmbedMolecules(flat, EmbedParameters(useRandomCoords=False))
+
+
+def test_initial_coordinates_equal_cpu(cuda):
+    """Stage 0 alone: the random 4-D box is bit-identical to the CPU stream; the metric-matrix start (random distance matrix
+    inside the bounds -> metric matrix -> top-4 eigenpairs by power iteration) agrees with the CPU
+    restatement to the eigensolver's tolerance and fails on exactly the same attempts."""
+    from nvmolkit_b200 import _lib
+    from nvmolkit_b200.embedMolecules import EmbedParamsC
+
+    flat, mols = S.random_embed_molecules(10, 3, 20, seed=29)
+    dev = torch.device("cuda", 0)
+    dg, _a = flat.dg.to_device(dev)
+    slot_mol = np.repeat(np.arange(len(flat), dtype=np.int32), 3)
+    starts = np.concatenate([[0], np.cumsum(flat.atom_counts[slot_mol])]).astype(np.int32)
+    d_mol, d_st = torch.from_numpy(slot_mol).to(dev), torch.from_numpy(starts).to(dev)
+    for metric in (0, 1):
+        n_ok = 0
+        for attempt in (0, 5):
+            p = dict(PARAMS, useMetricStart=metric)
+            pc = EmbedParamsC(**p)
+            pos = torch.full((int(starts[-1]), 4), 7.0, dtype=torch.float64, device=dev)
+            ok = torch.zeros(len(slot_mol), dtype=torch.int8, device=dev)
+            _lib.call("b200mol_etkdg_initial_coords", C.byref(dg), C.byref(pc), len(slot_mol), d_mol.data_ptr(), d_st.data_ptr(),
+                      int(flat.atom_counts.max()), attempt, pos.data_ptr(), ok.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            pos, ok = pos.cpu().numpy(), ok.cpu().numpy().astype(bool)
+            for s_, m in enumerate(slot_mol):
+                want, ok_c = oracle.etkdg_initial_coords((flat.dg.atom_counts, flat.dg.tables), p, s_, int(m), attempt)
+                got = pos[starts[s_]:starts[s_ + 1]]
+                assert ok[s_] == ok_c, (metric, attempt, s_)
+                if not ok_c:
+                    continue
+                n_ok += 1
+                if metric == 0:
+                    assert np.array_equal(got, want)
+                else:
+                    assert np.allclose(got, want, atol=1e-6 * max(1.0, np.abs(want).max())), (s_, np.abs(got - want).max())
+        assert n_ok > 0
+
+
+def test_etkdg_embed_from_the_metric_matrix_start(cuda):
+    """useRandomCoords=False (refused by the reference, src/etkdg.cpp:99-101): every attempt starts from the on-device
+    eigen embedding of a random distance matrix; the accepted conformers pass the CPU's acceptance checks."""
+    from nvmolkit_b200.embedMolecules import EmbedMolecules, EmbedParameters, embed_slots
+
+    flat, mols = S.random_embed_molecules(12, 5, 14, seed=30)
+    params = EmbedParameters(randomSeed=77, useRandomCoords=False)
+    raw = embed_slots(flat, params, 2, max_iterations=40)
+    ok = raw.ok.cpu().numpy().astype(bool)
+    assert ok.mean() > 0.3
+    fails = raw.stage_failures.cpu().numpy()
+    coords = raw.coords.cpu().numpy()
+    for s_ in np.nonzero(ok)[0]:
+        xyz = coords[raw.slot_atom_start[s_]:raw.slot_atom_start[s_ + 1]]
+        p4 = np.concatenate([xyz, np.zeros((len(xyz), 1))], axis=1)
+        mask = oracle.etkdg_check((flat.dg.atom_counts, flat.dg.tables), (flat.etk.atom_counts, flat.etk.tables),
+                                  flat.checks.tables, flat.checks.num_impropers, PARAMS, int(raw.slot_mol[s_]), p4)
+        assert mask & 0b11111100000 == 0
+    raw2 = embed_slots(flat, params, 2, max_iterations=40)  # bit-reproducible like the random-box start
+    assert torch.equal(raw2.ok, raw.ok) and torch.equal(raw2.coords, raw.coords)
+    # the CPU pipeline with the same streams: same statistics
+    cpu_out, cpu_att, _e, cpu_fail = oracle.etkdg_embed((flat.dg.atom_counts, flat.dg.tables), (flat.etk.atom_counts, flat.etk.tables),
+                                                        flat.checks.tables, flat.checks.num_impropers,
+                                                        dict(PARAMS, seed=77, maxAttempts=40, useMetricStart=1), raw.slot_mol.tolist())
+    cpu_ok = np.array([o is not None for o in cpu_out])
+    assert abs(cpu_ok.mean() - ok.mean()) < 0.3
+    assert (fails[0] > 0) == (cpu_fail[0] > 0)  # stage-0 failures (degenerate metric matrices) occur on both or neither
+    per = EmbedMolecules(flat, params, confsPerMolecule=2, maxIterations=40)
+    assert sum(len(c) for c in per) == int(ok.sum())
 
 
 # ------------------------------------------------------------------ UFF
