@@ -10,11 +10,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-src = os.path.join(ROOT, "nvmolkit_b200", "csrc")
-out = "/tmp/libb200mol_timing.so"
-srcs = [os.path.join(src, f) for f in os.listdir(src) if f.endswith(".cu")]
-subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DB200_BFGS_TIMING", "-Xcompiler", "-fPIC",
-                "--expt-relaxed-constexpr", "-shared", "-o", out] + srcs + ["-lcudart_static"], check=True)
+out = os.path.join(ROOT, "nvmolkit_b200", "lib", "libb200mol_timing.so")
+subprocess.run(["make", "-C", os.path.join(ROOT, "nvmolkit_b200", "csrc"), "-j", "8", "-s", "timing"], check=True)
 from nvmolkit_b200 import _lib  # noqa: E402
 
 _lib.LIB_PATH = out
