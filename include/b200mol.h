@@ -46,7 +46,9 @@ int b200mol_free_async(void* d_ptr, void* stream);
  *                                  operands (kind::mxf4, fingerprints of a multiple of 256 bits); 0: the int8 tile
  *   "similarity_tensor_cluster"    1 (default): that tile runs in clusters of two CTAs sharing the column operand
  *                                  through TMA multicast; 2: CTA pairs with tcgen05 cta_group::2 MMAs (M = 256, each
- *                                  CTA stages half of the column operand); 0: one CTA per tile
+ *                                  CTA stages half of the column operand); 3: CTA pairs with the multicast column operand
+ *                                  and the ROW operand stationary in shared memory for a run of 16 tile columns
+ *                                  (fingerprints up to 2048 bits; half the L2 -> SM bytes per pair); 0: one CTA per tile
  *   "butina_min_round_commits"     a parallel Butina round that commits fewer clusters than this hands over to the
  *                                  one-cluster-per-step loop (default 32; 0 = rounds only, >= 1e9 = stepwise only)
  *   "bfgs_ctas_per_sm"             resident CTAs per SM of the minimiser / embedder kernels (default 3 = the register

@@ -55,6 +55,18 @@ class _EtkBuffersC(C.Structure):
                 for k in ("idx", "par")]
 
 
+def inversion_coefficients(z: int, c_bound_to_o: bool):
+    """(k / 3, C0, C1, C2) of an inversion centre of atomic number z - the formula of csrc/builders.cu
+    (dist_geom_flattened_builder.cpp:178-235; the UFF inversion shares it, uff_flattened_builder.cpp:454-530)."""
+    if z in (6, 7, 8):
+        return (50.0 if c_bound_to_o else 6.0) / 3.0, 1.0, -1.0, 0.0
+    w = np.pi / 180.0 * {15: 84.4339, 33: 86.9735, 51: 87.7047, 83: 90.0}.get(z, 1.0)
+    c2 = 1.0
+    c1 = -4.0 * np.cos(w)
+    c0 = -(c1 * np.cos(w) + c2 * np.cos(2.0 * w))
+    return 22.0 / (c0 + c1 + c2) / 3.0, c0, c1, c2
+
+
 def dg_terms_from_bounds(bounds: np.ndarray, chiral_atoms=None, chiral_bounds=None, dim: int = 4,
                          basin_size_tol: float = 1e8) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
     """DG tables {dist, chiral, fourth} of one molecule from its (smoothed) bounds matrix and chiral sets
@@ -119,3 +131,55 @@ def flat_embed_molecules(bounds_list: Sequence[np.ndarray], details_list: Sequen
     checks = checks_list if checks_list is not None else [{} for _ in counts]
     return FlatEmbedMolecules(FlatSystem.from_molecules("dg", counts, dgs), FlatSystem.from_molecules("etk", counts, etks),
                               CheckTables.from_molecules(counts, checks, nimp))
+
+
+@dataclass
+class StereoInfo:
+    """What the reference's ``findChiralSets`` / ``findDoubleBonds`` extract from a molecule
+    (``src/embedder_utils.cpp:117-206, 617-664``), as plain arrays: the structural input of the acceptance checks."""
+
+    chiral_centers: np.ndarray = field(default_factory=lambda: np.zeros((0, 5), np.int32))  # centre, n1..n4 (n4 = centre if 3-coord.)
+    chiral_bounds: np.ndarray = field(default_factory=lambda: np.zeros((0, 2)))  # volume lower, upper
+    tetrahedral: np.ndarray = field(default_factory=lambda: np.zeros((0, 5), np.int32))  # centre, n1..n4
+    tetrahedral_fused: np.ndarray = field(default_factory=lambda: np.zeros(0))  # 1 = in two or more small (< 5) rings
+    double_bond_ends: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int32))  # neighbour, atom, other end
+    stereo_double_bonds: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.int32))  # stereo atom, begin, end, stereo atom
+    stereo_signs: np.ndarray = field(default_factory=lambda: np.zeros(0))  # -1 cis / Z, +1 trans / E
+
+    def __post_init__(self):
+        self.chiral_centers = np.ascontiguousarray(self.chiral_centers, np.int32).reshape(-1, 5)
+        self.chiral_bounds = np.ascontiguousarray(self.chiral_bounds, np.float64).reshape(-1, 2)
+        self.tetrahedral = np.ascontiguousarray(self.tetrahedral, np.int32).reshape(-1, 5)
+        self.tetrahedral_fused = np.ascontiguousarray(self.tetrahedral_fused, np.float64).reshape(-1)
+        self.double_bond_ends = np.ascontiguousarray(self.double_bond_ends, np.int32).reshape(-1, 3)
+        self.stereo_double_bonds = np.ascontiguousarray(self.stereo_double_bonds, np.int32).reshape(-1, 4)
+        self.stereo_signs = np.ascontiguousarray(self.stereo_signs, np.float64).reshape(-1)
+
+    def dg_chiral_terms(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(atoms [n,4], bounds [n,2] lower/upper) of the DG chiral-volume terms: the four neighbours of every chiral set
+        (RDKit ChiralSet d_idx1..4; dist_geom_flattened_builder.cpp:88-109)."""
+        return self.chiral_centers[:, 1:5], self.chiral_bounds
+
+
+def check_tables(bounds: np.ndarray, stereo: StereoInfo) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
+    """Acceptance-check tables of one molecule (layout ``forcefield.CHECK_LAYOUT`` / b200mol_etkdg_checks):
+    tetrahedral and chiral sets as they are; the chiral distance-matrix check over every pair of atoms that belong to a
+    four-coordinate chiral set, with that pair's bounds (ETKDGChiralDistMatrixCheckStage::loadDataset,
+    src/etkdg_stage_stereochem_checks.cu:614-655); double-bond geometry triples and stereo quadruples."""
+    b = np.asarray(bounds, np.float64)
+    atoms = sorted({int(a) for row in stereo.chiral_centers if row[0] != row[4] for a in row})
+    pairs = [(atoms[j], atoms[k]) for j in range(len(atoms)) for k in range(j + 1, len(atoms))]
+    cd_par = [[b[max(i, j), min(i, j)], b[min(i, j), max(i, j)]] for i, j in pairs]
+    return {"tetrahedral": (stereo.tetrahedral.astype(np.int16), stereo.tetrahedral_fused.reshape(-1, 1)),
+            "chiral": (stereo.chiral_centers.astype(np.int16), stereo.chiral_bounds),
+            "chiralDist": (np.array(pairs, np.int16).reshape(-1, 2), np.array(cd_par, np.float64).reshape(-1, 2)),
+            "dbStereo": (stereo.stereo_double_bonds.astype(np.int16), stereo.stereo_signs.reshape(-1, 1)),
+            "dbGeom": (stereo.double_bond_ends.astype(np.int16), np.zeros((len(stereo.double_bond_ends), 0)))}
+
+
+def flat_embed_from_parts(bounds_list, details_list, stereo_list, use_basic_knowledge: bool = True):
+    """FlatEmbedMolecules from per-molecule (smoothed bounds, CrystalFFDetails, StereoInfo): what prepareEmbedderArgs
+    leaves behind after RDKit's own calls (``src/embedder_utils.cpp:671-708``), flattened for the embedding kernel."""
+    chiral = [s.dg_chiral_terms() for s in stereo_list]
+    checks = [check_tables(b, s) for b, s in zip(bounds_list, stereo_list)]
+    return flat_embed_molecules(bounds_list, details_list, chiral, checks, use_basic_knowledge)

@@ -115,6 +115,7 @@ __device__ inline int powerEigen(double* mat, int n, int numEigs, const double* 
     if (tid == 0) eigvals[e] = eig;
     __syncthreads();
     for (int idx = tid; idx < n * n; idx += kEigT) mat[idx] -= eig * v[idx / n] * v[idx % n];
+    __syncthreads();  // the next eigenpair's start vector overwrites v: every thread must be done deflating with it
     ++done;
   }
   __syncthreads();

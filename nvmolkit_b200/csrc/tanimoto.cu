@@ -414,7 +414,7 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
     }
     else if (k == "similarity_tensor_fp4") g_tensorFp4 = value != 0;
     else if (k == "similarity_tensor_cluster") {
-      B200_REQUIRE(value >= 0 && value <= 2, "similarity_tensor_cluster must be 0, 1 or 2");
+      B200_REQUIRE(value >= 0 && value <= 3, "similarity_tensor_cluster must be 0, 1, 2 or 3");
       g_tensorCluster = static_cast<int>(value);
     }
     else if (k == "butina_min_round_commits") {

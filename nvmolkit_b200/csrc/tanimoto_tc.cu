@@ -38,6 +38,10 @@ constexpr int kABytes   = kTM * kTK;
 constexpr int kBBytes   = kTN * kTK;
 constexpr int kTNFp4    = 224;  // fp4 count mode: 2 x 224 accumulator columns leave TMEM columns 448..511 for the scale factors
 constexpr int kGroupTC  = 16;  // tile rows per L2 reuse group
+constexpr int kGroupStat = 64;  // the same for the A-stationary tile: 32 CTA pairs stream one column chunk together
+constexpr int kRunStat   = 16;  // tile columns per unit of the A-stationary tile (the row operand is loaded once per unit)
+constexpr int kStagesStat = 3;  // its ring holds the column operand only (28 KB per stage, next to 128 KB of row operand)
+constexpr int kMaxChunksStat = 8;  // row operand resident in shared memory: 8 K-chunks x 16 KB (fingerprints <= 2048 bits)
 
 struct TcParams {
   uint32_t        n;  // X == Y (symmetric) or nX/nY
@@ -210,9 +214,13 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
 // cycles mirrored), which balances the triangle's shrinking rows across ranks to < 0.1 %.
 // A CTA walks units first, first + step, ... of the concatenated owned groups; (cycle, index in group) are kept
 // incrementally, the only divisions are by compile-time constants and happen once per group.
-template <int TN, bool PAIR>
+// RUN > 1 (the A-stationary tile, CL = 3): a unit is a RUN of consecutive tile columns of one unit row - the row
+// operand is loaded once per unit and stays in shared memory - and the units of a group go chunk-major (all rows of the
+// group take column chunk q, then q + 1): the CTA pairs of a group stream the same column tiles at about the same time,
+// so a column tile comes from HBM once per group and from L2 for the other rows.
+template <int TN, bool PAIR, int RUN = 1, int GROUPTC = kGroupTC>
 struct UnitWalk {
-  static constexpr uint32_t G = PAIR ? kGroupTC / 2 : kGroupTC;
+  static constexpr uint32_t G = PAIR ? GROUPTC / 2 : GROUPTC;
   uint32_t cycle, inGroup, units, gRows, tn0, group, step;
   bool     done;
   __device__ UnitWalk(const TcParams& p, uint32_t first, uint32_t stepBy) : cycle(0), inGroup(first), units(0), gRows(G), tn0(0), group(0), step(stepBy), done(false) {
@@ -229,10 +237,10 @@ struct UnitWalk {
       units = 0;
       if (group * G < unitRows) {
         gRows = min(G, unitRows - group * G);
-        // first tile column holding a pair with row < col for the group's top tile row tm0 = group * kGroupTC:
+        // first tile column holding a pair with row < col for the group's top tile row tm0 = group * GROUPTC:
         // (tn + 1) * TN - 1 > tm0 * kTM
-        tn0   = p.symmetric ? (group * static_cast<uint32_t>(kGroupTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
-        if (tn0 < p.tilesN) units = gRows * (p.tilesN - tn0);
+        tn0   = p.symmetric ? (group * static_cast<uint32_t>(GROUPTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
+        if (tn0 < p.tilesN) units = gRows * ((p.tilesN - tn0 + RUN - 1) / RUN);
       }
       if (inGroup < units) return;
       inGroup -= units;
@@ -247,8 +255,8 @@ struct UnitWalk {
       settle(p);
     }
   }
-  // tile of this unit for CTA `rank` of the pair (0 when unpaired); false = nothing to do (below the diagonal)
-  __device__ bool coords(const TcParams& p, uint32_t rank, uint32_t& tm, uint32_t& tn) const {
+  // tiles [tnBeg, tnEnd) of tile row tm for CTA `rank` of the pair (0 when unpaired); false = nothing to do
+  __device__ bool coords(const TcParams& p, uint32_t rank, uint32_t& tm, uint32_t& tnBeg, uint32_t& tnEnd) const {
     uint32_t row, col;
     if (gRows == G) {
       row = inGroup % G;  // G is a power of two
@@ -257,35 +265,43 @@ struct UnitWalk {
       row = inGroup % gRows;
       col = inGroup / gRows;
     }
-    tn                = tn0 + col;
-    const uint32_t tr = group * G + row;  // unit row
+    tnBeg              = tn0 + col * RUN;
+    tnEnd              = min(p.tilesN, tnBeg + RUN);
+    const uint32_t tr  = group * G + row;  // unit row
     const uint32_t top = PAIR ? 2 * tr : tr;
     // the upper tile decides for both CTAs of a pair (if it has no pair with row < col, neither has the lower one); a
-    // lower tile past the end or below the diagonal still runs - its loads are zero-filled / its predicates reject all
-    if (p.symmetric && (tn * TN + TN - 1) <= top * kTM) return false;
+    // lower tile past the end or below the diagonal still runs - its loads are zero-filled / its predicates reject all.
+    // A tile column is useful iff (tn + 1) * TN - 1 > top * kTM: monotone in tn, so a run is clipped from the left.
+    if (p.symmetric) tnBeg = max(tnBeg, (top * static_cast<uint32_t>(kTM) + 1u) / static_cast<uint32_t>(TN));
+    if (tnBeg >= tnEnd) return false;
     tm = top + (PAIR ? rank : 0u);
     return true;
   }
 };
 
 // host twin of the walk's unit count (sizes the grid)
-template <int TN, bool PAIR>
+template <int TN, bool PAIR, int RUN = 1, int GROUPTC = kGroupTC>
 uint64_t countUnits(const TcParams& p) {
-  constexpr uint32_t G = PAIR ? kGroupTC / 2 : kGroupTC;
+  constexpr uint32_t G = PAIR ? GROUPTC / 2 : GROUPTC;
   const uint32_t     unitRows = PAIR ? (p.tilesM + 1) / 2 : p.tilesM;
   uint64_t           total = 0;
   for (uint32_t cycle = 0; cycle * p.groupStride * G < unitRows; ++cycle) {
     const uint32_t group = cycle * p.groupStride + ((cycle & 1u) ? p.groupStride - 1 - p.groupOffset : p.groupOffset);
     if (group * G >= unitRows) continue;
     const uint32_t gRows = std::min(G, unitRows - group * G);
-    const uint32_t tn0   = p.symmetric ? (group * static_cast<uint32_t>(kGroupTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
-    if (tn0 < p.tilesN) total += static_cast<uint64_t>(gRows) * (p.tilesN - tn0);
+    const uint32_t tn0   = p.symmetric ? (group * static_cast<uint32_t>(GROUPTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
+    if (tn0 < p.tilesN) total += static_cast<uint64_t>(gRows) * ((p.tilesN - tn0 + RUN - 1) / RUN);
   }
   return total;
 }
 
 // CL: 0 = one CTA per tile; 1 = CTA pair, column operand multicast; 2 = CTA pair with cta_group::2 MMAs (each CTA stages
-// half of the column operand, the leader issues M = 256 instructions for both)
+// half of the column operand, the leader issues M = 256 instructions for both); 3 = CTA pair, column operand multicast,
+// ROW OPERAND STATIONARY: a unit is a run of kRunStat tile columns of one tile row, the row tile's K chunks (128 KB)
+// are loaded once per unit into their own shared-memory region and only the column operand streams through the ring.
+// Per pair that is 4.3 B from L2 instead of 8.6 (the pass was bound by L2 -> SM delivery at 9.6 TB/s and by 3.7 TB/s of
+// HBM re-reads, profiles/r02_path_a_summary.md); the K chunks of the next unit's row tile are requested as soon as the
+// last tile of the current unit has consumed them, so the reload hides behind that tile's remaining MMAs.
 template <int MODE, bool FP4, int CL>
 __global__ void __launch_bounds__(threadsTC(MODE), 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -297,19 +313,23 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   static_assert(!CL || FP4, "the two-CTA cluster is wired for the fp4 count tile");
   const uint32_t rank      = CL ? clusterCtaRank() : 0u;
   const uint32_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
-  using Walk               = UnitWalk<TN, CL != 0>;
   constexpr bool P2          = CL == 2;
+  constexpr bool ST          = CL == 3;  // row operand stationary
+  using Walk                 = UnitWalk<TN, CL != 0, ST ? kRunStat : 1, ST ? kGroupStat : kGroupTC>;
   constexpr int  kBStage     = P2 ? kBBytes / 2 : kBBytes;  // bytes of the column operand one CTA stages per K chunk
-  constexpr int  kStageBytes = kABytes + kBStage;
-  constexpr int  kStagesTC   = P2 ? kStagesPair : (MODE == kTcCount ? kStagesCount : kStagesMat);
+  constexpr int  kStageBytes = ST ? kBStage : kABytes + kBStage;
+  constexpr int  kStagesTC   = ST ? kStagesStat : (P2 ? kStagesPair : (MODE == kTcCount ? kStagesCount : kStagesMat));
+  constexpr int  kAResident  = ST ? kMaxChunksStat * kABytes : 0;  // the stationary row tile, ahead of the ring
   __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
+  __shared__ uint64_t aFull[ST ? kMaxChunksStat : 1], aEmpty[ST ? kMaxChunksStat : 1];
   __shared__ uint32_t tmemBase;
   __shared__ int      popB[2][kTN];
   __shared__ int      popA[2][kTM];
   __shared__ int      colAcc[2][kTN];
   __shared__ int      popBMin[2][kEpiWarps];
 
-  const uint32_t smemBase = (smemAddr(smemRaw) + 1023u) & ~1023u;
+  const uint32_t smemA    = (smemAddr(smemRaw) + 1023u) & ~1023u;  // (stationary tile: the row operand's K chunks)
+  const uint32_t smemBase = smemA + kAResident;                    // the ring
   uint8_t*       smemGen  = smemRaw + (smemBase - smemAddr(smemRaw));
   uint16_t*      threshS  = reinterpret_cast<uint16_t*>(smemGen + kStagesTC * kStageBytes);
 
@@ -320,8 +340,13 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     tmaPrefetchDesc(&tmB);
     for (int s = 0; s < kStagesTC; ++s) {
       mbarInit(&fullBar[s], 1);
-      mbarInit(&emptyBar[s], CL == 1 ? 2 : 1);  // multicast pair: the MMAs of both CTAs read what the pair's producers overwrite
+      mbarInit(&emptyBar[s], (CL == 1 || ST) ? 2 : 1);  // multicast pair: the MMAs of both CTAs read what the pair's producers overwrite
     }
+    if constexpr (ST)
+      for (int s = 0; s < kMaxChunksStat; ++s) {
+        mbarInit(&aFull[s], 1);
+        mbarInit(&aEmpty[s], 1);
+      }
     for (int s = 0; s < 2; ++s) {
       mbarInit(&tmemFull[s], 1);
       mbarInit(&tmemEmpty[s], P2 ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (pair MMA: of both CTAs, at the leader)
@@ -337,8 +362,12 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
   }
-  for (int i = threadIdx.x; i < 2 * p.threshLen; i += kThreadsTC) threshS[i] = p.thresh[i];  // table | its suffix-min
-  const uint16_t* threshLoS = threshS + p.threshLen;
+  if constexpr (!ST)
+    for (int i = threadIdx.x; i < 2 * p.threshLen; i += kThreadsTC) threshS[i] = p.thresh[i];  // table | its suffix-min
+  // (stationary tile: shared memory is full of operands; the tables are read through L1 - once per row and tile plus once
+  // per surviving pair)
+  const uint16_t* threshT   = ST ? p.thresh : threshS;
+  const uint16_t* threshLoS = threshT + p.threshLen;
   double* recipS = reinterpret_cast<double*>(threshS);  // materialise Tanimoto: RN(1/u), u = |A u B| <= 2 * bits
   if constexpr (MODE == kTcTanimoto) {
     for (int u = threadIdx.x; u <= p.recipLen; u += kThreadsTC) recipS[u] = u ? __drcp_rn(static_cast<double>(u)) : 0.0;
@@ -365,10 +394,19 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     if (lane == 0) {
       int      stage = 0;
       uint32_t phase = 0;
+      uint32_t aPhase = 0;
       for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
-        uint32_t tm, tn;
-        if (!w.coords(p, rank, tm, tn)) continue;
+        uint32_t tm, tnBeg, tnEnd;
+        if (!w.coords(p, rank, tm, tnBeg, tnEnd)) continue;
+        for (uint32_t tn = tnBeg; tn < tnEnd; ++tn) {
         for (int kc = 0; kc < p.kChunks; ++kc) {
+          if constexpr (ST) {
+            if (tn == tnBeg) {  // this unit's row tile, chunk kc: as soon as the previous unit's last tile is done with it
+              mbarWait(&aEmpty[kc], aPhase ^ 1);
+              mbarExpectTx(&aFull[kc], kABytes);
+              tmaLoad2D(smemRaw + (smemA - smemAddr(smemRaw)) + kc * kABytes, &tmA, kc * kTK, tm * kTM, &aFull[kc]);
+            }
+          }
           mbarWait(&emptyBar[stage], phase ^ 1);
           uint8_t* dst = smemGen + stage * kStageBytes;
           if constexpr (P2) {
@@ -378,6 +416,11 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
             if (rank == 0) mbarExpectTx(&fullBar[stage], 2 * kStageBytes);
             tmaLoad2DPair(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
             tmaLoad2DPair(dst + kABytes, &tmB, kc * kTK, tn * TN + rank * kHalfRows, &fullBar[stage]);
+          } else if constexpr (ST) {
+            constexpr int kHalfRows = TN / 2;
+            mbarExpectTx(&fullBar[stage], kBBytes);
+            tmaLoad2DMulticast(dst + rank * (kHalfRows * kTK), &tmB, kc * kTK, tn * TN + rank * kHalfRows, &fullBar[stage],
+                               static_cast<uint16_t>(3));
           } else {
             mbarExpectTx(&fullBar[stage], kABytes + kBBytes);
             tmaLoad2D(dst, &tmA, kc * kTK, tm * kTM, &fullBar[stage]);
@@ -395,6 +438,8 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
             phase ^= 1;
           }
         }
+        }
+        aPhase ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -402,18 +447,23 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     if (lane == 0 && !(P2 && rank != 0)) {  // (pair MMA: the leader issues for both CTAs)
       int      stage = 0;
       uint32_t phase = 0, local = 0;
+      uint32_t aPhase = 0;
       for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
-        uint32_t tm, tn;
-        if (!w.coords(p, rank, tm, tn)) continue;
+        uint32_t tm, tnBeg, tnEnd;
+        if (!w.coords(p, rank, tm, tnBeg, tnEnd)) continue;
+        for (uint32_t tn = tnBeg; tn < tnEnd; ++tn) {
         const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
         mbarWait(&tmemEmpty[as], accPhase ^ 1);
         tcFenceAfter();
         const uint32_t dAddr = tmem + as * TN;
         for (int kc = 0; kc < p.kChunks; ++kc) {
+          if constexpr (ST) {
+            if (tn == tnBeg) mbarWait(&aFull[kc], aPhase);
+          }
           mbarWait(&fullBar[stage], phase);
           tcFenceAfter();
-          const uint32_t aAddr = smemBase + stage * kStageBytes;
-          const uint64_t aDesc = makeSmemDesc(aAddr), bDesc = makeSmemDesc(aAddr + kABytes);
+          const uint32_t sAddr = smemBase + stage * kStageBytes;
+          const uint64_t aDesc = makeSmemDesc(ST ? smemA + kc * kABytes : sAddr), bDesc = makeSmemDesc(ST ? sAddr : sAddr + kABytes);
 #pragma unroll
           for (int k = 0; k < kTK / 32; ++k)  // K = 32 bytes per instruction: +32 B = +2 in the 16-byte address field
           {
@@ -422,8 +472,11 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
             else ummaI8(dAddr, aDesc + 2 * k, bDesc + 2 * k, (kc | k) != 0 ? 1u : 0u);
           }
           if constexpr (P2) ummaCommitPairMulticast(&emptyBar[stage], static_cast<uint16_t>(3));
-          else if constexpr (CL == 1) ummaCommitMulticast(&emptyBar[stage], static_cast<uint16_t>(3));
+          else if constexpr (CL == 1 || ST) ummaCommitMulticast(&emptyBar[stage], static_cast<uint16_t>(3));
           else ummaCommit(&emptyBar[stage]);  // frees the smem stage when these MMAs retire
+          if constexpr (ST) {
+            if (tn + 1 == tnEnd) ummaCommit(&aEmpty[kc]);  // the unit's last tile: the row tile's chunk may be replaced
+          }
           if (++stage == kStagesTC) {
             stage = 0;
             phase ^= 1;
@@ -432,6 +485,8 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         if constexpr (P2) ummaCommitPairMulticast(&tmemFull[as], static_cast<uint16_t>(3));  // both CTAs' epilogues
         else ummaCommit(&tmemFull[as]);
         ++local;
+        }
+        aPhase ^= 1;
       }
     }
   } else {
@@ -443,8 +498,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     uint32_t       local   = 0;
     uint32_t       tnOf[2] = {0, 0};  // tile column each accumulator-side buffer last served
     for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
-      uint32_t tm, tn;
-      if (!w.coords(p, rank, tm, tn)) continue;
+      uint32_t tm, tnBeg, tnEnd;
+      if (!w.coords(p, rank, tm, tnBeg, tnEnd)) continue;
+      for (uint32_t tn = tnBeg; tn < tnEnd; ++tn) {
       const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
       // stage this tile's column popcounts
       int minPb = 0x3fffffff;  // smallest |B| among this tile's valid columns (pre-filter of the threshold test)
@@ -559,7 +615,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
 #pragma unroll
             for (int q = 0; q < 32; ++q)
               if (q == j) cij = FP4 ? __float2int_rn(__uint_as_float(r[q])) : static_cast<int>(r[q]);
-            if (cij >= threshS[pa + popB[as][cb * 32 + j]]) mask |= 1u << j;
+            if (cij >= threshT[pa + popB[as][cb * 32 + j]]) mask |= 1u << j;
           }
         }
         const unsigned any = __ballot_sync(0xffffffffu, mask != 0);
@@ -603,6 +659,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       }
       if (MODE == kTcCount && rowHits) atomicAdd(p.counts + gr, p.sign * rowHits);
       ++local;
+      }
     }
     if (MODE == kTcCount && p.countsY) {  // the last two tiles' column counts
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -695,26 +752,32 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
 
   CUtensorMap tmA, tmB;
   makeTensorMap2D(&tmA, expX.get(), q.nX, rowBytes, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
-  const bool cluster = fp4 && g_tensorCluster != 0;  // CTA pairs: 1 = multicast column operand, 2 = cta_group::2 MMAs
-  const bool pairMma = cluster && g_tensorCluster == 2;
+  const bool cluster = fp4 && g_tensorCluster != 0;  // CTA pairs: 1 = multicast column operand, 2 = cta_group::2 MMAs,
+  const bool pairMma = cluster && g_tensorCluster == 2;  // 3 = multicast column operand + stationary row operand
+  const bool stationary = cluster && g_tensorCluster == 3 && p.kChunks <= kMaxChunksStat;
   makeTensorMap2D(&tmB, expY, q.nY, rowBytes, cluster ? tn / 2 : tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
-  const size_t smemBytes = (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
-                                    : static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK)) +
-                           (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
+  const size_t smemBytes =
+    stationary ? static_cast<size_t>(kMaxChunksStat) * kABytes + static_cast<size_t>(kStagesStat) * tn * kTK + 1024 + 64
+               : (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
+                          : static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK)) +
+                   (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
   static bool configured[kMaxDevices] = {};
   if (!configured[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
     configured[currentDeviceSlot()] = true;
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
   // units this call owns: tiles, or vertical tile pairs (same enumeration as the kernel's UnitWalk)
-  const uint64_t total = cluster ? countUnits<kTNFp4, true>(p) : (fp4 ? countUnits<kTNFp4, false>(p) : countUnits<kTN, false>(p));
+  const uint64_t total = stationary ? countUnits<kTNFp4, true, kRunStat, kGroupStat>(p)
+                         : cluster  ? countUnits<kTNFp4, true>(p)
+                                    : (fp4 ? countUnits<kTNFp4, false>(p) : countUnits<kTN, false>(p));
   if (total == 0) return true;  // nothing owned by this rank (more ranks than row groups)
   int            blocks  = smCount();
   if (static_cast<uint64_t>(blocks) > total) blocks = static_cast<int>(total);
@@ -734,13 +797,15 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
       cfg.numAttrs         = 1;
       cfg.gridDim          = dim3(2);
       int maxClusters = 0;
-      if (pairMma) B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, 2>, &cfg));
+      if (stationary) B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, 3>, &cfg));
+      else if (pairMma) B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, 2>, &cfg));
       else B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, 1>, &cfg));
       B200_REQUIRE(maxClusters >= 1, "no CTA pair fits the device");
       uint64_t pairs = maxClusters;  // persistent: one resident cluster per schedulable SM pair
       if (pairs > total) pairs = total;
       cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-      if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, p));
+      if (stationary) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 3>, tmA, tmB, p));
+      else if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, p));
       else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, p));
     } else if (fp4) simTensorKernel<kTcCount, true, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p);
     else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p);

@@ -281,11 +281,11 @@ def test_butina_parallel_rounds_keep_the_greedy_order(cuda, min_commits, n, degr
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05 int8) path of the count pass
-@pytest.fixture(params=[1, 0, 2], ids=["multicast_pair", "single_cta", "pair_mma"])
+@pytest.fixture(params=[1, 0, 2, 3], ids=["multicast_pair", "single_cta", "pair_mma", "row_stationary"])
 def force_tensor_path(cuda, request):
-    """Every test that takes this fixture runs on all three tile variants of the fp4 count pass:
-    similarity_tensor_cluster = 1 (CTA pair, multicast column operand; the default), 0 (one CTA per tile),
-    2 (CTA pair with tcgen05 cta_group::2 MMAs)."""
+    """Every test that takes this fixture runs on all four tile variants of the fp4 count pass:
+    similarity_tensor_cluster = 1 (CTA pair, multicast column operand), 0 (one CTA per tile),
+    2 (CTA pair with tcgen05 cta_group::2 MMAs), 3 (CTA pair, multicast column operand, row operand stationary)."""
     from nvmolkit_b200 import _lib
 
     _lib.set_option("similarity_tensor_min_pairs", 0)
@@ -318,6 +318,17 @@ def test_tensor_fused_butina_equals_rdkit_definition(cuda, force_tensor_path, ce
     fp = S.clustered_fingerprints(centres, members, seed=centres * 100 + members)
     ids, cen = fused_butina_device(_dev(fp, cuda), cutoff)
     ids_cpu, cen_cpu = oracle.butina_fp(fp, cutoff)
+    assert (ids.cpu().numpy() == ids_cpu).all() and (cen.cpu().numpy() == cen_cpu).all()
+
+
+def test_tensor_neighbor_counts_on_a_many_tile_problem(cuda, force_tensor_path):
+    """9,000 points = 71 tile rows x 41 tile columns: several row groups and, for the row-stationary tile, several runs of
+    16 tile columns per row with a row-operand reload between them."""
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    fp = S.clustered_fingerprints(180, 50, seed=99)
+    ids, cen = fused_butina_device(_dev(fp, cuda), 0.3)
+    ids_cpu, cen_cpu = oracle.butina_fp(fp, 0.3)
     assert (ids.cpu().numpy() == ids_cpu).all() and (cen.cpu().numpy() == cen_cpu).all()
 
 
@@ -383,7 +394,7 @@ def _sharded_butina_one_gpu(fp, cutoff, world, cuda):
     return ids.cpu().numpy(), cen[:k].cpu().numpy(), all_edges.cpu().numpy(), deg.cpu().numpy(), per_rank
 
 
-@pytest.mark.parametrize("tensor", [False, True], ids=["simt_tile", "tensor_tile"])
+@pytest.mark.parametrize("tensor", [0, 1, 3], ids=["simt_tile", "tensor_tile", "tensor_row_stationary"])
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("centres,members", [(30, 20), (130, 50)])  # 600 and 6500 points: 5 and 51 tile rows
 def test_sharded_neighbor_pass_equals_oracle(cuda, world, centres, members, tensor):
@@ -393,10 +404,12 @@ def test_sharded_neighbor_pass_equals_oracle(cuda, world, centres, members, tens
 
     fp = S.clustered_fingerprints(centres, members, seed=centres + world)
     _lib.set_option("similarity_tensor_min_pairs", 0 if tensor else -1)
+    _lib.set_option("similarity_tensor_cluster", tensor if tensor else 1)
     try:
         ids, cen, edges, deg, per_rank = _sharded_butina_one_gpu(fp, 0.3, world, cuda)
     finally:
         _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
+        _lib.set_option("similarity_tensor_cluster", 1)
     ids_cpu, cen_cpu = oracle.butina_fp(fp, 0.3)
     want_deg = oracle.count_ge(fp, fp, 0.3) - 1  # neighbours other than the point itself
     assert (deg == want_deg).all()
@@ -404,6 +417,6 @@ def test_sharded_neighbor_pass_equals_oracle(cuda, world, centres, members, tens
     key = edges[:, 0].astype(np.int64) * len(fp) + edges[:, 1]
     assert len(np.unique(key)) == len(key) == int(want_deg.sum()) // 2  # every neighbour pair exactly once
     assert (ids == ids_cpu).all() and (cen == cen_cpu).all()
-    rows_per_group = 128 * (16 if tensor else 32)  # tile-row group of the tensor tile | of the SIMT tile
+    rows_per_group = 128 * {0: 32, 1: 16, 3: 64}[tensor]  # tile-row group of the SIMT tile | tensor tile | stationary tile
     if -(-len(fp) // rows_per_group) >= world and centres * members >= 1000:  # every rank owns a group -> finds edges
         assert all(c > 0 for c in per_rank), per_rank

@@ -368,7 +368,9 @@ def test_initial_coordinates_equal_cpu(cuda):
                 if metric == 0:
                     assert np.array_equal(got, want)
                 else:
-                    assert np.allclose(got, want, atol=1e-6 * max(1.0, np.abs(want).max())), (s_, np.abs(got - want).max())
+                    # (the power iteration stops when the eigenvalue estimate moves by < 1e-3, so the two sides agree to
+                    # about that, not to rounding: the same iteration count gives 1e-9, one iteration apart ~1e-3)
+                    assert np.allclose(got, want, atol=5e-3 * max(1.0, np.abs(want).max())), (s_, np.abs(got - want).max())
         assert n_ok > 0
 
 
