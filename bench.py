@@ -175,6 +175,8 @@ def run_b200(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     _lib.profile_enable(True)
+    if args.tensor_cluster >= 0:
+        _lib.set_option("similarity_tensor_cluster", args.tensor_cluster)
     if args.workload == "conformers":
         legs = run_conformer_legs(args, pool, dev, world, rank)
         if rank == 0:
@@ -665,6 +667,7 @@ def main() -> None:
     ap.add_argument("--pool", type=int, default=10000, help="distinct pseudo-molecules generated (cycled beyond that)")
     ap.add_argument("--pool-procs", type=int, default=0, help="generator processes (0 = host cores / ranks, at most 48)")
     ap.add_argument("--etkdg-cpu-mols", type=int, default=0, help="molecules of that leg's CPU sample (0 = one per host core)")
+    ap.add_argument("--tensor-cluster", type=int, default=-1, help="pair-pass tile variant override (testing; -1 = library default)")
     ap.add_argument("--all-configs", action="store_true", help="run configs 4 and 5 on fewer than 8 GPUs too")
     ap.add_argument("--mmff-mols", type=int, default=100000, help="config 4 size")
     ap.add_argument("--e2e-mols", type=int, default=1000000, help="config 5 size")

@@ -36,14 +36,16 @@ def _canon(idx, par):
 
 def _mols(n, seed, with_uff=False):
     rng = np.random.default_rng(seed)
-    flat, mols = S.random_embed_molecules(n, 5, 12, seed=seed)
     if with_uff:
-        sysu, _xyz, mu = S.random_uff_system(n, 5, 12, seed=seed)
-        for m, u, k in zip(mols, mu, range(n)):
-            assert (m["z"] == u["z"]).all()
+        sysu, _xyz, mols = S.random_uff_system(n, 5, 12, seed=seed)
+        flat = None
+        for k, m in enumerate(mols):
+            m["planar"] = {a for a in range(len(m["z"])) if len(m["nbrs"][a]) == 3 and m["z"][a] in (6, 7)}
             m["uff"] = {name: (sysu.tables[name][1][sysu.tables[name][0][k]:sysu.tables[name][0][k + 1]],
                                sysu.tables[name][2][sysu.tables[name][0][k]:sysu.tables[name][0][k + 1]])
                         for name, _k, _p in LAYOUT["uff"]}
+    else:
+        flat, mols = S.random_embed_molecules(n, 5, 12, seed=seed)
     for m in mols:
         # (the generator draws the stretch-bend rest lengths independently of the bond table; RDKit - and the adapter -
         # take them from the bond parameters, so make the reference tables consistent with that)
