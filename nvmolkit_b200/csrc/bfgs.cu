@@ -18,6 +18,7 @@
 
 namespace b200 {
 int g_bfgsCtasPerSm = kMinCtas;  // resident minimisation CTAs per SM (option "bfgs_ctas_per_sm")
+int g_bfgsL2Persist = 0;         // mark the inverse-Hessian slabs persisting in L2 (option "bfgs_l2_persist")
 
 // Device-side work counters of the conformer kernels, one small buffer per device, allocated on first use: two banks of
 // kStatCount, [0] the embedder (etkdgKernel), [1] the stand-alone minimisers (bfgsKernel<FF>).
@@ -150,6 +151,7 @@ void runMinimize(const typename FF::System& sys, const typename FF::Params& par,
   B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));
   Batch b{nConf, confMol, confAtomStart, pos, maxIters, gradTol, scaleGrads, 0, active, energy, status, iters,
           hess.get(), stride, queue.get(), maxN, pathBStats() + kStatCount};
+  L2Persist  keep(s, hess.get(), stride * blocks * sizeof(double), g_bfgsL2Persist != 0);
   PhaseTimer t("bfgs", s);
   bfgsKernel<FF><<<blocks, kT, smem, s>>>(sys, par, b);
   B200_LAUNCHED();

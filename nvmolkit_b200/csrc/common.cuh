@@ -119,4 +119,38 @@ inline int currentDeviceSlot() {
 
 inline cudaStream_t asStream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// RAII: while alive, accesses of kernels launched on `s` to [ptr, ptr + bytes) are marked PERSISTING in L2 (the rest
+// streaming): the inverse-Hessian slabs of the minimiser kernels are re-read every iteration while the term tables only
+// stream through. Best effort - failures of the attribute calls are ignored (the kernels are correct without it).
+struct L2Persist {
+  cudaStream_t s      = nullptr;
+  bool         active = false;
+  L2Persist(cudaStream_t stream, const void* ptr, size_t bytes, bool enable) : s(stream) {
+    if (!enable || !ptr || !bytes) return;
+    int dev = 0, maxPersist = 0, maxWindow = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (maxPersist <= 0 || maxWindow <= 0) return;
+    cudaCtxResetPersistingL2Cache();  // lines a previous launch left persisting
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(maxPersist)) != cudaSuccess) return;
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr  = const_cast<void*>(ptr);
+    v.accessPolicyWindow.num_bytes = bytes < static_cast<size_t>(maxWindow) ? bytes : static_cast<size_t>(maxWindow);
+    const double ratio             = static_cast<double>(maxPersist) / static_cast<double>(v.accessPolicyWindow.num_bytes);
+    v.accessPolicyWindow.hitRatio  = ratio < 1.0 ? static_cast<float>(ratio) : 1.0f;
+    v.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+    active = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
+    cudaGetLastError();
+  }
+  ~L2Persist() {
+    if (!active) return;
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);  // (later launches on `s` are unaffected; the
+    cudaGetLastError();  // kernel just launched keeps the policy it was launched with; its persisting lines age out)
+  }
+};
+
 }  // namespace b200

@@ -25,6 +25,7 @@
 
 namespace b200 {
 extern int g_bfgsCtasPerSm;
+extern int g_bfgsL2Persist;
 unsigned long long* pathBStats();
 namespace {
 
@@ -500,6 +501,7 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
                 reinterpret_cast<unsigned long long*>(d_stage_failures), hess.get(), stride, queue.get(), maxN,
                 state.get(), state.get() + nSlots, state.get() + 2 * static_cast<size_t>(nSlots), state.get() + 3 * static_cast<size_t>(nSlots),
                 pathBStats()};
+    L2Persist  keep(s, hess.get(), stride * blocks * sizeof(float), g_bfgsL2Persist != 0);
     PhaseTimer t("etkdg", s);
     etkdgKernel<<<blocks, kT, smem, s>>>(a);
     B200_LAUNCHED();

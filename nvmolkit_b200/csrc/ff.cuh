@@ -65,17 +65,106 @@ __device__ __forceinline__ void emptyRange(Range& r) {
   r.end  = r.beg;
   r.wend = r.wbeg;
 }
+// One term record in registers: K molecule-local atom indices + P parameters.
+template <int K, int P>
+struct TermRec {
+  int16_t ix[K];
+  double  q[P > 0 ? P : 1];
+};
+template <int K, int P>
+__device__ __forceinline__ void loadTerm(const b200mol_term_table& T, int t, TermRec<K, P>& r) {
+  if constexpr (K == 2) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(T.idx + 2 * t);
+    r.ix[0]          = static_cast<int16_t>(u & 0xffffu);
+    r.ix[1]          = static_cast<int16_t>(u >> 16);
+  } else if constexpr (K == 4) {
+    const uint2 u = *reinterpret_cast<const uint2*>(T.idx + 4 * t);
+    r.ix[0] = static_cast<int16_t>(u.x & 0xffffu), r.ix[1] = static_cast<int16_t>(u.x >> 16);
+    r.ix[2] = static_cast<int16_t>(u.y & 0xffffu), r.ix[3] = static_cast<int16_t>(u.y >> 16);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.ix[k] = T.idx[K * t + k];
+  }
+#pragma unroll
+  for (int k = 0; k < P; ++k) r.q[k] = T.par[P * t + k];
+}
 // Energy mode: thread-strided over the terms. Gradient mode: warp-strided over the waves, lane = term of the wave.
-template <bool GRAD, class F>
+// Both loops keep the NEXT term's record in flight while the current one is evaluated: the records stream from L2 / HBM
+// (a molecule's tables are 70-120 KB and ten thousand molecules do not fit L2), and a load-then-use loop paid that
+// latency once per term and thread - it, not the arithmetic, set the evaluation time (profiles/r02_path_b_summary.md).
+#ifndef B200_TERM_PREFETCH
+#define B200_TERM_PREFETCH 1  // 0 = load-then-use; 1 = prefetch.global.L1 of the next record; 2 = next record in registers
+#endif
+template <int K, int P>
+__device__ __forceinline__ void prefetchTerm(const b200mol_term_table& T, int t) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(T.idx + K * t));
+  if constexpr (P > 0) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(T.par + P * t));
+    if constexpr (P * 8 > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(T.par + P * t + P - 1));  // a record may straddle lines
+  }
+}
+template <bool GRAD, int K, int P, class F>
 __device__ __forceinline__ void forTerms(const b200mol_term_table& T, const Range& r, int tid, int nT, F&& f) {
+  constexpr bool kRegs = B200_TERM_PREFETCH == 2 && P <= 4;  // (two records of the fat tables do not fit the register budget)
+  constexpr bool kL1   = B200_TERM_PREFETCH == 1;
+  TermRec<K, P> cur;
   if constexpr (!GRAD) {
-    for (int t = r.beg + tid; t < r.end; t += nT) f(t);
+    int t = r.beg + tid;
+    if constexpr (kRegs) {
+      if (t < r.end) loadTerm<K, P>(T, t, cur);
+      while (t < r.end) {
+        TermRec<K, P> nxt;
+        const int     tn = t + nT;
+        if (tn < r.end) loadTerm<K, P>(T, tn, nxt);
+        f(cur);
+        cur = nxt;
+        t   = tn;
+      }
+    } else {
+      for (; t < r.end; t += nT) {
+        if constexpr (kL1)
+          if (t + nT < r.end) prefetchTerm<K, P>(T, t + nT);
+        loadTerm<K, P>(T, t, cur);
+        f(cur);
+      }
+    }
   } else {
     const int warp = tid >> 5, lane = tid & 31, nW = nT >> 5;
-    for (int w = r.wbeg + warp; w < r.wend; w += nW) {
-      const int t = T.waves[w] + lane;
-      if (t < T.waves[w + 1]) f(t);
-      __syncwarp();
+    int       w = r.wbeg + warp;
+    if constexpr (kRegs) {
+      int t = 0, tEnd = 0;
+      if (w < r.wend) {
+        t    = T.waves[w] + lane;
+        tEnd = T.waves[w + 1];
+        if (t < tEnd) loadTerm<K, P>(T, t, cur);
+      }
+      while (w < r.wend) {
+        TermRec<K, P> nxt;
+        const int     wn = w + nW;
+        int           tn = 0, tnEnd = 0;
+        if (wn < r.wend) {
+          tn    = T.waves[wn] + lane;
+          tnEnd = T.waves[wn + 1];
+          if (tn < tnEnd) loadTerm<K, P>(T, tn, nxt);
+        }
+        if (t < tEnd) f(cur);
+        __syncwarp();
+        cur  = nxt;
+        t    = tn;
+        tEnd = tnEnd;
+        w    = wn;
+      }
+    } else {
+      for (; w < r.wend; w += nW) {
+        const int t = T.waves[w] + lane;
+        if constexpr (kL1)
+          if (w + nW < r.wend) prefetchTerm<K, P>(T, T.waves[w + nW] + lane);  // (a lane past the wave's end prefetches the next wave's head: harmless)
+        if (t < T.waves[w + 1]) {
+          loadTerm<K, P>(T, t, cur);
+          f(cur);
+        }
+        __syncwarp();
+      }
     }
   }
 }
@@ -106,9 +195,9 @@ struct Mmff {
     const System& s = *v.s;
     double        e = 0.0;
     // ---- bond stretch ----
-    forTerms<GRAD>(s.bond, v.bond, tid, nT, [&](int t) {
-      const int    i = s.bond.idx[2 * t], j = s.bond.idx[2 * t + 1];
-      const double r0 = s.bond.par[2 * t], kb = s.bond.par[2 * t + 1];
+    forTerms<GRAD, 2, 2>(s.bond, v.bond, tid, nT, [&](const TermRec<2, 2>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1];
+      const double r0 = rec.q[0], kb = rec.q[1];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
       const double dist = sqrt(dot(d, d)), dr = dist - r0;
       constexpr double cs = -2.0;
@@ -122,10 +211,10 @@ struct Mmff {
       }
     });
     // ---- angle bend ----
-    forTerms<GRAD>(s.angle, v.angle, tid, nT, [&](int t) {
-      const int    i = s.angle.idx[3 * t], j = s.angle.idx[3 * t + 1], k = s.angle.idx[3 * t + 2];
-      const double theta0 = s.angle.par[3 * t], ka = s.angle.par[3 * t + 1];
-      const bool   linear = s.angle.par[3 * t + 2] != 0.0;
+    forTerms<GRAD, 3, 3>(s.angle, v.angle, tid, nT, [&](const TermRec<3, 3>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1], k = rec.ix[2];
+      const double theta0 = rec.q[0], ka = rec.q[1];
+      const bool   linear = rec.q[2] != 0.0;
       const V3     d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
       const double l1sq = dot(d1, d1), l2sq = dot(d2, d2), l1 = sqrt(l1sq), l2 = sqrt(l2sq);
       const double cosT = clampd(dot(d1, d2) / (l1 * l2), -1.0, 1.0);
@@ -147,30 +236,29 @@ struct Mmff {
       }
     });
     // ---- stretch-bend ----
-    forTerms<GRAD>(s.strbend, v.strbend, tid, nT, [&](int t) {
-      const int     i = s.strbend.idx[3 * t], j = s.strbend.idx[3 * t + 1], k = s.strbend.idx[3 * t + 2];
-      const double* q = s.strbend.par + 5 * t;
+    forTerms<GRAD, 3, 5>(s.strbend, v.strbend, tid, nT, [&](const TermRec<3, 5>& rec) {
+      const int     i = rec.ix[0], j = rec.ix[1], k = rec.ix[2];
       const V3      d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
       const double  l1 = sqrt(dot(d1, d1)), l2 = sqrt(dot(d2, d2));
       const double  cosT = clampd(dot(d1, d2) / (l1 * l2), -1.0, 1.0);
-      const double  dT = kRad2Deg * acos(cosT) - q[0], dr1 = l1 - q[1], dr2 = l2 - q[2];
+      const double  dT = kRad2Deg * acos(cosT) - rec.q[0], dr1 = l1 - rec.q[1], dr2 = l2 - rec.q[2];
       if (!GRAD) {
-        e += 2.51210 * dT * (dr1 * q[3] + dr2 * q[4]);
+        e += 2.51210 * dT * (dr1 * rec.q[3] + dr2 * rec.q[4]);
       } else {
         constexpr double pre = 143.9325 * kDeg2Rad;
         const double     invSin = fmin(1.0 / sqrt(1.0 - cosT * cosT), 1.0e8);
-        const double     bt = kRad2Deg * (q[3] * dr1 + q[4] * dr2) * invSin;
+        const double     bt = kRad2Deg * (rec.q[3] * dr1 + rec.q[4] * dr2) * invSin;
         const V3         n1 = d1 * (1.0 / l1), n2 = d2 * (1.0 / l2);
         const V3         a = (n2 - n1 * cosT) * (1.0 / l1), b = (n1 - n2 * cosT) * (1.0 / l2);
-        acc<3>(grad, i, (n1 * (dT * q[3]) - a * bt) * pre);
-        acc<3>(grad, j, ((n1 * q[3] + n2 * q[4]) * (-dT) + (a + b) * bt) * pre);
-        acc<3>(grad, k, (n2 * (dT * q[4]) - b * bt) * pre);
+        acc<3>(grad, i, (n1 * (dT * rec.q[3]) - a * bt) * pre);
+        acc<3>(grad, j, ((n1 * rec.q[3] + n2 * rec.q[4]) * (-dT) + (a + b) * bt) * pre);
+        acc<3>(grad, k, (n2 * (dT * rec.q[4]) - b * bt) * pre);
       }
     });
     // ---- out-of-plane ----
-    forTerms<GRAD>(s.oop, v.oop, tid, nT, [&](int t) {
-      const int    i = s.oop.idx[4 * t], j = s.oop.idx[4 * t + 1], k = s.oop.idx[4 * t + 2], l = s.oop.idx[4 * t + 3];
-      const double koop = s.oop.par[t];
+    forTerms<GRAD, 4, 1>(s.oop, v.oop, tid, nT, [&](const TermRec<4, 1>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1], k = rec.ix[2], l = rec.ix[3];
+      const double koop = rec.q[0];
       V3           ji = ld<3>(pos, i) - ld<3>(pos, j), jk = ld<3>(pos, k) - ld<3>(pos, j), jl = ld<3>(pos, l) - ld<3>(pos, j);
       const double li = sqrt(dot(ji, ji)), lk = sqrt(dot(jk, jk)), ll = sqrt(dot(jl, jl));
       ji = ji * (1.0 / li);
@@ -200,11 +288,10 @@ struct Mmff {
       }
     });
     // ---- torsion ----
-    forTerms<GRAD>(s.torsion, v.torsion, tid, nT, [&](int t) {
-      const int16_t* ix = s.torsion.idx + 4 * t;
-      const double   V1 = s.torsion.par[3 * t], V2 = s.torsion.par[3 * t + 1], V3c = s.torsion.par[3 * t + 2];
-      const V3       d1 = ld<3>(pos, ix[0]) - ld<3>(pos, ix[1]), d2 = ld<3>(pos, ix[2]) - ld<3>(pos, ix[1]),
-               d4 = ld<3>(pos, ix[3]) - ld<3>(pos, ix[2]);
+    forTerms<GRAD, 4, 3>(s.torsion, v.torsion, tid, nT, [&](const TermRec<4, 3>& rec) {
+      const double   V1 = rec.q[0], V2 = rec.q[1], V3c = rec.q[2];
+      const V3       d1 = ld<3>(pos, rec.ix[0]) - ld<3>(pos, rec.ix[1]), d2 = ld<3>(pos, rec.ix[2]) - ld<3>(pos, rec.ix[1]),
+               d4 = ld<3>(pos, rec.ix[3]) - ld<3>(pos, rec.ix[2]);
       V3           c1 = cross(d1, d2), c2 = cross(-d2, d4);
       const double n1 = 1.0 / sqrt(dot(c1, c1)), n2 = 1.0 / sqrt(dot(c2, c2));
       if (!GRAD) {
@@ -220,23 +307,23 @@ struct Mmff {
         double       sinTerm = 0.0;
         if (sinSq > 0.0) sinTerm = 0.5 * (V1 - 2.0 * V2 * (2.0 * cosPhi) + 3.0 * V3c * (3.0 - 4.0 * sinSq));
         const V3 a = (c2 - c1 * cosPhi) * i1, b = (c1 - c2 * cosPhi) * i2;
-        acc<3>(grad, ix[0], V3{a.z * d2.y - a.y * d2.z, a.x * d2.z - a.z * d2.x, a.y * d2.x - a.x * d2.y} * sinTerm);
-        acc<3>(grad, ix[1],
+        acc<3>(grad, rec.ix[0], V3{a.z * d2.y - a.y * d2.z, a.x * d2.z - a.z * d2.x, a.y * d2.x - a.x * d2.y} * sinTerm);
+        acc<3>(grad, rec.ix[1],
                V3{a.y * (d2.z - d1.z) + a.z * (d1.y - d2.y) + b.y * (-d4.z) + b.z * (d4.y),
                   a.x * (d1.z - d2.z) + a.z * (d2.x - d1.x) + b.x * (d4.z) + b.z * (-d4.x),
                   a.x * (d2.y - d1.y) + a.y * (d1.x - d2.x) + b.x * (-d4.y) + b.y * (d4.x)} * sinTerm);
-        acc<3>(grad, ix[2],
+        acc<3>(grad, rec.ix[2],
                V3{a.y * (d1.z) + a.z * (-d1.y) + b.y * (d4.z + d2.z) + b.z * (-d4.y - d2.y),
                   a.x * (-d1.z) + a.z * (d1.x) + b.x * (-d4.z - d2.z) + b.z * (d4.x + d2.x),
                   a.x * (d1.y) + a.y * (-d1.x) + b.x * (d4.y + d2.y) + b.y * (-d4.x - d2.x)} * sinTerm);
-        acc<3>(grad, ix[3],
+        acc<3>(grad, rec.ix[3],
                V3{b.y * (-d2.z) - b.z * (-d2.y), b.z * (-d2.x) - b.x * (-d2.z), b.x * (-d2.y) - b.y * (-d2.x)} * sinTerm);
       }
     });
     // ---- buffered 14-7 van der Waals ----
-    forTerms<GRAD>(s.vdw, v.vdw, tid, nT, [&](int t) {
-      const int    i = s.vdw.idx[2 * t], j = s.vdw.idx[2 * t + 1];
-      const double R = s.vdw.par[2 * t], eps = s.vdw.par[2 * t + 1];
+    forTerms<GRAD, 2, 2>(s.vdw, v.vdw, tid, nT, [&](const TermRec<2, 2>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1];
+      const double R = rec.q[0], eps = rec.q[1];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
       const double d2   = dot(d, d), dist = sqrt(d2);
       if (!GRAD) {
@@ -253,10 +340,10 @@ struct Mmff {
       }
     });
     // ---- buffered Coulomb ----
-    forTerms<GRAD>(s.ele, v.ele, tid, nT, [&](int t) {
-      const int    i = s.ele.idx[2 * t], j = s.ele.idx[2 * t + 1];
-      const double ct = s.ele.par[3 * t];
-      const bool   sq = s.ele.par[3 * t + 1] == 2.0, is14 = s.ele.par[3 * t + 2] != 0.0;
+    forTerms<GRAD, 2, 3>(s.ele, v.ele, tid, nT, [&](const TermRec<2, 3>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1];
+      const double ct = rec.q[0];
+      const bool   sq = rec.q[1] == 2.0, is14 = rec.q[2] != 0.0;
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
       const double dist = sqrt(dot(d, d)), rb = dist + 0.05;
       if (!GRAD) {
@@ -299,9 +386,9 @@ struct Dg {
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
     double        e = 0.0;
-    forTerms<GRAD>(s.dist, v.dist, tid, nT, [&](int t) {
-      const int    i = s.dist.idx[2 * t], j = s.dist.idx[2 * t + 1];
-      const double lb2 = s.dist.par[3 * t], ub2 = s.dist.par[3 * t + 1], w = s.dist.par[3 * t + 2];
+    forTerms<GRAD, 2, 3>(s.dist, v.dist, tid, nT, [&](const TermRec<2, 3>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1];
+      const double lb2 = rec.q[0], ub2 = rec.q[1], w = rec.q[2];
       double       dd[DIM], d2 = 0.0;
 #pragma unroll
       for (int c = 0; c < DIM; ++c) {
@@ -335,10 +422,9 @@ struct Dg {
         }
       }
     });
-    forTerms<GRAD>(s.chiral, v.chiral, tid, nT, [&](int t) {
-      const int16_t* ix = s.chiral.idx + 4 * t;
-      const double   ub = s.chiral.par[2 * t], lb = s.chiral.par[2 * t + 1];
-      const V3       p1 = ld<DIM>(pos, ix[0]), p2 = ld<DIM>(pos, ix[1]), p3 = ld<DIM>(pos, ix[2]), p4 = ld<DIM>(pos, ix[3]);
+    forTerms<GRAD, 4, 2>(s.chiral, v.chiral, tid, nT, [&](const TermRec<4, 2>& rec) {
+      const double   ub = rec.q[0], lb = rec.q[1];
+      const V3       p1 = ld<DIM>(pos, rec.ix[0]), p2 = ld<DIM>(pos, rec.ix[1]), p3 = ld<DIM>(pos, rec.ix[2]), p4 = ld<DIM>(pos, rec.ix[3]);
       const V3       v1 = p1 - p4, v2 = p2 - p4, v3 = p3 - p4;
       const double   vol = dot(v1, cross(v2, v3));
       double         diff;
@@ -349,18 +435,18 @@ struct Dg {
         e += v.cw * diff * diff;
       } else {
         const double pre = v.cw * diff;  // RDKit: no factor 2
-        acc<DIM>(grad, ix[0], cross(v2, v3) * pre);
-        acc<DIM>(grad, ix[1], cross(v3, v1) * pre);
-        acc<DIM>(grad, ix[2], V3{v2.z * v1.y - v2.y * v1.z, v2.x * v1.z - v2.z * v1.x, v2.y * v1.x - v2.x * v1.y} * pre);
-        acc<DIM>(grad, ix[3],
+        acc<DIM>(grad, rec.ix[0], cross(v2, v3) * pre);
+        acc<DIM>(grad, rec.ix[1], cross(v3, v1) * pre);
+        acc<DIM>(grad, rec.ix[2], V3{v2.z * v1.y - v2.y * v1.z, v2.x * v1.z - v2.z * v1.x, v2.y * v1.x - v2.x * v1.y} * pre);
+        acc<DIM>(grad, rec.ix[3],
                  V3{p1.z * (p2.y - p3.y) + p2.z * (p3.y - p1.y) + p3.z * (p1.y - p2.y),
                     p1.x * (p2.z - p3.z) + p2.x * (p3.z - p1.z) + p3.x * (p1.z - p2.z),
                     p1.y * (p2.x - p3.x) + p2.y * (p3.x - p1.x) + p3.y * (p1.x - p2.x)} * pre);
       }
     });
     if constexpr (DIM == 4) {
-      forTerms<GRAD>(s.fourth, v.fourth, tid, nT, [&](int t) {
-        const int    a  = s.fourth.idx[t];
+      forTerms<GRAD, 1, 0>(s.fourth, v.fourth, tid, nT, [&](const TermRec<1, 0>& rec) {
+        const int    a  = rec.ix[0];
         const double w4 = pos[a * 4 + 3];
         if (!GRAD) e += v.fw * w4 * w4;
         else grad[a * 4 + 3] += v.fw * w4;  // RDKit: no factor 2
@@ -402,11 +488,11 @@ struct Etk {
   __device__ static double distTerms(const b200mol_term_table& T, Range r, const double* pos, double* grad, int tid, int nT,
                                      const double* refPos) {
     double e = 0.0;
-    forTerms<GRAD>(T, r, tid, nT, [&](int t) {
-      const int i = T.idx[2 * t], j = T.idx[2 * t + 1];
-      double    mn = T.par[P * t], mx = T.par[P * t + 1];
-      const double fk = T.par[P * t + 2];
-      if (P == 4 && refPos && T.par[P * t + 3] == 0.0) {
+    forTerms<GRAD, 2, P>(T, r, tid, nT, [&](const TermRec<2, P>& rec) {
+      const int i = rec.ix[0], j = rec.ix[1];
+      double    mn = rec.q[0], mx = rec.q[1];
+      const double fk = rec.q[2];
+      if (P == 4 && refPos && rec.q[3] == 0.0) {
         const V3     rd   = ld<4>(refPos, i) - ld<4>(refPos, j);
         const double dref = sqrt(dot(rd, rd)), half = (mx - mn) / 2.0;
         mn                = dref - half;
@@ -434,11 +520,10 @@ struct Etk {
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
     double        e = 0.0;
-    forTerms<GRAD>(s.torsion, v.torsion, tid, nT, [&](int t) {
-      const int16_t* ix = s.torsion.idx + 4 * t;
-      const double*  fc = s.torsion.par + 12 * t;
+    forTerms<GRAD, 4, 12>(s.torsion, v.torsion, tid, nT, [&](const TermRec<4, 12>& rec) {
+      const double*  fc = rec.q;
       const double*  sg = fc + 6;
-      const V3       p1 = ld<4>(pos, ix[0]), p2 = ld<4>(pos, ix[1]), p3 = ld<4>(pos, ix[2]), p4 = ld<4>(pos, ix[3]);
+      const V3       p1 = ld<4>(pos, rec.ix[0]), p2 = ld<4>(pos, rec.ix[1]), p3 = ld<4>(pos, rec.ix[2]), p4 = ld<4>(pos, rec.ix[3]);
       const V3       r1 = p1 - p2, r2 = p3 - p2, r3 = p2 - p3, r4 = p4 - p3;
       V3             t0 = cross(r1, r2), t1 = cross(r3, r4);
       const double   d02 = dot(t0, t0), d12 = dot(t1, t1);
@@ -464,24 +549,23 @@ struct Etk {
                            6.0 * fc[4] * sg[4] * (32.0 * q5 * sp - 32.0 * q3 * sp + 6.0 * sp));  // V5 twice: RDKit quirk
         const double sinTerm = -dE * (isZero(sp) ? 1.0 / cp : 1.0 / sp);
         const V3     a = (t1 - t0 * cp) * i0, b = (t0 - t1 * cp) * i1;
-        acc<4>(grad, ix[0], V3{a.z * r2.y - a.y * r2.z, a.x * r2.z - a.z * r2.x, a.y * r2.x - a.x * r2.y} * sinTerm);
-        acc<4>(grad, ix[3], V3{b.y * r3.z - b.z * r3.y, b.z * r3.x - b.x * r3.z, b.x * r3.y - b.y * r3.x} * sinTerm);
-        acc<4>(grad, ix[1],
+        acc<4>(grad, rec.ix[0], V3{a.z * r2.y - a.y * r2.z, a.x * r2.z - a.z * r2.x, a.y * r2.x - a.x * r2.y} * sinTerm);
+        acc<4>(grad, rec.ix[3], V3{b.y * r3.z - b.z * r3.y, b.z * r3.x - b.x * r3.z, b.x * r3.y - b.y * r3.x} * sinTerm);
+        acc<4>(grad, rec.ix[1],
                V3{a.y * (r2.z - r1.z) + a.z * (r1.y - r2.y) + b.y * (-r4.z) + b.z * (r4.y),
                   a.x * (r1.z - r2.z) + a.z * (r2.x - r1.x) + b.x * (r4.z) + b.z * (-r4.x),
                   a.x * (r2.y - r1.y) + a.y * (r1.x - r2.x) + b.x * (-r4.y) + b.y * (r4.x)} * sinTerm);
-        acc<4>(grad, ix[2],
+        acc<4>(grad, rec.ix[2],
                V3{a.y * r1.z + a.z * (-r1.y) + b.y * (r4.z - r3.z) + b.z * (r3.y - r4.y),
                   a.x * (-r1.z) + a.z * r1.x + b.x * (r3.z - r4.z) + b.z * (r4.x - r3.x),
                   a.x * r1.y + a.y * (-r1.x) + b.x * (r4.y - r3.y) + b.y * (r3.x - r4.x)} * sinTerm);
       }
     });
-    forTerms<GRAD>(s.improper, v.improper, tid, nT, [&](int t) {
-      const int16_t* ix = s.improper.idx + 4 * t;
-      const double   C0 = s.improper.par[4 * t], C1 = s.improper.par[4 * t + 1], C2 = s.improper.par[4 * t + 2],
-                   fk = s.improper.par[4 * t + 3];
-      const V3     ji = ld<4>(pos, ix[0]) - ld<4>(pos, ix[1]), jk = ld<4>(pos, ix[2]) - ld<4>(pos, ix[1]),
-               jl = ld<4>(pos, ix[3]) - ld<4>(pos, ix[1]);
+    forTerms<GRAD, 4, 4>(s.improper, v.improper, tid, nT, [&](const TermRec<4, 4>& rec) {
+      const double   C0 = rec.q[0], C1 = rec.q[1], C2 = rec.q[2],
+                   fk = rec.q[3];
+      const V3     ji = ld<4>(pos, rec.ix[0]) - ld<4>(pos, rec.ix[1]), jk = ld<4>(pos, rec.ix[2]) - ld<4>(pos, rec.ix[1]),
+               jl = ld<4>(pos, rec.ix[3]) - ld<4>(pos, rec.ix[1]);
       const double l2i = dot(ji, ji), l2k = dot(jk, jk), l2l = dot(jl, jl);
       if (!GRAD) {
         double cosY = 0.0;
@@ -506,19 +590,18 @@ struct Etk {
         const V3     g1 = (t1 * inv1 - (a - b * cT) * term2) * ii;
         const V3     g3 = (t2 * inv1 - (b - a * cT) * term2) * ik;
         const V3     g4 = (t3 * inv1 - c * cOs) * il;
-        acc<4>(grad, ix[0], g1 * dE);
-        acc<4>(grad, ix[1], (g1 + g3 + g4) * (-dE));
-        acc<4>(grad, ix[2], g3 * dE);
-        acc<4>(grad, ix[3], g4 * dE);
+        acc<4>(grad, rec.ix[0], g1 * dE);
+        acc<4>(grad, rec.ix[1], (g1 + g3 + g4) * (-dE));
+        acc<4>(grad, rec.ix[2], g3 * dE);
+        acc<4>(grad, rec.ix[3], g4 * dE);
       }
     });
     e += distTerms<GRAD, 4>(s.dist12, v.d12, pos, grad, tid, nT, v.refPos);
     e += distTerms<GRAD, 4>(s.dist13, v.d13, pos, grad, tid, nT, v.refPos);
     e += distTerms<GRAD, 3>(s.longrange, v.lr, pos, grad, tid, nT, nullptr);
-    forTerms<GRAD>(s.angle13, v.a13, tid, nT, [&](int t) {
-      const int16_t* ix = s.angle13.idx + 3 * t;
-      const double   mn = s.angle13.par[2 * t], mx = s.angle13.par[2 * t + 1];
-      const V3       r1 = ld<4>(pos, ix[0]) - ld<4>(pos, ix[1]), r2 = ld<4>(pos, ix[2]) - ld<4>(pos, ix[1]);
+    forTerms<GRAD, 3, 2>(s.angle13, v.a13, tid, nT, [&](const TermRec<3, 2>& rec) {
+      const double   mn = rec.q[0], mx = rec.q[1];
+      const V3       r1 = ld<4>(pos, rec.ix[0]) - ld<4>(pos, rec.ix[1]), r2 = ld<4>(pos, rec.ix[2]) - ld<4>(pos, rec.ix[1]);
       const double   l1 = dot(r1, r1), l2 = dot(r2, r2);
       if (!GRAD) {
         if (isZero(l1 * l2)) return;
@@ -533,9 +616,9 @@ struct Etk {
         const V3     rp  = cross(r2, r1);
         const double pre = dE / sqrt(fmax(dot(rp, rp), 1.0e-10));
         const V3     a = cross(r1, rp) * (-pre / m1), b = cross(r2, rp) * (pre / m2);
-        acc<4>(grad, ix[0], a);
-        acc<4>(grad, ix[1], -(a + b));
-        acc<4>(grad, ix[2], b);
+        acc<4>(grad, rec.ix[0], a);
+        acc<4>(grad, rec.ix[1], -(a + b));
+        acc<4>(grad, rec.ix[2], b);
       }
     });
     return e;
@@ -564,9 +647,9 @@ struct Uff {
   __device__ static double eval(const View& v, const double* pos, double* grad, int tid, int nT) {
     const System& s = *v.s;
     double        e = 0.0;
-    forTerms<GRAD>(s.bond, v.bond, tid, nT, [&](int t) {
-      const int    i = s.bond.idx[2 * t], j = s.bond.idx[2 * t + 1];
-      const double r0 = s.bond.par[2 * t], k = s.bond.par[2 * t + 1];
+    forTerms<GRAD, 2, 2>(s.bond, v.bond, tid, nT, [&](const TermRec<2, 2>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1];
+      const double r0 = rec.q[0], k = rec.q[1];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
       const double dist = sqrt(dot(d, d));
       if (!GRAD) {
@@ -577,10 +660,9 @@ struct Uff {
         acc<3>(grad, j, -g);
       }
     });
-    forTerms<GRAD>(s.angle, v.angle, tid, nT, [&](int t) {
-      const int     i = s.angle.idx[3 * t], j = s.angle.idx[3 * t + 1], k = s.angle.idx[3 * t + 2];
-      const double* q = s.angle.par + 6 * t;  // theta0, k, order, C0, C1, C2
-      const int     order = static_cast<int>(q[2]);
+    forTerms<GRAD, 3, 6>(s.angle, v.angle, tid, nT, [&](const TermRec<3, 6>& rec) {
+      const int     i = rec.ix[0], j = rec.ix[1], k = rec.ix[2];
+      const int     order = static_cast<int>(rec.q[2]);
       const V3      d1 = ld<3>(pos, i) - ld<3>(pos, j), d2 = ld<3>(pos, k) - ld<3>(pos, j);
       const double  l1sq = dot(d1, d1), l2sq = dot(d2, d2);
       if (l1sq <= 0.0 || l2sq <= 0.0) return;
@@ -592,7 +674,7 @@ struct Uff {
         const double c2t = c * c - sSq;
         double       term;
         if (order == 0) {
-          term = q[3] + q[4] * c + q[5] * c2t;
+          term = rec.q[3] + rec.q[4] * c + rec.q[5] * c2t;
         } else {
           double r = 0.0;
           if (order == 1) r = -c;
@@ -601,24 +683,24 @@ struct Uff {
           else if (order == 4) r = c * c * c * c - 6.0 * c * c * sSq + sSq * sSq;
           term = (1.0 - r) / static_cast<double>(order * order);
         }
-        double en = q[1] * term;
-        if (corr) en += exp(-20.0 * (acos(c) - q[0] + 0.25));
+        double en = rec.q[1] * term;
+        if (corr) en += exp(-20.0 * (acos(c) - rec.q[0] + 0.25));
         e += en;
       } else {
         if (isZero(sSq)) return;
         const double sn = fmax(sqrt(sSq), 1.0e-8), s2t = 2.0 * sn * c;
         double       dE;
         if (order == 0) {
-          dE = -q[1] * (q[4] * sn + 2.0 * q[5] * s2t);
+          dE = -rec.q[1] * (rec.q[4] * sn + 2.0 * rec.q[5] * s2t);
         } else {
           double r = 0.0;
           if (order == 1) r = -sn;
           else if (order == 2) r = s2t;
           else if (order == 3) r = sn * (3.0 - 4.0 * sn * sn);
           else if (order == 4) r = c * sn * (4.0 - 8.0 * sn * sn);
-          dE = (order >= 1 && order <= 4) ? r * q[1] / static_cast<double>(order) : 0.0;
+          dE = (order >= 1 && order <= 4) ? r * rec.q[1] / static_cast<double>(order) : 0.0;
         }
-        if (corr) dE += -20.0 * exp(-20.0 * (acos(c) - q[0] + 0.25));
+        if (corr) dE += -20.0 * exp(-20.0 * (acos(c) - rec.q[0] + 0.25));
         const double cf = dE / (-sn);
         const V3     n1 = d1 * (1.0 / l1), n2 = d2 * (1.0 / l2);
         const V3     a = (n2 - n1 * c) * (cf / l1), b = (n1 - n2 * c) * (cf / l2);
@@ -627,12 +709,11 @@ struct Uff {
         acc<3>(grad, k, b);
       }
     });
-    forTerms<GRAD>(s.torsion, v.torsion, tid, nT, [&](int t) {
-      const int16_t* ix = s.torsion.idx + 4 * t;
-      const double   fk = s.torsion.par[3 * t], cosTerm = s.torsion.par[3 * t + 2];
-      const int      order = static_cast<int>(s.torsion.par[3 * t + 1]);
-      const V3       r0 = ld<3>(pos, ix[0]) - ld<3>(pos, ix[1]), r1 = ld<3>(pos, ix[2]) - ld<3>(pos, ix[1]), r2 = -r1,
-               r3 = ld<3>(pos, ix[3]) - ld<3>(pos, ix[2]);
+    forTerms<GRAD, 4, 3>(s.torsion, v.torsion, tid, nT, [&](const TermRec<4, 3>& rec) {
+      const double   fk = rec.q[0], cosTerm = rec.q[2];
+      const int      order = static_cast<int>(rec.q[1]);
+      const V3       r0 = ld<3>(pos, rec.ix[0]) - ld<3>(pos, rec.ix[1]), r1 = ld<3>(pos, rec.ix[2]) - ld<3>(pos, rec.ix[1]), r2 = -r1,
+               r3 = ld<3>(pos, rec.ix[3]) - ld<3>(pos, rec.ix[2]);
       V3           t0 = cross(r0, r1), t1 = cross(r2, r3);
       const double d0 = sqrt(dot(t0, t0)), d1 = sqrt(dot(t1, t1));
       if (!GRAD) {
@@ -657,24 +738,23 @@ struct Uff {
         const double dE = r * fk / 2.0 * cosTerm * -1.0 * static_cast<double>(order);
         const double sinTerm = dE * (isZero(sn) ? (1.0 / fmax(fabs(c), 1.0e-8)) : (1.0 / sn));
         const V3     a = (t1 - t0 * c) * (1.0 / d0), b = (t0 - t1 * c) * (1.0 / d1);
-        acc<3>(grad, ix[0], V3{a.z * r1.y - a.y * r1.z, a.x * r1.z - a.z * r1.x, a.y * r1.x - a.x * r1.y} * sinTerm);
-        acc<3>(grad, ix[1],
+        acc<3>(grad, rec.ix[0], V3{a.z * r1.y - a.y * r1.z, a.x * r1.z - a.z * r1.x, a.y * r1.x - a.x * r1.y} * sinTerm);
+        acc<3>(grad, rec.ix[1],
                V3{a.y * (r1.z - r0.z) + a.z * (r0.y - r1.y) + b.y * (-r3.z) + b.z * (r3.y),
                   a.x * (r0.z - r1.z) + a.z * (r1.x - r0.x) + b.x * (r3.z) + b.z * (-r3.x),
                   a.x * (r1.y - r0.y) + a.y * (r0.x - r1.x) + b.x * (-r3.y) + b.y * (r3.x)} * sinTerm);
-        acc<3>(grad, ix[2],
+        acc<3>(grad, rec.ix[2],
                V3{a.y * r0.z + a.z * (-r0.y) + b.y * (r3.z - r2.z) + b.z * (r2.y - r3.y),
                   a.x * (-r0.z) + a.z * r0.x + b.x * (r2.z - r3.z) + b.z * (r3.x - r2.x),
                   a.x * r0.y + a.y * (-r0.x) + b.x * (r3.y - r2.y) + b.y * (r2.x - r3.x)} * sinTerm);
-        acc<3>(grad, ix[3], V3{b.y * r2.z - b.z * r2.y, b.z * r2.x - b.x * r2.z, b.x * r2.y - b.y * r2.x} * sinTerm);
+        acc<3>(grad, rec.ix[3], V3{b.y * r2.z - b.z * r2.y, b.z * r2.x - b.x * r2.z, b.x * r2.y - b.y * r2.x} * sinTerm);
       }
     });
-    forTerms<GRAD>(s.inversion, v.inversion, tid, nT, [&](int t) {
-      const int16_t* ix = s.inversion.idx + 4 * t;
-      const double   fk = s.inversion.par[4 * t], C0 = s.inversion.par[4 * t + 1], C1 = s.inversion.par[4 * t + 2],
-                   C2 = s.inversion.par[4 * t + 3];
-      const V3     ji = ld<3>(pos, ix[0]) - ld<3>(pos, ix[1]), jk = ld<3>(pos, ix[2]) - ld<3>(pos, ix[1]),
-               jl = ld<3>(pos, ix[3]) - ld<3>(pos, ix[1]);
+    forTerms<GRAD, 4, 4>(s.inversion, v.inversion, tid, nT, [&](const TermRec<4, 4>& rec) {
+      const double   fk = rec.q[0], C0 = rec.q[1], C1 = rec.q[2],
+                   C2 = rec.q[3];
+      const V3     ji = ld<3>(pos, rec.ix[0]) - ld<3>(pos, rec.ix[1]), jk = ld<3>(pos, rec.ix[2]) - ld<3>(pos, rec.ix[1]),
+               jl = ld<3>(pos, rec.ix[3]) - ld<3>(pos, rec.ix[1]);
       const double l2i = dot(ji, ji), l2k = dot(jk, jk), l2l = dot(jl, jl);
       if (!GRAD) {
         double cosY = 0.0;
@@ -701,15 +781,15 @@ struct Uff {
         const V3     g1 = (t1 * (1.0 / term1) - (a - b * cT) * term2) * (1.0 / dI);
         const V3     g3 = (t2 * (1.0 / term1) - (b - a * cT) * term2) * (1.0 / dK);
         const V3     g4 = (t3 * (1.0 / term1) - c * (cY / sY)) * (1.0 / dL);
-        acc<3>(grad, ix[0], g1 * dE);
-        acc<3>(grad, ix[1], (g1 + g3 + g4) * (-dE));
-        acc<3>(grad, ix[2], g3 * dE);
-        acc<3>(grad, ix[3], g4 * dE);
+        acc<3>(grad, rec.ix[0], g1 * dE);
+        acc<3>(grad, rec.ix[1], (g1 + g3 + g4) * (-dE));
+        acc<3>(grad, rec.ix[2], g3 * dE);
+        acc<3>(grad, rec.ix[3], g4 * dE);
       }
     });
-    forTerms<GRAD>(s.vdw, v.vdw, tid, nT, [&](int t) {
-      const int    i = s.vdw.idx[2 * t], j = s.vdw.idx[2 * t + 1];
-      const double x = s.vdw.par[3 * t], eps = s.vdw.par[3 * t + 1], thr = s.vdw.par[3 * t + 2];
+    forTerms<GRAD, 2, 3>(s.vdw, v.vdw, tid, nT, [&](const TermRec<2, 3>& rec) {
+      const int    i = rec.ix[0], j = rec.ix[1];
+      const double x = rec.q[0], eps = rec.q[1], thr = rec.q[2];
       const V3     d    = ld<3>(pos, i) - ld<3>(pos, j);
       const double dist = sqrt(dot(d, d));
       if (dist > thr) return;

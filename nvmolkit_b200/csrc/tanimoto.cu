@@ -296,6 +296,7 @@ void launchTile(const CUtensorMap& tmX, const CUtensorMap& tmY, const TileParams
 
 bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s);
 extern int g_bfgsCtasPerSm;
+extern int g_bfgsL2Persist;
 extern int g_butinaMinCommits;
 extern int g_tensorFp4;
 extern int g_tensorCluster;
@@ -412,6 +413,7 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       B200_REQUIRE(value >= 1 && value <= 8, "bfgs_ctas_per_sm must be in [1, 8]");
       g_bfgsCtasPerSm = static_cast<int>(value);
     }
+    else if (k == "bfgs_l2_persist") g_bfgsL2Persist = value != 0;
     else if (k == "similarity_tensor_fp4") g_tensorFp4 = value != 0;
     else if (k == "similarity_tensor_cluster") {
       B200_REQUIRE(value >= 0 && value <= 3, "similarity_tensor_cluster must be 0, 1, 2 or 3");

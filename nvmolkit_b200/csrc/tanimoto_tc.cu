@@ -596,11 +596,38 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         // Pre-filter: the threshold grows with |A| + |B|, so c < thresh[|A| + min |B| of the tile] rules a pair out with
         // one compare; the exact table test (and the bounds / upper-triangle predicates) runs for the survivors only —
         // a handful per million pairs on fingerprint data.
+        // The common case is "no survivor in these 32 columns": a max tree (31 independent-ish min/max instructions, depth
+        // 5) and ONE compare decide it. Building the bit mask directly was a chain of 32 dependent compare-select-or
+        // triples per block; with two epilogue warps per scheduler nothing hides that latency, and ~1,100 instructions
+        // per warp and tile at one issue every ~7 clocks made the epilogue, not the MMA, pace the tile
+        // (profiles/r02_path_a_summary.md).
         uint32_t maybe = 0;
+        bool     hot;
+        if constexpr (FP4) {
+          float m[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if constexpr (FP4) maybe |= (__uint_as_float(r[j]) >= fThMin ? 1u : 0u) << j;
-          else maybe |= (static_cast<int>(r[j]) >= thMin ? 1u : 0u) << j;
+          for (int j = 0; j < 16; ++j) m[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 16]));
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+            for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
+          hot = m[0] >= fThMin;
+        } else {
+          int m[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = max(static_cast<int>(r[j]), static_cast<int>(r[j + 16]));
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+            for (int j = 0; j < w; ++j) m[j] = max(m[j], m[j + w]);
+          hot = m[0] >= thMin;
+        }
+        if (hot) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if constexpr (FP4) maybe |= (__uint_as_float(r[j]) >= fThMin ? 1u : 0u) << j;
+            else maybe |= (static_cast<int>(r[j]) >= thMin ? 1u : 0u) << j;
+          }
         }
         uint32_t mask = 0;
         while (maybe) {

@@ -10,8 +10,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-out = os.path.join(ROOT, "nvmolkit_b200", "lib", "libb200mol_timing.so")
-subprocess.run(["make", "-C", os.path.join(ROOT, "nvmolkit_b200", "csrc"), "-j", "8", "-s", "timing"], check=True)
+out = os.environ.get("B200_TIMING_LIB") or os.path.join(ROOT, "nvmolkit_b200", "lib", "libb200mol_timing.so")
+if not os.environ.get("B200_TIMING_LIB"):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "nvmolkit_b200", "csrc"), "-j", "8", "-s", "timing"], check=True)
 from nvmolkit_b200 import _lib  # noqa: E402
 
 _lib.LIB_PATH = out
@@ -26,6 +27,8 @@ torch.cuda.set_device(0)
 _lib.profile_enable(True)
 if len(sys.argv) > 3:
     _lib.set_option("bfgs_ctas_per_sm", int(sys.argv[3]))
+if os.environ.get("B200_L2_PERSIST"):
+    _lib.set_option("bfgs_l2_persist", 1)
 L = _lib.load()
 buf = (C.c_ulonglong * 8)()
 leg = bench.ConformerLeg(pool[0], pool[1], torch.device("cuda", 0), 1, 0)
