@@ -385,6 +385,23 @@ int b200mol_metric_embed(double* d_dist, const int64_t* d_matrix_starts, const i
                          int dim, const double* d_v0, const int64_t* d_v0_starts, uint32_t seed, double* d_coords,
                          int8_t* d_ok, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU result exchange (one process per GPU, NCCL over NVLink / NVSwitch): the single collective at the end of a
+ * molecule-range-sharded conformer job. `nccl_comm` is the caller's ncclComm_t. NCCL is resolved at run time from the
+ * library already loaded in the process (or libnccl.so.2), never linked. Replaces DeviceCoordCollector::finalizeOnTarget
+ * + copyDeviceToDeviceAsync (src/conformer/device_coord_collector.cpp:30-145, src/utils/p2p.cpp:56-86): every rank ends
+ * up with the whole CSR result instead of one target GPU.
+ * Step 1: conformer / atom counts of every rank to the host (h_*[world]); synchronises `stream`. */
+int b200mol_allgather_counts(void* nccl_comm, int64_t n_conf_local, int64_t n_atoms_local, int64_t* h_conf_counts,
+                             int64_t* h_atom_counts, void* stream);
+/* Step 2: the payload, rank-major, exact sizes (one ncclBroadcast per rank and array inside one group):
+ *   d_positions[sum atoms][3] f64, d_conf_atoms[sum conf] i32 (atoms per conformer), d_energy[sum conf] f64,
+ *   d_converged[sum conf] i8. Any of the four output arrays may be NULL (skipped on every rank alike). Asynchronous. */
+int b200mol_allgather_results(void* nccl_comm, const int64_t* h_conf_counts, const int64_t* h_atom_counts,
+                              const double* d_positions_local, const int32_t* d_conf_atoms_local, const double* d_energy_local,
+                              const int8_t* d_converged_local, double* d_positions, int32_t* d_conf_atoms, double* d_energy,
+                              int8_t* d_converged, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

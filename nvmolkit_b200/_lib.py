@@ -61,6 +61,8 @@ SIGNATURES = {
     "b200mol_schedule_waves": (C.c_int, [C.c_int32, _vp, _vp, C.c_int, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "b200mol_dg_terms_from_bounds": (C.c_int, [C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mol_etk_terms_from_details": (C.c_int, [C.c_int32, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "b200mol_allgather_counts": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "b200mol_allgather_results": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mol_morgan": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                                  _vp]),
 }

@@ -93,7 +93,7 @@ __device__ __forceinline__ void loadTerm(const b200mol_term_table& T, int t, Ter
 // (a molecule's tables are 70-120 KB and ten thousand molecules do not fit L2), and a load-then-use loop paid that
 // latency once per term and thread - it, not the arithmetic, set the evaluation time (profiles/r02_path_b_summary.md).
 #ifndef B200_TERM_PREFETCH
-#define B200_TERM_PREFETCH 1  // 0 = load-then-use; 1 = prefetch.global.L1 of the next record; 2 = next record in registers
+#define B200_TERM_PREFETCH 0  // 0 = load-then-use (default: neither prefetch form paid on B200, profiles/r02_path_b_summary.md); 1 = prefetch.global.L1 of the next record; 2 = next record in registers
 #endif
 template <int K, int P>
 __device__ __forceinline__ void prefetchTerm(const b200mol_term_table& T, int t) {

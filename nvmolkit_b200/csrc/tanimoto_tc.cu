@@ -69,6 +69,17 @@ enum TcMode : int { kTcCount = 0, kTcTanimoto = 1, kTcCosine = 2 };
 int g_tensorCluster = 1;  // fp4 count tile in clusters of two CTAs with a multicast column operand (option "similarity_tensor_cluster")
 int g_tensorFp4 = 1;  // count mode on block-scaled fp4 operands (option "similarity_tensor_fp4"; 0 = int8 tile)
 namespace {
+#ifdef B200_TC_TIMING
+// clock64() attribution of the count tile: [0] MMA thread total, [1] its wait for operands (fullBar / aFull), [2] its wait for a
+// free accumulator (tmemEmpty), [3] epilogue warp 0 total, [4] its wait for a finished accumulator (tmemFull), [5] its
+// staging barrier, [6] tiles (MMA thread), [7] producer wait for a free stage
+__device__ unsigned long long g_tcClk[8];
+#define TC_T0() const long long tc0_ = clock64()
+#define TC_T1(slot) tcAcc[slot] += clock64() - tc0_
+#else
+#define TC_T0()
+#define TC_T1(slot)
+#endif
 
 __global__ void expandBitsKernel(const uint32_t* __restrict__ fp, size_t nWords, uint4* __restrict__ out) {
   const size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -392,6 +403,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+#ifdef B200_TC_TIMING
+      long long tcAcc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
       int      stage = 0;
       uint32_t phase = 0;
       uint32_t aPhase = 0;
@@ -407,7 +421,11 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
               tmaLoad2D(smemRaw + (smemA - smemAddr(smemRaw)) + kc * kABytes, &tmA, kc * kTK, tm * kTM, &aFull[kc]);
             }
           }
-          mbarWait(&emptyBar[stage], phase ^ 1);
+          {
+            TC_T0();
+            mbarWait(&emptyBar[stage], phase ^ 1);
+            TC_T1(7);
+          }
           uint8_t* dst = smemGen + stage * kStageBytes;
           if constexpr (P2) {
             // both CTAs' loads are counted on the LEADER's barrier (it alone issues the MMAs); each CTA stages its own
@@ -441,10 +459,17 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         }
         aPhase ^= 1;
       }
+#ifdef B200_TC_TIMING
+      atomicAdd(&g_tcClk[7], static_cast<unsigned long long>(tcAcc[7]));
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && !(P2 && rank != 0)) {  // (pair MMA: the leader issues for both CTAs)
+#ifdef B200_TC_TIMING
+      long long       tcAcc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long tcStart  = clock64();
+#endif
       int      stage = 0;
       uint32_t phase = 0, local = 0;
       uint32_t aPhase = 0;
@@ -453,14 +478,22 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         if (!w.coords(p, rank, tm, tnBeg, tnEnd)) continue;
         for (uint32_t tn = tnBeg; tn < tnEnd; ++tn) {
         const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
-        mbarWait(&tmemEmpty[as], accPhase ^ 1);
+        {
+          TC_T0();
+          mbarWait(&tmemEmpty[as], accPhase ^ 1);
+          TC_T1(2);
+        }
         tcFenceAfter();
         const uint32_t dAddr = tmem + as * TN;
         for (int kc = 0; kc < p.kChunks; ++kc) {
-          if constexpr (ST) {
-            if (tn == tnBeg) mbarWait(&aFull[kc], aPhase);
+          {
+            TC_T0();
+            if constexpr (ST) {
+              if (tn == tnBeg) mbarWait(&aFull[kc], aPhase);
+            }
+            mbarWait(&fullBar[stage], phase);
+            TC_T1(1);
           }
-          mbarWait(&fullBar[stage], phase);
           tcFenceAfter();
           const uint32_t sAddr = smemBase + stage * kStageBytes;
           const uint64_t aDesc = makeSmemDesc(ST ? smemA + kc * kABytes : sAddr), bDesc = makeSmemDesc(ST ? sAddr : sAddr + kABytes);
@@ -488,6 +521,12 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         }
         aPhase ^= 1;
       }
+#ifdef B200_TC_TIMING
+      atomicAdd(&g_tcClk[0], static_cast<unsigned long long>(clock64() - tcStart));
+      atomicAdd(&g_tcClk[1], static_cast<unsigned long long>(tcAcc[1]));
+      atomicAdd(&g_tcClk[2], static_cast<unsigned long long>(tcAcc[2]));
+      atomicAdd(&g_tcClk[6], static_cast<unsigned long long>(local));
+#endif
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -497,6 +536,10 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     const int      et      = ew * 32 + lane;       // thread index among the epilogue warps
     uint32_t       local   = 0;
     uint32_t       tnOf[2] = {0, 0};  // tile column each accumulator-side buffer last served
+#ifdef B200_TC_TIMING
+    long long       tcAcc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tcStart  = clock64();
+#endif
     for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
       uint32_t tm, tnBeg, tnEnd;
       if (!w.coords(p, rank, tm, tnBeg, tnEnd)) continue;
@@ -527,7 +570,11 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         const uint32_t ga = tm * kTM + et;
         popA[as][et]      = ga < p.n ? __ldg(p.popX + ga) : 0;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      {
+        TC_T0();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        TC_T1(5);
+      }
       const uint32_t gr = tm * kTM + quarter * 32 + lane;
       const int      pa = gr < p.n ? __ldg(p.popX + gr) : 0;
       int thMin = 0;
@@ -539,7 +586,11 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       }
       const float fThMin = static_cast<float>(thMin);
       (void)fThMin;
-      mbarWait(&tmemFull[as], accPhase);
+      {
+        TC_T0();
+        mbarWait(&tmemFull[as], accPhase);
+        TC_T1(4);
+      }
       tcFenceAfter();
       int rowHits = 0;
       constexpr int kCb = TN / 32, kCbPer = (kCb + kParts - 1) / kParts;  // column blocks of 32; the warps of a quarter split them
@@ -688,6 +739,13 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       ++local;
       }
     }
+#ifdef B200_TC_TIMING
+    if (ew == 0 && lane == 0) {
+      atomicAdd(&g_tcClk[3], static_cast<unsigned long long>(clock64() - tcStart));
+      atomicAdd(&g_tcClk[4], static_cast<unsigned long long>(tcAcc[4]));
+      atomicAdd(&g_tcClk[5], static_cast<unsigned long long>(tcAcc[5]));
+    }
+#endif
     if (MODE == kTcCount && p.countsY) {  // the last two tiles' column counts
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       for (uint32_t back = 1; back <= 2 && back <= local; ++back) {
@@ -715,6 +773,15 @@ void launchRowPopcount(const uint32_t* fp, size_t n, int words, int32_t* pop, cu
 void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s);
 
 // Count / materialise modes on tensor cores. Returns false when the problem shape is not eligible (caller uses the SIMT tile).
+#ifdef B200_TC_TIMING
+extern "C" void b200mol_debug_clocks_tc(unsigned long long* out8) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_tcClk, sizeof(g_tcClk));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_tcClk, z, sizeof(z));
+}
+#endif
+
 bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   if (mode == kCountCosine) return false;
   const int bits = q.words * 32;
