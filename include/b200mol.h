@@ -49,11 +49,17 @@ int b200mol_free_async(void* d_ptr, void* stream);
  *                                  CTA stages half of the column operand); 3: CTA pairs with the multicast column operand
  *                                  and the ROW operand stationary in shared memory for a run of 16 tile columns
  *                                  (fingerprints up to 2048 bits; half the L2 -> SM bytes per pair); 0: one CTA per tile
+ *   "similarity_superpose"         4 (default), 2 or 1: fingerprints summed into one row operand of the Butina neighbour pass
+ *                                  (values 0..4 are exact in fp4): one accumulator then bounds that many pair counts, the
+ *                                  few survivors are re-examined exactly by a second kernel; 1 = off
  *   "butina_min_round_commits"     a parallel Butina round that commits fewer clusters than this hands over to the
  *                                  one-cluster-per-step loop (default 32; 0 = rounds only, >= 1e9 = stepwise only)
  *   "bfgs_ctas_per_sm"             resident CTAs per SM of the minimiser / embedder kernels (default 3 = the register
  *                                  budget they are compiled for) */
 int b200mol_set_option(const char* key, long long value);
+/* Current value of an option; also "similarity_superpose_last": the factor the last neighbour pass really ran with
+ * (1 after a candidate-list overflow made it fall back). */
+int b200mol_get_option(const char* key, long long* value);
 /* Per-phase CUDA-event timing inside the library (off by default). Phases: "neighbor_pass" (the N^2 tile kernel
  * alone), "csr_build", "cluster_loop", "bfgs". b200mol_profile_read waits for the phase's stop event. */
 int b200mol_profile_enable(int on);

@@ -7,6 +7,11 @@ import numpy as np
 
 def rows_of(starts: np.ndarray, order: np.ndarray) -> np.ndarray:
     """Concatenation of arange(starts[c], starts[c+1]) for c in `order` (CSR row gather), int64."""
+    from nvmolkit_b200 import _lib
+
+    mod = _lib.core()
+    if mod is not None:
+        return mod.rows_of(np.ascontiguousarray(starts, dtype=np.int64), np.ascontiguousarray(order, dtype=np.int64))
     starts = np.asarray(starts, dtype=np.int64)
     order = np.asarray(order, dtype=np.int64)
     sizes = starts[order + 1] - starts[order]
@@ -19,6 +24,11 @@ def rows_of(starts: np.ndarray, order: np.ndarray) -> np.ndarray:
 
 def running_index(keys: np.ndarray) -> np.ndarray:
     """k-th occurrence number of each key, in order of appearance (conformer index within its molecule), int32."""
+    from nvmolkit_b200 import _lib
+
+    mod = _lib.core()
+    if mod is not None:
+        return mod.running_index(np.ascontiguousarray(keys, dtype=np.int64))
     keys = np.asarray(keys)
     n = len(keys)
     if n == 0:

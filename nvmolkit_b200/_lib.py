@@ -25,6 +25,7 @@ SIGNATURES = {
     "b200mol_check_device": (C.c_int, [C.c_int]),
     "b200mol_free_async": (C.c_int, [_vp, _vp]),
     "b200mol_set_option": (C.c_int, [C.c_char_p, C.c_longlong]),
+    "b200mol_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_longlong)]),
     "b200mol_profile_enable": (C.c_int, [C.c_int]),
     "b200mol_profile_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_float)]),
     "b200mol_stats_read": (C.c_int, [_vp, C.c_int, _vp]),
@@ -101,7 +102,52 @@ def check(status: int) -> None:
     raise B200MolError(msg)
 
 
+_core = None
+_core_tried = False
+
+
+def core():
+    """The pybind11 host module nvmolkit_b200._core (C++ glue over the same C-ABI, built by `make pymodule`): native calls
+    go through it so that the GIL is released while a kernel launch / synchronisation is in progress. None when it has not
+    been built (the ctypes binding below then makes the calls itself, holding the GIL like the reference does)."""
+    global _core, _core_tried
+    if not _core_tried:
+        _core_tried = True
+        try:
+            from nvmolkit_b200 import _core as mod  # noqa: PLC0415
+
+            if mod.abi_version() == load().b200mol_abi_version():
+                _core = mod
+        except ImportError:
+            _core = None
+    return _core
+
+
+def _plain(a):
+    """ctypes argument -> what the pybind11 signatures take (addresses as integers)."""
+    if a is None:
+        return 0
+    if isinstance(a, (int, float, str)):
+        return a
+    if isinstance(a, bytes):
+        return a.decode()
+    if isinstance(a, C._SimpleCData):
+        return a.value or 0
+    if hasattr(a, "_obj"):  # ctypes.byref(x)
+        return C.addressof(a._obj)
+    if isinstance(a, (C.Structure, C.Array)):
+        return C.addressof(a)
+    raise TypeError(f"cannot pass {type(a).__name__} to the native library")
+
+
 def call(name: str, *args) -> None:
+    mod = core()
+    if mod is not None and hasattr(mod, name):
+        try:
+            getattr(mod, name)(*[_plain(a) for a in args])
+        except mod.B200MolError as e:
+            raise B200MolError(str(e)) from None
+        return
     check(getattr(load(), name)(*args))
 
 
@@ -117,6 +163,12 @@ def profile_read(phase: str) -> float:
     ms = C.c_float(0.0)
     check(load().b200mol_profile_read(phase.encode(), C.byref(ms)))
     return float(ms.value)
+
+
+def get_option(key: str) -> int:
+    v = C.c_longlong(0)
+    check(load().b200mol_get_option(key.encode(), C.byref(v)))
+    return int(v.value)
 
 
 def stats_read(reset: bool = True) -> dict:

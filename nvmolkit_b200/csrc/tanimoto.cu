@@ -300,6 +300,8 @@ extern int g_bfgsL2Persist;
 extern int g_butinaMinCommits;
 extern int g_tensorFp4;
 extern int g_tensorCluster;
+extern int g_superpose;
+extern int g_superposeLast;
 long long g_tensorMinPairs = 1ll << 24;  // pair count from which the count mode runs on tcgen05 (< 0: never)
 
 void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s) {
@@ -414,6 +416,10 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       g_bfgsCtasPerSm = static_cast<int>(value);
     }
     else if (k == "bfgs_l2_persist") g_bfgsL2Persist = value != 0;
+    else if (k == "similarity_superpose") {
+      B200_REQUIRE(value == 1 || value == 2 || value == 4, "similarity_superpose must be 1, 2 or 4");
+      g_superpose = static_cast<int>(value);
+    }
     else if (k == "similarity_tensor_fp4") g_tensorFp4 = value != 0;
     else if (k == "similarity_tensor_cluster") {
       B200_REQUIRE(value >= 0 && value <= 3, "similarity_tensor_cluster must be 0, 1, 2 or 3");
@@ -423,6 +429,22 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       B200_REQUIRE(value >= 0, "butina_min_round_commits must be >= 0");
       g_butinaMinCommits = static_cast<int>(value > 1000000000 ? 1000000000 : value);  // huge = stepwise loop only
     }
+    else fail(B200MOL_ERR_INVALID, "unknown option '%s'", key);
+  });
+}
+
+extern "C" int b200mol_get_option(const char* key, long long* value) {
+  return guarded([&] {
+    B200_REQUIRE(key && value, "null pointer");
+    const std::string k(key);
+    if (k == "similarity_tensor_min_pairs") *value = g_tensorMinPairs;
+    else if (k == "bfgs_ctas_per_sm") *value = g_bfgsCtasPerSm;
+    else if (k == "bfgs_l2_persist") *value = g_bfgsL2Persist;
+    else if (k == "similarity_tensor_fp4") *value = g_tensorFp4;
+    else if (k == "similarity_tensor_cluster") *value = g_tensorCluster;
+    else if (k == "similarity_superpose") *value = g_superpose;
+    else if (k == "similarity_superpose_last") *value = g_superposeLast;  // read-only: the factor the last pass ran with
+    else if (k == "butina_min_round_commits") *value = g_butinaMinCommits;
     else fail(B200MOL_ERR_INVALID, "unknown option '%s'", key);
   });
 }

@@ -35,10 +35,9 @@ constexpr int kEpiWarpsMat   = 16;  // materialise modes: four per quarter (the 
 constexpr int epiWarps(int mode) { return mode == 0 ? kEpiWarpsCount : kEpiWarpsMat; }
 constexpr int threadsTC(int mode) { return 64 + 32 * epiWarps(mode); }  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kABytes   = kTM * kTK;
-constexpr int kBBytes   = kTN * kTK;
 constexpr int kTNFp4    = 224;  // fp4 count mode: 2 x 224 accumulator columns leave TMEM columns 448..511 for the scale factors
-constexpr int kGroupTC  = 16;  // tile rows per L2 reuse group
-constexpr int kGroupStat = 64;  // the same for the A-stationary tile: 32 CTA pairs stream one column chunk together
+constexpr int kGroupRows = 8192;  // fingerprints per row group: the unit of L2 reuse of the column operand AND of the
+                                  // multi-GPU row split (independent of the tile variant and of the superposition factor)
 constexpr int kRunStat   = 16;  // tile columns per unit of the A-stationary tile (the row operand is loaded once per unit)
 constexpr int kStagesStat = 3;  // its ring holds the column operand only (28 KB per stage, next to 128 KB of row operand)
 constexpr int kMaxChunksStat = 8;  // row operand resident in shared memory: 8 K-chunks x 16 KB (fingerprints <= 2048 bits)
@@ -62,6 +61,16 @@ struct TcParams {
   unsigned long long  edgeCap;
   double*         out;  // materialise modes: [n][nY] fp64
   int             recipLen;  // 2 * bits (materialise Tanimoto)
+  // Row superposition (count mode): a row of the X operand is the SUM of superS consecutive fingerprints (values 0..4,
+  // exact in E2M1), so one accumulator bounds superS pair counts at once; n / tilesM then count SUPER rows, popX holds
+  // the smallest popcount of each super row, and the epilogue only lists candidates (super row, column) for the exact
+  // verification kernel. rowSpan = fingerprints per tile row = kTM * superS.
+  int                 superS;
+  uint32_t            rowSpan;
+  uint32_t            groupTiles;  // tile rows per row group (a power of two): kGroupRows fingerprints whatever superS is
+  int2*               cand;
+  unsigned long long* candCursor;
+  unsigned long long  candCap;
 };
 
 enum TcMode : int { kTcCount = 0, kTcTanimoto = 1, kTcCosine = 2 };
@@ -111,6 +120,101 @@ __global__ void expandBitsFp4Kernel(const uint32_t* __restrict__ fp, size_t nWor
     b[q]       = v << 1;
   }
   out[w] = make_uint4(b[0], b[1], b[2], b[3]);
+}
+
+// Superposed row operand: fp4 row R = sum over s < S of the 0/1 expansions of fingerprints S R + s (0..4 -> E2M1 codes
+// 0x0 0x2 0x4 0x5 0x6, all exact). One thread per 32 fingerprint bits.
+__global__ void expandBitsFp4SuperKernel(const uint32_t* __restrict__ fp, size_t n, int words, int S, size_t nSuper,
+                                         uint4* __restrict__ out) {
+  const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= nSuper * static_cast<size_t>(words)) return;
+  const size_t R = t / words;
+  const int    w = static_cast<int>(t % words);
+  uint32_t     b[4] = {0, 0, 0, 0};  // 8 nibble counters each
+  for (int s = 0; s < S; ++s) {
+    const size_t i = R * S + s;
+    if (i >= n) break;
+    const uint32_t x = fp[i * words + w];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v = (x >> (8 * q)) & 0xFFu;
+      v          = (v | (v << 12)) & 0x000F000Fu;
+      v          = (v | (v << 6)) & 0x03030303u;
+      v          = (v | (v << 3)) & 0x11111111u;
+      b[q] += v;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t code = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) code |= ((0x65420u >> (4 * ((b[q] >> (4 * k)) & 0xFu))) & 0xFu) << (4 * k);
+    b[q] = code;
+  }
+  out[t] = make_uint4(b[0], b[1], b[2], b[3]);
+}
+
+// smallest popcount among the fingerprints of each super row (the epilogue's conservative pre-filter needs the lowest
+// threshold any pair of the group can have)
+__global__ void superMinPopKernel(const int32_t* __restrict__ pop, size_t n, int S, size_t nSuper, int32_t* __restrict__ out) {
+  const size_t R = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (R >= nSuper) return;
+  int m = 0x3fffffff;
+  for (int s = 0; s < S; ++s)
+    if (R * S + s < n) m = min(m, pop[R * S + s]);
+  out[R] = m;
+}
+
+// Exact verification of the candidates of a superposed pass: one warp per (super row R, column j), for each fingerprint
+// i = S R + s of the group the exact count |X_i & Y_j| and the exact integer threshold test; counts for both endpoints
+// and the (i < j) edge list exactly as the unsuperposed epilogue produces them. A CTA gathers the edges of its 8
+// candidates in shared memory and reserves their slots with ONE atomic.
+__global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ y, int words,
+                                                             const int2* __restrict__ cand, unsigned long long nCand, int S,
+                                                             uint32_t nRows, int symmetric, const int32_t* __restrict__ popX,
+                                                             const int32_t* __restrict__ popY, const uint16_t* __restrict__ thresh,
+                                                             int sign, int32_t* counts, int32_t* countsY, int2* edges,
+                                                             unsigned long long* edgeCursor, unsigned long long edgeCap) {
+  __shared__ int2               hit[8 * 4];
+  __shared__ int                nHit;
+  __shared__ unsigned long long base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned long long c0 = static_cast<unsigned long long>(blockIdx.x) * 8; c0 < nCand; c0 += static_cast<unsigned long long>(gridDim.x) * 8) {
+    if (threadIdx.x == 0) nHit = 0;
+    __syncthreads();
+    const unsigned long long c = c0 + warp;
+    if (c < nCand) {
+      const int2      rj = cand[c];
+      const uint32_t  j  = static_cast<uint32_t>(rj.y);
+      const uint32_t* yj = y + static_cast<size_t>(j) * words;
+      uint32_t        yw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) yw[k] = lane + 32 * k < words ? yj[lane + 32 * k] : 0u;
+      for (int s = 0; s < S; ++s) {
+        const uint32_t i = static_cast<uint32_t>(rj.x) * S + s;
+        if (i >= nRows || (symmetric && i >= j)) continue;
+        const uint32_t* xi = x + static_cast<size_t>(i) * words;
+        int             cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k < words) cnt += __popc(xi[lane + 32 * k] & yw[k]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && cnt >= thresh[popX[i] + popY[j]]) {
+          atomicAdd(counts + i, sign);
+          if (countsY) atomicAdd(countsY + j, sign);
+          if (edges) hit[atomicAdd(&nHit, 1)] = make_int2(static_cast<int>(i), static_cast<int>(j));
+        }
+      }
+    }
+    __syncthreads();
+    if (edges && nHit) {
+      if (threadIdx.x == 0) base = atomicAdd(edgeCursor, static_cast<unsigned long long>(nHit));
+      __syncthreads();
+      if (threadIdx.x < nHit && base + threadIdx.x < edgeCap) edges[base + threadIdx.x] = hit[threadIdx.x];
+    }
+    __syncthreads();
+  }
 }
 
 // lo[S] = min(thresh[S..len-1]): the threshold table need not be monotone (cutoff 0 admits only even |A|+|B|), its
@@ -216,8 +320,8 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // Work units. A unit = one tile (CL = 0) or two vertically adjacent tiles of one tile column (CTA pairs: unit row r
-// holds tile rows 2 r and 2 r + 1, the two CTAs share the column operand). Unit rows come in groups of G (= kGroupTC
-// tile rows), a group sweeps the tile columns row-fastest (L2 reuse of the row operand). Only units that can hold a pair
+// holds tile rows 2 r and 2 r + 1, the two CTAs share the column operand). Unit rows come in groups of G (p.groupTiles
+// tile rows = kGroupRows fingerprints), a group sweeps the tile columns row-fastest (L2 reuse of the row operand). Only units that can hold a pair
 // are enumerated: a rank walks the groups it OWNS, and a group starts at the first tile column that reaches past the
 // diagonal for its top tile row (closed form), so that neither the other ranks' groups nor the lower triangle cost
 // loop iterations (round 1 walked all of them: 215 ns per skipped unit, the 1 -> 8 GPU limiter).
@@ -229,12 +333,14 @@ __device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
 // operand is loaded once per unit and stays in shared memory - and the units of a group go chunk-major (all rows of the
 // group take column chunk q, then q + 1): the CTA pairs of a group stream the same column tiles at about the same time,
 // so a column tile comes from HBM once per group and from L2 for the other rows.
-template <int TN, bool PAIR, int RUN = 1, int GROUPTC = kGroupTC>
+template <int TN, bool PAIR, int RUN = 1>
 struct UnitWalk {
-  static constexpr uint32_t G = PAIR ? GROUPTC / 2 : GROUPTC;
-  uint32_t cycle, inGroup, units, gRows, tn0, group, step;
+  uint32_t cycle, inGroup, units, gRows, tn0, group, step, G, gShift;
   bool     done;
-  __device__ UnitWalk(const TcParams& p, uint32_t first, uint32_t stepBy) : cycle(0), inGroup(first), units(0), gRows(G), tn0(0), group(0), step(stepBy), done(false) {
+  __device__ UnitWalk(const TcParams& p, uint32_t first, uint32_t stepBy)
+      : cycle(0), inGroup(first), units(0), gRows(0), tn0(0), group(0), step(stepBy), G(PAIR ? p.groupTiles / 2 : p.groupTiles),
+        gShift(0), done(false) {
+    while ((1u << gShift) < G) ++gShift;  // G is a power of two
     settle(p);
   }
   __device__ void settle(const TcParams& p) {  // make (cycle, inGroup) point at an existing unit, or set done
@@ -248,9 +354,9 @@ struct UnitWalk {
       units = 0;
       if (group * G < unitRows) {
         gRows = min(G, unitRows - group * G);
-        // first tile column holding a pair with row < col for the group's top tile row tm0 = group * GROUPTC:
-        // (tn + 1) * TN - 1 > tm0 * kTM
-        tn0   = p.symmetric ? (group * static_cast<uint32_t>(GROUPTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
+        // first tile column holding a pair with row < col for the group's top tile row tm0 = group * groupTiles:
+        // (tn + 1) * TN - 1 > tm0 * rowSpan   (rowSpan = fingerprints per tile row)
+        tn0   = p.symmetric ? (group * p.groupTiles * p.rowSpan + 1u) / static_cast<uint32_t>(TN) : 0u;
         if (tn0 < p.tilesN) units = gRows * ((p.tilesN - tn0 + RUN - 1) / RUN);
       }
       if (inGroup < units) return;
@@ -270,8 +376,8 @@ struct UnitWalk {
   __device__ bool coords(const TcParams& p, uint32_t rank, uint32_t& tm, uint32_t& tnBeg, uint32_t& tnEnd) const {
     uint32_t row, col;
     if (gRows == G) {
-      row = inGroup % G;  // G is a power of two
-      col = inGroup / G;
+      row = inGroup & (G - 1);  // G is a power of two
+      col = inGroup >> gShift;
     } else {  // the last, partial group
       row = inGroup % gRows;
       col = inGroup / gRows;
@@ -282,8 +388,8 @@ struct UnitWalk {
     const uint32_t top = PAIR ? 2 * tr : tr;
     // the upper tile decides for both CTAs of a pair (if it has no pair with row < col, neither has the lower one); a
     // lower tile past the end or below the diagonal still runs - its loads are zero-filled / its predicates reject all.
-    // A tile column is useful iff (tn + 1) * TN - 1 > top * kTM: monotone in tn, so a run is clipped from the left.
-    if (p.symmetric) tnBeg = max(tnBeg, (top * static_cast<uint32_t>(kTM) + 1u) / static_cast<uint32_t>(TN));
+    // A tile column is useful iff (tn + 1) * TN - 1 > top * rowSpan: monotone in tn, so a run is clipped from the left.
+    if (p.symmetric) tnBeg = max(tnBeg, (top * p.rowSpan + 1u) / static_cast<uint32_t>(TN));
     if (tnBeg >= tnEnd) return false;
     tm = top + (PAIR ? rank : 0u);
     return true;
@@ -291,16 +397,16 @@ struct UnitWalk {
 };
 
 // host twin of the walk's unit count (sizes the grid)
-template <int TN, bool PAIR, int RUN = 1, int GROUPTC = kGroupTC>
+template <int TN, bool PAIR, int RUN = 1>
 uint64_t countUnits(const TcParams& p) {
-  constexpr uint32_t G = PAIR ? GROUPTC / 2 : GROUPTC;
-  const uint32_t     unitRows = PAIR ? (p.tilesM + 1) / 2 : p.tilesM;
-  uint64_t           total = 0;
+  const uint32_t G        = PAIR ? p.groupTiles / 2 : p.groupTiles;
+  const uint32_t unitRows = PAIR ? (p.tilesM + 1) / 2 : p.tilesM;
+  uint64_t       total    = 0;
   for (uint32_t cycle = 0; cycle * p.groupStride * G < unitRows; ++cycle) {
     const uint32_t group = cycle * p.groupStride + ((cycle & 1u) ? p.groupStride - 1 - p.groupOffset : p.groupOffset);
     if (group * G >= unitRows) continue;
     const uint32_t gRows = std::min(G, unitRows - group * G);
-    const uint32_t tn0   = p.symmetric ? (group * static_cast<uint32_t>(GROUPTC * kTM) + 1u) / static_cast<uint32_t>(TN) : 0u;
+    const uint32_t tn0   = p.symmetric ? (group * p.groupTiles * p.rowSpan + 1u) / static_cast<uint32_t>(TN) : 0u;
     if (tn0 < p.tilesN) total += static_cast<uint64_t>(gRows) * ((p.tilesN - tn0 + RUN - 1) / RUN);
   }
   return total;
@@ -326,7 +432,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   const uint32_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
   constexpr bool P2          = CL == 2;
   constexpr bool ST          = CL == 3;  // row operand stationary
-  using Walk                 = UnitWalk<TN, CL != 0, ST ? kRunStat : 1, ST ? kGroupStat : kGroupTC>;
+  using Walk                 = UnitWalk<TN, CL != 0, ST ? kRunStat : 1>;
   constexpr int  kBStage     = P2 ? kBBytes / 2 : kBBytes;  // bytes of the column operand one CTA stages per K chunk
   constexpr int  kStageBytes = ST ? kBStage : kABytes + kBStage;
   constexpr int  kStagesTC   = ST ? kStagesStat : (P2 ? kStagesPair : (MODE == kTcCount ? kStagesCount : kStagesMat));
@@ -681,6 +787,37 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
           }
         }
         uint32_t mask = 0;
+        if (p.superS > 1) {
+          // superposed rows: the accumulator is the SUM of superS pair counts, so "sum < smallest threshold of the group"
+          // rejected all of them above; what is left goes to the exact verification kernel as (super row, column)
+          while (maybe) {
+            const int j = __ffs(maybe) - 1;
+            maybe &= maybe - 1;
+            const uint32_t gc = tn * TN + cb * 32 + j;
+            if (gr < p.n && gc < p.nY && (!p.symmetric || gr * static_cast<uint32_t>(p.superS) < gc)) mask |= 1u << j;
+          }
+          if (__ballot_sync(0xffffffffu, mask != 0)) {
+            const int mine = __popc(mask);
+            int       incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            const int          total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned long long base  = 0;
+            if (lane == 31) base = atomicAdd(p.candCursor, static_cast<unsigned long long>(total));
+            base                  = __shfl_sync(0xffffffffu, base, 31);
+            unsigned long long at = base + incl - mine;
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              if (at < p.candCap) p.cand[at] = make_int2(static_cast<int>(gr), static_cast<int>(tn * TN + cb * 32 + j));
+              ++at;
+            }
+          }
+          continue;
+        }
         while (maybe) {
           const int j = __ffs(maybe) - 1;
           maybe &= maybe - 1;
@@ -782,7 +919,28 @@ extern "C" void b200mol_debug_clocks_tc(unsigned long long* out8) {
 }
 #endif
 
+int g_superpose = 4;  // fingerprints summed into one row of the count pass (option "similarity_superpose": 1, 2 or 4)
+int g_superposeLast = 0;  // what the last tensor count pass really ran with (1 after an overflow fallback); b200mol_get_option
+
+static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, int superS, bool* overflow);
+
+// Count / materialise modes on tensor cores. Returns false when the problem shape is not eligible (caller uses the SIMT tile).
 bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
+  // Row superposition serves the Butina passes (symmetric and / or with an edge list): they synchronise for their edge
+  // total anyway, and the superposed pass needs one host read of its candidate count. The plain thresholded count
+  // (b200mol_tanimoto_count_ge) stays asynchronous on the unsuperposed tile.
+  const bool graphPass = mode == kCountTanimoto && (q.symmetric || q.edges != nullptr);
+  if (graphPass && g_superpose > 1) {
+    bool overflow = false;
+    if (!launchTensorImpl(mode, q, s, g_superpose, &overflow)) return false;
+    g_superposeLast = g_superpose;
+    if (!overflow) return true;  // else: the candidate list overflowed (dense graph / loose cutoff), nothing was counted yet
+  }
+  g_superposeLast = 1;
+  return launchTensorImpl(mode, q, s, 1, nullptr);
+}
+
+static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, int superS, bool* overflow) {
   if (mode == kCountCosine) return false;
   const int bits = q.words * 32;
   if (bits % kTK != 0 || bits > 4096) return false;
@@ -795,12 +953,17 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   const bool fp4   = count && g_tensorFp4 && bits % (2 * kTK) == 0;
   const int  tn    = fp4 ? kTNFp4 : kTN;
   const int  rowBytes = fp4 ? bits / 2 : bits;  // bytes of one expanded fingerprint
+  if (superS > 1 && !fp4) superS = 1;  // the superposed sums need the fp4 value set {0..4}
+  const size_t nSuper = (q.nX + superS - 1) / superS;  // rows of the X operand
 
   TcParams p{};
-  p.n         = static_cast<uint32_t>(q.nX);
+  p.n         = static_cast<uint32_t>(nSuper);
   p.nY        = static_cast<uint32_t>(q.nY);
   p.kChunks   = rowBytes / kTK;
-  p.tilesM    = static_cast<uint32_t>((q.nX + kTM - 1) / kTM);
+  p.tilesM    = static_cast<uint32_t>((nSuper + kTM - 1) / kTM);
+  p.superS    = superS;
+  p.rowSpan   = static_cast<uint32_t>(kTM * superS);
+  p.groupTiles = static_cast<uint32_t>(kGroupRows / (kTM * superS));
   p.tilesN    = static_cast<uint32_t>((q.nY + tn - 1) / tn);
   p.symmetric = q.symmetric ? 1 : 0;
   p.groupOffset = q.groupOffset;
@@ -814,10 +977,20 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   p.out       = q.out;
   p.recipLen  = 2 * bits;
 
-  // 0/1 expansion of the fingerprints: bytes (2 KB per 2048-bit row) or packed fp4 (1 KB)
-  Scratch<uint8_t> expX(q.nX * static_cast<size_t>(rowBytes), s);
-  Scratch<uint8_t> expYown(same ? 0 : q.nY * static_cast<size_t>(rowBytes), s);
-  {
+  // 0/1 expansion of the fingerprints: bytes (2 KB per 2048-bit row) or packed fp4 (1 KB); with superposition the X
+  // operand is the sum of superS consecutive expansions and the Y operand always the plain one
+  const bool       ownY = !same || superS > 1;
+  Scratch<uint8_t> expX(nSuper * static_cast<size_t>(rowBytes), s);
+  Scratch<uint8_t> expYown(ownY ? q.nY * static_cast<size_t>(rowBytes) : 0, s);
+  if (superS > 1) {
+    const size_t nw = nSuper * static_cast<size_t>(q.words);
+    expandBitsFp4SuperKernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(q.x, q.nX, q.words, superS, nSuper,
+                                                                                      reinterpret_cast<uint4*>(expX.get()));
+    B200_LAUNCHED();
+    const size_t nwy = q.nY * static_cast<size_t>(q.words);
+    expandBitsFp4Kernel<<<static_cast<unsigned>((nwy + 255) / 256), 256, 0, s>>>(q.y, nwy, reinterpret_cast<uint4*>(expYown.get()));
+    B200_LAUNCHED();
+  } else {
     auto expand = [&](const uint32_t* src, size_t rows, uint8_t* dst) {
       const size_t nw = rows * static_cast<size_t>(q.words);
       if (fp4) expandBitsFp4Kernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(src, nw, reinterpret_cast<uint4*>(dst));
@@ -827,13 +1000,29 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
     expand(q.x, q.nX, expX.get());
     if (!same) expand(q.y, q.nY, expYown.get());
   }
-  const uint8_t* expY = same ? expX.get() : expYown.get();
+  const uint8_t* expY = ownY ? expYown.get() : expX.get();
 
-  Scratch<int32_t> popX(q.nX, s), popYown(same ? 0 : q.nY, s);
+  Scratch<int32_t> popX(q.nX, s), popYown(same ? 0 : q.nY, s), popSuper(superS > 1 ? nSuper : 0, s);
   launchRowPopcount(q.x, q.nX, q.words, popX.get(), s);
   if (!same) launchRowPopcount(q.y, q.nY, q.words, popYown.get(), s);
   p.popX = popX.get();
   p.popY = same ? popX.get() : popYown.get();
+  // candidates of a superposed pass: (super row, column) pairs the exact kernel re-examines. Sized for the neighbour
+  // graphs this pass is used on (tens of edges per point); a denser graph overflows it and the caller falls back.
+  unsigned long long          candCap = 0;
+  Scratch<int2>               cand;
+  Scratch<unsigned long long> candCursor;
+  if (superS > 1) {
+    superMinPopKernel<<<static_cast<unsigned>((nSuper + 255) / 256), 256, 0, s>>>(popX.get(), q.nX, superS, nSuper, popSuper.get());
+    B200_LAUNCHED();
+    p.popX = popSuper.get();
+    const unsigned long long all = static_cast<unsigned long long>(nSuper) * q.nY;
+    candCap                      = std::min<unsigned long long>(all, std::max<unsigned long long>(1ull << 22, 64ull * q.nX));
+    cand                         = Scratch<int2>(candCap, s);
+    candCursor                   = Scratch<unsigned long long>(1, s);
+    B200_CUDA(cudaMemsetAsync(candCursor.get(), 0, sizeof(unsigned long long), s));
+    p.cand = cand.get(), p.candCursor = candCursor.get(), p.candCap = candCap;
+  }
   const int         maxS = 2 * bits;
   Scratch<uint16_t> thresh(2 * static_cast<size_t>(maxS + 1), s);
   if (mode == kCountTanimoto) {
@@ -845,7 +1034,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   p.thresh = thresh.get();
 
   CUtensorMap tmA, tmB;
-  makeTensorMap2D(&tmA, expX.get(), q.nX, rowBytes, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  makeTensorMap2D(&tmA, expX.get(), nSuper, rowBytes, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
   const bool cluster = fp4 && g_tensorCluster != 0;  // CTA pairs: 1 = multicast column operand, 2 = cta_group::2 MMAs,
   const bool pairMma = cluster && g_tensorCluster == 2;  // 3 = multicast column operand + stationary row operand
   const bool stationary = cluster && g_tensorCluster == 3 && p.kChunks <= kMaxChunksStat;
@@ -869,7 +1058,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
   }
   B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
   // units this call owns: tiles, or vertical tile pairs (same enumeration as the kernel's UnitWalk)
-  const uint64_t total = stationary ? countUnits<kTNFp4, true, kRunStat, kGroupStat>(p)
+  const uint64_t total = stationary ? countUnits<kTNFp4, true, kRunStat>(p)
                          : cluster  ? countUnits<kTNFp4, true>(p)
                                     : (fp4 ? countUnits<kTNFp4, false>(p) : countUnits<kTN, false>(p));
   if (total == 0) return true;  // nothing owned by this rank (more ranks than row groups)
@@ -911,6 +1100,25 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
     simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, p);
   }
   B200_LAUNCHED();
+  if (superS > 1) {
+    // the one host read of a superposed pass: how many candidates (the callers synchronise for their edge total anyway)
+    unsigned long long nCand = 0;
+    B200_CUDA(cudaMemcpyAsync(&nCand, candCursor.get(), sizeof(nCand), cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    if (nCand > candCap) {
+      if (overflow) *overflow = true;  // nothing has been counted yet: the caller reruns without superposition
+      return true;
+    }
+    if (nCand) {
+      PhaseTimer         t("verify_candidates", s);
+      const unsigned int blocks2 = static_cast<unsigned int>(std::min<unsigned long long>((nCand + 7) / 8, static_cast<unsigned long long>(smCount()) * 16));
+      verifyCandidatesKernel<<<blocks2, 256, 0, s>>>(q.x, q.y, q.words, cand.get(), nCand, superS, static_cast<uint32_t>(q.nX),
+                                                     q.symmetric ? 1 : 0, popX.get(), same ? popX.get() : popYown.get(),
+                                                     thresh.get(), q.sign, q.rowCounts, q.symmetric ? q.rowCounts : nullptr,
+                                                     q.edges, q.edgeCursor, q.edgeCap);
+      B200_LAUNCHED();
+    }
+  }
   return true;
 }
 

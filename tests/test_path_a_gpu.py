@@ -281,17 +281,22 @@ def test_butina_parallel_rounds_keep_the_greedy_order(cuda, min_commits, n, degr
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05 int8) path of the count pass
-@pytest.fixture(params=[1, 0, 2, 3], ids=["multicast_pair", "single_cta", "pair_mma", "row_stationary"])
+@pytest.fixture(params=[(1, 4), (0, 4), (2, 4), (3, 4), (1, 1), (3, 1), (0, 2)],
+                ids=["multicast_pair-super4", "single_cta-super4", "pair_mma-super4", "row_stationary-super4",
+                     "multicast_pair-plain", "row_stationary-plain", "single_cta-super2"])
 def force_tensor_path(cuda, request):
     """Every test that takes this fixture runs on all four tile variants of the fp4 count pass:
     similarity_tensor_cluster = 1 (CTA pair, multicast column operand), 0 (one CTA per tile),
-    2 (CTA pair with tcgen05 cta_group::2 MMAs), 3 (CTA pair, multicast column operand, row operand stationary)."""
+    2 (CTA pair with tcgen05 cta_group::2 MMAs), 3 (CTA pair, multicast column operand, row operand stationary) - crossed
+    with the row superposition of the Butina neighbour pass (4 = default, 2, 1 = off)."""
     from nvmolkit_b200 import _lib
 
     _lib.set_option("similarity_tensor_min_pairs", 0)
-    _lib.set_option("similarity_tensor_cluster", request.param)
+    _lib.set_option("similarity_tensor_cluster", request.param[0])
+    _lib.set_option("similarity_superpose", request.param[1])
     yield request.param
     _lib.set_option("similarity_tensor_cluster", 1)
+    _lib.set_option("similarity_superpose", 4)
     _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
 
 
@@ -330,6 +335,21 @@ def test_tensor_neighbor_counts_on_a_many_tile_problem(cuda, force_tensor_path):
     ids, cen = fused_butina_device(_dev(fp, cuda), 0.3)
     ids_cpu, cen_cpu = oracle.butina_fp(fp, 0.3)
     assert (ids.cpu().numpy() == ids_cpu).all() and (cen.cpu().numpy() == cen_cpu).all()
+
+
+def test_superposed_pass_falls_back_when_its_candidate_list_overflows(cuda):
+    """6,000 identical fingerprints: every pair is an edge, so the superposed pass lists ~4.5 M candidates, more than its
+    list holds; nothing may have been counted when it notices, and the unsuperposed rerun must give the exact answer."""
+    from nvmolkit_b200 import _lib
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    one = np.repeat(S.random_fingerprints(1, seed=3), 6000, axis=0)
+    _lib.set_option("similarity_tensor_min_pairs", 0)
+    try:
+        ids, cen = fused_butina_device(_dev(one, cuda), 0.3)
+    finally:
+        _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
+    assert (ids.cpu().numpy() == 0).all() and cen.cpu().numpy().tolist() == [5999]
 
 
 def test_tensor_and_simt_paths_agree_on_identical_rows(cuda, force_tensor_path):
@@ -417,6 +437,6 @@ def test_sharded_neighbor_pass_equals_oracle(cuda, world, centres, members, tens
     key = edges[:, 0].astype(np.int64) * len(fp) + edges[:, 1]
     assert len(np.unique(key)) == len(key) == int(want_deg.sum()) // 2  # every neighbour pair exactly once
     assert (ids == ids_cpu).all() and (cen == cen_cpu).all()
-    rows_per_group = 128 * {0: 32, 1: 16, 3: 64}[tensor]  # tile-row group of the SIMT tile | tensor tile | stationary tile
+    rows_per_group = 8192 if tensor else 4096  # row group of the tensor tiles (any variant / superposition) | of the SIMT tile
     if -(-len(fp) // rows_per_group) >= world and centres * members >= 1000:  # every rank owns a group -> finds edges
         assert all(c > 0 for c in per_rank), per_rank
