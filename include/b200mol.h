@@ -188,6 +188,10 @@ typedef struct b200mol_mmff_system {
   int32_t            nMols;
   const int32_t*     atomCounts; /* [nMols] */
   b200mol_term_table bond, angle, strbend, oop, torsion, vdw, ele;
+  /* restraints (RDKit MMFF/UFF "constraints", src/forcefields/mmff_kernels_device.cuh:673-1036); empty tables = none:
+   *   distc K2 P3 {minLen, maxLen, k}   posc K1 P5 {refX, refY, refZ, maxDispl, k}
+   *   anglec K3 P3 {minDeg, maxDeg, k}  torsc K4 P3 {minDeg, maxDeg, k} (signed dihedral, degrees, periodic) */
+  b200mol_term_table distc, posc, anglec, torsc;
 } b200mol_mmff_system;
 
 /* Distance geometry (src/forcefields/dist_geom_kernels_device.cuh:37-231; src/forcefields/dist_geom.h:31-56)
@@ -218,6 +222,7 @@ typedef struct b200mol_uff_system {
   int32_t            nMols;
   const int32_t*     atomCounts;
   b200mol_term_table bond, angle, torsion, inversion, vdw;
+  b200mol_term_table distc, posc, anglec, torsc; /* restraints, as in b200mol_mmff_system */
 } b200mol_uff_system;
 
 /* ------------------------------------------------------------------------------------------
@@ -365,6 +370,20 @@ int b200mol_etkdg_check(const b200mol_dg_system* dg, const b200mol_etk_system* e
                         const b200mol_embed_params* params, int32_t nSlots, const int32_t* d_slot_mol,
                         const int32_t* d_slot_atom_start, int max_atoms, const double* d_pos4, uint32_t* d_fail_masks,
                         void* stream);
+
+/* RMS pruning of embedded conformers on the device (RDKit EmbedParameters::pruneRmsThresh). Conformers of molecule m are
+ * [d_mol_conf_start[m], d_mol_conf_start[m+1]) in embedding order; conformer c owns atoms [d_conf_atom_start[c],
+ * d_conf_atom_start[c+1]) of d_xyz[.][3]. d_keep[c] = 1 when conformer c is valid (d_conf_valid[c] != 0, NULL = all) and its
+ * best-alignment sum of squared deviations to every conformer kept before it is >= nSel * rms_thresh^2.
+ * Atom selection / symmetry: per molecule K_m index lists ("self matches") of L_m atoms each, d_match_atoms
+ * [d_match_offset[m] .. d_match_offset[m+1]) = K_m * L_m molecule-local indices, d_match_len[m] = L_m; list 0 selects the
+ * atoms of the conformer under test, every list in turn those of an earlier conformer (RDKit useSymmetryForPruning); one
+ * list of the heavy atoms = onlyHeavyAtomsForRMS; all three NULL = all atoms, identity mapping.
+ * Replaces addConformersToMoleculeWithPruning / _isConfFarFromRest (rdkit_extensions/conformer_pruning.cpp:96-137), which
+ * the reference runs on the host and refuses for DEVICE output (src/etkdg.cpp:106-110). */
+int b200mol_rms_prune(int32_t nMols, const int32_t* d_mol_conf_start, const int32_t* d_conf_atom_start, const double* d_xyz,
+                      const int32_t* d_match_offset, const int32_t* d_match_len, const int16_t* d_match_atoms, double rms_thresh,
+                      const uint8_t* d_conf_valid, uint8_t* d_keep, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Distance-geometry preparation (per-molecule, matrix resident in shared memory).

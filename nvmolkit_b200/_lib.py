@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200mol_etk_terms_from_details": (C.c_int, [C.c_int32, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "b200mol_allgather_counts": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "b200mol_allgather_results": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200mol_rms_prune": (C.c_int, [C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp]),
     "b200mol_morgan": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                                  _vp]),
 }

@@ -169,6 +169,102 @@ __device__ __forceinline__ void forTerms(const b200mol_term_table& T, const Rang
   }
 }
 
+// ============================================================================================ restraints
+// The four restraint ("constraint") term types of RDKit's MMFF / UFF force fields, shared by both
+// (src/forcefields/mmff_kernels_device.cuh:673-1036; specs src/forcefields/forcefield_constraints.h:31-73):
+//   distance K2 P3 {minLen, maxLen, k}      flat-bottomed  1/2 k (d - bound)^2
+//   position K1 P5 {refX, refY, refZ, maxDispl, k}          1/2 k max(|x - ref| - maxDispl, 0)^2
+//   angle    K3 P3 {minDeg, maxDeg, k}      k (theta - bound)^2 in DEGREES (no 1/2)
+//   torsion  K4 P3 {minDeg, maxDeg, k}      k (phi - nearest bound)^2, signed dihedral in degrees, periodic
+struct RestraintRanges {
+  Range dist, pos, angle, torsion;
+};
+__device__ __forceinline__ double normDeg(double a) {
+  a = fmod(a, 360.0);
+  if (a < -180.0) a += 360.0;
+  else if (a > 180.0) a -= 360.0;
+  return a;
+}
+template <bool GRAD>
+__device__ __forceinline__ double restraintTerms(const b200mol_term_table& TD, const b200mol_term_table& TP, const b200mol_term_table& TA,
+                                                 const b200mol_term_table& TT, const RestraintRanges& r, const double* pos, double* grad,
+                                                 int tid, int nT) {
+  double e = 0.0;
+  forTerms<GRAD, 2, 3>(TD, r.dist, tid, nT, [&](const TermRec<2, 3>& rec) {
+    const V3     d  = ld<3>(pos, rec.ix[0]) - ld<3>(pos, rec.ix[1]);
+    const double d2 = dot(d, d), mn = rec.q[0], mx = rec.q[1];
+    double       bound;
+    if (d2 < mn * mn) bound = mn;
+    else if (d2 > mx * mx) bound = mx;
+    else return;
+    const double dist = sqrt(d2);
+    if (!GRAD) {
+      e += 0.5 * rec.q[2] * (dist - bound) * (dist - bound);
+    } else {
+      const V3 g = d * ((dist - bound) * rec.q[2] / fmax(1.0e-8, dist));
+      acc<3>(grad, rec.ix[0], g);
+      acc<3>(grad, rec.ix[1], -g);
+    }
+  });
+  forTerms<GRAD, 1, 5>(TP, r.pos, tid, nT, [&](const TermRec<1, 5>& rec) {
+    const V3     d    = ld<3>(pos, rec.ix[0]) - V3{rec.q[0], rec.q[1], rec.q[2]};
+    const double dist = sqrt(dot(d, d));
+    if (!GRAD) {
+      const double t = fmax(dist - rec.q[3], 0.0);
+      e += 0.5 * rec.q[4] * t * t;
+    } else {
+      if (dist <= rec.q[3]) return;
+      acc<3>(grad, rec.ix[0], d * ((dist - rec.q[3]) * rec.q[4] / fmax(dist, 1.0e-8)));
+    }
+  });
+  forTerms<GRAD, 3, 3>(TA, r.angle, tid, nT, [&](const TermRec<3, 3>& rec) {
+    const V3     r1 = ld<3>(pos, rec.ix[0]) - ld<3>(pos, rec.ix[1]), r2 = ld<3>(pos, rec.ix[2]) - ld<3>(pos, rec.ix[1]);
+    const double l1 = fmax(1.0e-5, dot(r1, r1)), l2 = fmax(1.0e-5, dot(r2, r2));
+    const double ang = kRad2Deg * acos(clampd(dot(r1, r2) / sqrt(l1 * l2), -1.0, 1.0));
+    const double at  = ang < rec.q[0] ? ang - rec.q[0] : (ang > rec.q[1] ? ang - rec.q[1] : 0.0);
+    if (!GRAD) {
+      e += rec.q[2] * at * at;
+    } else {
+      if (isZero(at)) return;
+      const V3     rp  = cross(r2, r1);
+      const double pre = 2.0 * kRad2Deg * rec.q[2] * at / fmax(1.0e-5, sqrt(dot(rp, rp)));
+      const V3     a = cross(r1, rp) * (-pre / l1), b = cross(r2, rp) * (pre / l2);
+      acc<3>(grad, rec.ix[0], a);
+      acc<3>(grad, rec.ix[1], -(a + b));
+      acc<3>(grad, rec.ix[2], b);
+    }
+  });
+  forTerms<GRAD, 4, 3>(TT, r.torsion, tid, nT, [&](const TermRec<4, 3>& rec) {
+    const V3     p1 = ld<3>(pos, rec.ix[0]), p2 = ld<3>(pos, rec.ix[1]), p3 = ld<3>(pos, rec.ix[2]), p4 = ld<3>(pos, rec.ix[3]);
+    const V3     r0 = p1 - p2, r1 = p3 - p2, r2 = -r1, r3 = p4 - p3;
+    const V3     tt0 = cross(r0, r1), tt1 = cross(r2, r3);
+    const double d0 = fmax(sqrt(dot(tt0, tt0)), 1.0e-5), d1 = fmax(sqrt(dot(tt1, tt1)), 1.0e-5);
+    const V3     t0 = tt0 * (1.0 / d0), t1 = tt1 * (1.0 / d1);
+    const double cosPhi = clampd(dot(t0, t1), -1.0, 1.0);
+    const V3     mv = cross(t0, r1);
+    const double phi = kRad2Deg * -atan2(dot(mv, t1) / fmax(sqrt(dot(mv, mv)), 1.0e-5), cosPhi);
+    const double mn = rec.q[0], mx = rec.q[1];
+    double       target = phi;
+    if (!(phi > mn && phi < mx) && !(phi > mn && mn > mx) && !(phi < mx && mn > mx))
+      target = fabs(normDeg(phi - mn)) < fabs(normDeg(phi - mx)) ? mn : mx;
+    const double term = normDeg(phi - target);
+    if (!GRAD) {
+      e += rec.q[2] * term * term;
+    } else {
+      if (isZero(term)) return;
+      const V3     d23v = p2 - p3;
+      const double pre  = 2.0 * kRad2Deg * rec.q[2] * term / fmax(sqrt(dot(d23v, d23v)), 1.0e-8);
+      const V3     dedt0 = cross(tt0, r2) * (pre / fmax(dot(tt0, tt0), 1.0e-8));
+      const V3     dedt1 = cross(tt1, r1) * (pre / fmax(dot(tt1, tt1), 1.0e-8));
+      acc<3>(grad, rec.ix[0], cross(r2, dedt0));
+      acc<3>(grad, rec.ix[1], cross(p3 - p1, dedt0) - cross(r3, dedt1));
+      acc<3>(grad, rec.ix[2], cross(r0, dedt0) + cross(p4 - p2, dedt1));
+      acc<3>(grad, rec.ix[3], cross(r2, dedt1));
+    }
+  });
+  return e;
+}
+
 // ============================================================================================ MMFF94
 struct Mmff {
   static constexpr int  kDim    = 3;
@@ -176,12 +272,14 @@ struct Mmff {
   using System            = b200mol_mmff_system;
   struct Params {};
   struct View {
-    const System* s;
-    Range         bond, angle, strbend, oop, torsion, vdw, ele;
+    const System*   s;
+    Range           bond, angle, strbend, oop, torsion, vdw, ele;
+    RestraintRanges rs;
   };
   __device__ static View view(const System& s, int mol, const Params&) {
     return {&s,          range(s.bond, mol),    range(s.angle, mol), range(s.strbend, mol),
-            range(s.oop, mol), range(s.torsion, mol), range(s.vdw, mol),   range(s.ele, mol)};
+            range(s.oop, mol), range(s.torsion, mol), range(s.vdw, mol),   range(s.ele, mol),
+            {range(s.distc, mol), range(s.posc, mol), range(s.anglec, mol), range(s.torsc, mol)}};
   }
 
   // bytes of this molecule's term records (K int16 + P fp64 each): the T of SURVEY.md 8d's per-iteration figure
@@ -358,6 +456,7 @@ struct Mmff {
         acc<3>(grad, j, -g);
       }
     });
+    e += restraintTerms<GRAD>(s.distc, s.posc, s.anglec, s.torsc, v.rs, pos, grad, tid, nT);
     return e;
   }
 };
@@ -633,11 +732,13 @@ struct Uff {
   using System                  = b200mol_uff_system;
   struct Params {};
   struct View {
-    const System* s;
-    Range         bond, angle, torsion, inversion, vdw;
+    const System*   s;
+    Range           bond, angle, torsion, inversion, vdw;
+    RestraintRanges rs;
   };
   __device__ static View view(const System& s, int mol, const Params&) {
-    return {&s, range(s.bond, mol), range(s.angle, mol), range(s.torsion, mol), range(s.inversion, mol), range(s.vdw, mol)};
+    return {&s, range(s.bond, mol), range(s.angle, mol), range(s.torsion, mol), range(s.inversion, mol), range(s.vdw, mol),
+            {range(s.distc, mol), range(s.posc, mol), range(s.anglec, mol), range(s.torsc, mol)}};
   }
   __device__ static unsigned termBytes(const View& v) {
     return (v.bond.end - v.bond.beg) * 20u + (v.angle.end - v.angle.beg) * 54u + (v.torsion.end - v.torsion.beg) * 32u +
@@ -809,6 +910,7 @@ struct Uff {
         acc<3>(grad, j, -g);
       }
     });
+    e += restraintTerms<GRAD>(s.distc, s.posc, s.anglec, s.torsc, v.rs, pos, grad, tid, nT);
     return e;
   }
 };
@@ -857,10 +959,12 @@ inline void needWaves(const b200mol_term_table& t, const char* what) {
 inline void requireSchedule(const b200mol_mmff_system& s) {
   needWaves(s.bond, "bond"), needWaves(s.angle, "angle"), needWaves(s.strbend, "strbend"), needWaves(s.oop, "oop");
   needWaves(s.torsion, "torsion"), needWaves(s.vdw, "vdw"), needWaves(s.ele, "ele");
+  needWaves(s.distc, "distc"), needWaves(s.posc, "posc"), needWaves(s.anglec, "anglec"), needWaves(s.torsc, "torsc");
 }
 inline void requireSchedule(const b200mol_uff_system& s) {
   needWaves(s.bond, "bond"), needWaves(s.angle, "angle"), needWaves(s.torsion, "torsion");
   needWaves(s.inversion, "inversion"), needWaves(s.vdw, "vdw");
+  needWaves(s.distc, "distc"), needWaves(s.posc, "posc"), needWaves(s.anglec, "anglec"), needWaves(s.torsc, "torsc");
 }
 inline void requireSchedule(const b200mol_dg_system& s) {
   needWaves(s.dist, "dist"), needWaves(s.chiral, "chiral"), needWaves(s.fourth, "fourth");

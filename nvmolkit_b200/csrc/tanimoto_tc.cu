@@ -28,7 +28,8 @@ constexpr int kTM       = 128;
 constexpr int kTN       = 256;
 constexpr int kTK       = 128;  // bytes (= bits of the fingerprint) per K chunk
 constexpr int kStagesCount = 4;  // smem ring depth of the count mode
-constexpr int kStagesMat   = 3;
+constexpr int kStagesMat   = 2;  // (the materialise modes are bound by the fp64 output; their shared memory also holds the
+                                 //  reciprocal table and 16 x 4 KB of staging for the TMA stores of the epilogue)
 constexpr int kStagesPair  = 6;  // pair-MMA count mode: 30 KB per stage and CTA  // materialise modes: one stage less, the space holds the reciprocal table
 constexpr int kEpiWarpsCount = 8;   // count mode: two warps per TMEM lane quarter share the column blocks
 constexpr int kEpiWarpsMat   = 16;  // materialise modes: four per quarter (the fp64 epilogue is the long pole there)
@@ -65,6 +66,7 @@ struct TcParams {
   // exact in E2M1), so one accumulator bounds superS pair counts at once; n / tilesM then count SUPER rows, popX holds
   // the smallest popcount of each super row, and the epilogue only lists candidates (super row, column) for the exact
   // verification kernel. rowSpan = fingerprints per tile row = kTM * superS.
+  int                 outTma;  // materialise modes: the epilogue leaves through TMA stores (out 16-byte aligned, nY even)
   int                 superS;
   uint32_t            rowSpan;
   uint32_t            groupTiles;  // tile rows per row group (a power of two): kGroupRows fingerprints whatever superS is
@@ -421,7 +423,8 @@ uint64_t countUnits(const TcParams& p) {
 // last tile of the current unit has consumed them, so the reload hides behind that tile's remaining MMAs.
 template <int MODE, bool FP4, int CL>
 __global__ void __launch_bounds__(threadsTC(MODE), 1)
-  simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smemRaw[];
   constexpr int kEpiWarps = epiWarps(MODE), kThreadsTC = threadsTC(MODE), kParts = kEpiWarps / 4;
   constexpr int TN      = FP4 ? kTNFp4 : kTN;  // tile columns; the accumulator stages sit TN TMEM columns apart
@@ -486,6 +489,9 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   const uint16_t* threshT   = ST ? p.thresh : threshS;
   const uint16_t* threshLoS = threshT + p.threshLen;
   double* recipS = reinterpret_cast<double*>(threshS);  // materialise Tanimoto: RN(1/u), u = |A u B| <= 2 * bits
+  // materialise modes: one [32 rows][128 B] box per epilogue warp, written with the 128-byte swizzle the output tensor map
+  // expects and handed to cp.async.bulk.tensor (store)
+  const uint32_t stagingAddr = (smemAddr(threshS) + static_cast<uint32_t>(p.recipLen + 1) * 8u + 1023u) & ~1023u;
   if constexpr (MODE == kTcTanimoto) {
     for (int u = threadIdx.x; u <= p.recipLen; u += kThreadsTC) recipS[u] = u ? __drcp_rn(static_cast<double>(u)) : 0.0;
   }
@@ -704,6 +710,55 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         uint32_t r[32];
         tmemLoad32(tmem + as * TN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
         if constexpr (MODE != kTcCount) {
+          if (p.outTma) {
+            // Lane = output row: 32 consecutive fp64 values of ITS row, 16 at a time into the warp's staging box (128-bit
+            // stores, conflict-free under the 128-byte swizzle: chunk c of row r sits at chunk c ^ (r & 7)), then one TMA
+            // store of the [32 rows][16 columns] box; the tensor map clips rows >= n and columns >= nY. This replaces
+            // 160 SHFL (the register transpose) + 32 scattered 256-byte stores per block: the epilogue, not HBM, bounded
+            // the materialised matrix at 0.43 of the copy bandwidth.
+            const uint32_t stg = stagingAddr + static_cast<uint32_t>(ew) * 4096u;
+            const int      pak = popA[as][quarter * 32 + lane];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous box has been read
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                double v2[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int j   = 16 * h + 2 * c + e;
+                  const int cnt = static_cast<int>(r[j]);
+                  const int pb  = popB[as][cb * 32 + j];
+                  double    v   = 0.0;
+                  if (cnt != 0) {
+                    if constexpr (MODE == kTcTanimoto) {
+                      const int    u  = pak + pb - cnt;
+                      const double dc = __hiloint2double(0x43300000, cnt) - 4503599627370496.0;
+                      const double du = __hiloint2double(0x43300000, u) - 4503599627370496.0;
+                      const double rc = recipS[u], q0 = __dmul_rn(dc, rc);
+                      v               = __fma_rn(__fma_rn(-q0, du, dc), rc, q0);
+                    } else {
+                      v = __ddiv_rn(static_cast<double>(cnt), __dsqrt_rn(__dmul_rn(static_cast<double>(pak), static_cast<double>(pb))));
+                    }
+                  }
+                  v2[e] = v;
+                }
+                const uint32_t at = stg + static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(at), "d"(v2[0]), "d"(v2[1]) : "memory");
+              }
+              fenceProxyAsync();
+              __syncwarp();
+              if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmOut)),
+                             "r"(static_cast<int>(tn * TN + cb * 32 + 16 * h)), "r"(static_cast<int>(tm * kTM + quarter * 32)), "r"(stg)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+            continue;
+          }
           // Transpose the 32 x 32 block in registers (5 butterfly rounds of SHFL) so that lane = column and k = row:
           // every store instruction then writes 32 consecutive doubles of one output row (8 full sectors) instead of
           // 32 scattered 8-byte pieces.
@@ -883,6 +938,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       atomicAdd(&g_tcClk[5], static_cast<unsigned long long>(tcAcc[5]));
     }
 #endif
+    if (MODE != kTcCount && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA stores
     if (MODE == kTcCount && p.countsY) {  // the last two tiles' column counts
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       for (uint32_t back = 1; back <= 2 && back <= local; ++back) {
@@ -1040,11 +1096,16 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   const bool stationary = cluster && g_tensorCluster == 3 && p.kChunks <= kMaxChunksStat;
   makeTensorMap2D(&tmB, expY, q.nY, rowBytes, cluster ? tn / 2 : tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
+  CUtensorMap tmOut = tmA;  // (unused in the count mode)
+  if (!count) {
+    p.outTma = (q.nY % 2 == 0 && (reinterpret_cast<uintptr_t>(q.out) & 15) == 0) ? 1 : 0;
+    if (p.outTma) makeTensorMap2D(&tmOut, q.out, q.nX, q.nY, 32, 16, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8);
+  }
   const size_t smemBytes =
     stationary ? static_cast<size_t>(kMaxChunksStat) * kABytes + static_cast<size_t>(kStagesStat) * tn * kTK + 1024 + 64
                : (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
                           : static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK)) +
-                   (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8) + 1024 + 64;
+                   (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8 + 1024 + kEpiWarpsMat * 4096) + 1024 + 64;
   static bool configured[kMaxDevices] = {};
   if (!configured[currentDeviceSlot()]) {
     B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
@@ -1087,17 +1148,17 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
       uint64_t pairs = maxClusters;  // persistent: one resident cluster per schedulable SM pair
       if (pairs > total) pairs = total;
       cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-      if (stationary) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 3>, tmA, tmB, p));
-      else if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, p));
-      else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, p));
-    } else if (fp4) simTensorKernel<kTcCount, true, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p);
-    else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, p);
+      if (stationary) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 3>, tmA, tmB, tmOut, p));
+      else if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, tmOut, p));
+      else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, tmOut, p));
+    } else if (fp4) simTensorKernel<kTcCount, true, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, tmOut, p);
+    else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, tmOut, p);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcTanimoto, false, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, p);
+    simTensorKernel<kTcTanimoto, false, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, tmOut, p);
   } else {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, p);
+    simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, tmOut, p);
   }
   B200_LAUNCHED();
   if (superS > 1) {

@@ -144,6 +144,7 @@ PYBIND11_MODULE(_core, m) {
   DEF(b200mol_triangle_smooth);
   DEF(b200mol_eig_topk);
   DEF(b200mol_metric_embed);
+  DEF(b200mol_rms_prune);
   DEF(b200mol_allgather_counts);
   DEF(b200mol_allgather_results);
 #undef DEF

@@ -52,6 +52,7 @@ class FlatEmbedMolecules:
     dg: FlatSystem
     etk: FlatSystem
     checks: CheckTables
+    prune_matches: Optional[list] = None  # per molecule: [K, L] atom-index lists for RMS pruning (None = all atoms)
 
     def __len__(self) -> int:
         return self.dg.n_mols
@@ -133,9 +134,22 @@ def embed_slots(flat: FlatEmbedMolecules, params, confs_per_molecule: int, max_i
     return EmbedRaw(coords, ok, attempts, energy, fails, slot_mol, slot_start)
 
 
-def _to_device_result(raw: EmbedRaw, n_mols: int, gpu_id: int) -> Device3DResult:
+def _prune(raw: EmbedRaw, flat: "FlatEmbedMolecules", rms_thresh: float) -> torch.Tensor:
+    """RDKit's pruneRmsThresh on the device: the slots of a molecule are contiguous and in embedding order."""
+    from nvmolkit_b200.pruning import rms_prune
+
+    change = np.nonzero(np.diff(raw.slot_mol) != 0)[0] + 1
+    mol_conf_start = np.concatenate([[0], change, [len(raw.slot_mol)]]).astype(np.int32)
+    mols = raw.slot_mol[mol_conf_start[:-1]]
+    matches = None
+    if getattr(flat, "prune_matches", None) is not None:
+        matches = [flat.prune_matches[int(m)] for m in mols]
+    return rms_prune(raw.coords, raw.slot_atom_start, mol_conf_start, rms_thresh, matches, flat.atom_counts[mols], valid=raw.ok)
+
+
+def _to_device_result(raw: EmbedRaw, n_mols: int, gpu_id: int, keep: Optional[torch.Tensor] = None) -> Device3DResult:
     """Compact the successful slots into the reference's CSR result (src/conformer/device_coord_result.h:58-67)."""
-    ok_h = raw.ok.cpu().numpy().astype(bool)
+    ok_h = (raw.ok if keep is None else keep).cpu().numpy().astype(bool)
     sizes = np.diff(raw.slot_atom_start)
     keep = np.nonzero(ok_h)[0]
     # present results in input molecule order, conformer order within a molecule
@@ -169,8 +183,8 @@ def EmbedMolecules(molecules, params, confsPerMolecule: int = 1, maxIterations: 
             if mol is None:
                 raise ValueError(f"Molecule at index {i} is None")
     # useRandomCoords=False (refused by the reference, src/etkdg.cpp:99-101) selects the on-device metric-matrix start
-    if output == CoordinateOutput.DEVICE and float(getattr(params, "pruneRmsThresh", -1.0)) > 0:
-        raise ValueError("DEVICE output is incompatible with pruneRmsThresh > 0")
+    # (the reference refuses pruneRmsThresh > 0 with DEVICE output, src/etkdg.cpp:106-110: its pruning is host-only;
+    #  here the pruning runs on the device, so both outputs take it)
     if hardwareOptions is None:
         hardwareOptions = HardwareOptions()
     gpu = int(targetGpu) if targetGpu >= 0 else (hardwareOptions.gpuIds[0] if hardwareOptions.gpuIds else torch.cuda.current_device())
@@ -182,13 +196,15 @@ def EmbedMolecules(molecules, params, confsPerMolecule: int = 1, maxIterations: 
         flat = embed_molecules_from_rdkit(molecules, params)
     with torch.cuda.device(gpu):
         raw = embed_slots(flat, params, int(confsPerMolecule), int(maxIterations))
+        prune = float(getattr(params, "pruneRmsThresh", -1.0))
+        keep = _prune(raw, flat, prune) if prune > 0.0 else None
         if output == CoordinateOutput.DEVICE:
-            return _to_device_result(raw, len(flat), gpu)
-        res = _to_device_result(raw, len(flat), gpu)
+            return _to_device_result(raw, len(flat), gpu, keep)
+        res = _to_device_result(raw, len(flat), gpu, keep)
         per_mol: List[List[np.ndarray]] = [[c.cpu().numpy() for c in confs] for confs in res.per_molecule()]
     if flat_input:
         return per_mol
     from nvmolkit_b200.rdkit_adapter import add_conformers
 
-    add_conformers(molecules, per_mol, float(getattr(params, "pruneRmsThresh", -1.0)))
+    add_conformers(molecules, per_mol, -1.0)  # (already pruned on the device)
     return None

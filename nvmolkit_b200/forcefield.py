@@ -17,8 +17,9 @@ import numpy as np
 # kind -> ordered (table name, K indices, P parameters); order = field order of the C structs in include/b200mol.h
 LAYOUT: Dict[str, Tuple[Tuple[str, int, int], ...]] = {
     "mmff": (("bond", 2, 2), ("angle", 3, 3), ("strbend", 3, 5), ("oop", 4, 1), ("torsion", 4, 3), ("vdw", 2, 2),
-             ("ele", 2, 3)),
-    "uff": (("bond", 2, 2), ("angle", 3, 6), ("torsion", 4, 3), ("inversion", 4, 4), ("vdw", 2, 3)),
+             ("ele", 2, 3), ("distc", 2, 3), ("posc", 1, 5), ("anglec", 3, 3), ("torsc", 4, 3)),
+    "uff": (("bond", 2, 2), ("angle", 3, 6), ("torsion", 4, 3), ("inversion", 4, 4), ("vdw", 2, 3), ("distc", 2, 3),
+            ("posc", 1, 5), ("anglec", 3, 3), ("torsc", 4, 3)),
     "dg": (("dist", 2, 3), ("chiral", 4, 2), ("fourth", 1, 0)),
     "etk": (("torsion", 4, 12), ("improper", 4, 4), ("dist12", 2, 4), ("dist13", 2, 4), ("angle13", 3, 2),
             ("longrange", 2, 3)),
@@ -75,6 +76,8 @@ class FlatSystem:
         n_mols = len(self.atom_counts)
         fixed = {}
         for name, k, p in LAYOUT[self.kind]:
+            if name not in self.tables:  # (restraint tables are optional: none)
+                self.tables[name] = (np.zeros(n_mols + 1, np.int32), np.zeros((0, k), np.int16), np.zeros((0, p)))
             starts, idx, par = self.tables[name]
             starts = np.ascontiguousarray(starts, dtype=np.int32)
             idx = np.ascontiguousarray(idx, dtype=np.int16).reshape(-1, k)

@@ -144,7 +144,7 @@ def _as_tables(kind: str, t) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
     from nvmolkit_b200.forcefield import LAYOUT
 
     return {name: (np.array(t[name][0], dtype=np.int16).reshape(-1, k), np.array(t[name][1], dtype=np.float64).reshape(-1, p))
-            for name, k, p in LAYOUT[kind]}
+            for name, k, p in LAYOUT[kind] if name in t}  # (the restraint tables are added by BatchedForcefield only)
 
 
 class _FlatWithMap:

@@ -158,8 +158,8 @@ class _TermTableC(C.Structure):
 
 
 _FF_LAYOUT = {
-    "mmff": ("bond", "angle", "strbend", "oop", "torsion", "vdw", "ele"),
-    "uff": ("bond", "angle", "torsion", "inversion", "vdw"),
+    "mmff": ("bond", "angle", "strbend", "oop", "torsion", "vdw", "ele", "distc", "posc", "anglec", "torsc"),
+    "uff": ("bond", "angle", "torsion", "inversion", "vdw", "distc", "posc", "anglec", "torsc"),
     "dg": ("dist", "chiral", "fourth"),
     "etk": ("torsion", "improper", "dist12", "dist13", "angle13", "longrange"),
 }
@@ -178,9 +178,16 @@ def _host_system(kind: str, atom_counts: np.ndarray, tables: dict):
     st = _FF_STRUCT[kind]()
     st.nMols = len(atom_counts)
     st.atomCounts = atom_counts.ctypes.data
+    keep = []
     for name in _FF_LAYOUT[kind]:
+        if name not in tables:  # restraint tables are optional
+            z = np.zeros(len(atom_counts) + 1, dtype=np.int32)
+            keep.append(z)
+            setattr(st, name, _TermTableC(z.ctypes.data, None, None))
+            continue
         starts, idx, par = tables[name]
         setattr(st, name, _TermTableC(starts.ctypes.data, idx.ctypes.data, par.ctypes.data if par.size else None))
+    st._keep = keep
     return st
 
 
@@ -482,3 +489,34 @@ def etk_terms(bounds, torsion_atoms, improper_atoms, bond_atoms, angle_atoms, sc
     return {"improper": (imp_i[: counts[0]], imp_p[: counts[0]]), "dist12": (ba.copy(), d12_p),
             "dist13": (d13_i[: counts[1]], d13_p[: counts[1]]), "angle13": (a13_i[: counts[2]], a13_p[: counts[2]]),
             "longrange": (lr_i[: counts[3]], lr_p[: counts[3]])}, int(counts[4])
+
+
+# ------------------------------------------------------------------------------------------------ conformer pruning
+def best_ssd(a: np.ndarray, b: np.ndarray) -> float:
+    """Best-alignment sum of squared deviations of two [n, 3] point sets (Horn quaternion eigenproblem, oracle_prune.c)."""
+    L = lib()
+    a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+    L.oracle_best_ssd.restype = C.c_double
+    L.oracle_best_ssd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    return float(L.oracle_best_ssd(a.ctypes.data, None, b.ctypes.data, None, len(a)))
+
+
+def rms_prune(xyz, conf_atom_start, mol_conf_start, thresh, matches=None, valid=None) -> np.ndarray:
+    """keep flags [nConf]; matches[m] = [K, L] index array or None (all atoms)."""
+    L = lib()
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    cas = np.ascontiguousarray(conf_atom_start, np.int32)
+    keep = np.zeros(len(cas) - 1, dtype=np.uint8)
+    v = np.ascontiguousarray(valid, np.uint8) if valid is not None else None
+    L.oracle_rms_prune_mol.restype = None
+    L.oracle_rms_prune_mol.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double,
+                                       C.c_void_p, C.c_void_p]
+    for m in range(len(mol_conf_start) - 1):
+        c0, c1 = int(mol_conf_start[m]), int(mol_conf_start[m + 1])
+        if c1 <= c0:
+            continue
+        mt = None if matches is None or matches[m] is None else np.ascontiguousarray(matches[m], np.int16)
+        k, ln = (1, int(cas[c0 + 1] - cas[c0])) if mt is None else mt.shape
+        L.oracle_rms_prune_mol(c0, c1, cas.ctypes.data, xyz.ctypes.data, int(k), int(ln), mt.ctypes.data if mt is not None else None,
+                               float(thresh), v.ctypes.data if v is not None else None, keep.ctypes.data)
+    return keep

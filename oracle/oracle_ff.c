@@ -33,6 +33,7 @@ typedef struct {
   int32_t        nMols;
   const int32_t* atomCounts;
   TermTable      bond, angle, strbend, oop, torsion, vdw, ele;
+  TermTable      distc, posc, anglec, torsc; /* restraints */
 } MmffSystem;
 
 typedef struct {
@@ -264,6 +265,124 @@ static double mmff_ele(const double* p, int i, int j, double chargeTerm, int die
 
 /* Energy of molecule `mol` at pos[nAtoms*3]; if grad != NULL the gradient is ACCUMULATED into it.
  * perType[7] (optional) receives the per-term-type energies (bond, angle, strbend, oop, torsion, vdw, ele). */
+/* =========================================================================================== restraints
+ * The four "constraint" contribs of RDKit's MMFF / UFF force fields as the reference evaluates them
+ * (src/forcefields/mmff_kernels_device.cuh:673-1036): flat-bottomed distance (1/2 k), position (1/2 k beyond maxDispl), angle
+ * and signed-dihedral windows in degrees (k, no 1/2; the dihedral window is periodic). */
+static double norm_deg(double a) {
+  a = fmod(a, 360.0);
+  if (a < -180.0) a += 360.0;
+  else if (a > 180.0) a -= 360.0;
+  return a;
+}
+static double restraint_terms(const TermTable* D, const TermTable* P, const TermTable* A, const TermTable* T, int mol, const double* p,
+                              double* g) {
+  double e = 0.0;
+  for (int t = D->starts[mol]; t < D->starts[mol + 1]; ++t) {
+    const int    i = D->idx[2 * t], j = D->idx[2 * t + 1];
+    const double mn = D->par[3 * t], mx = D->par[3 * t + 1], k = D->par[3 * t + 2];
+    double       d[3] = {p[3 * i] - p[3 * j], p[3 * i + 1] - p[3 * j + 1], p[3 * i + 2] - p[3 * j + 2]};
+    const double d2 = dot3(d, d);
+    double       bound;
+    if (d2 < mn * mn) bound = mn;
+    else if (d2 > mx * mx) bound = mx;
+    else continue;
+    const double dist = sqrt(d2);
+    e += 0.5 * k * (dist - bound) * (dist - bound);
+    if (g)
+      for (int c = 0; c < 3; ++c) {
+        const double v = k * (dist - bound) / fmax(1.0e-8, dist) * d[c];
+        g[3 * i + c] += v;
+        g[3 * j + c] -= v;
+      }
+  }
+  for (int t = P->starts[mol]; t < P->starts[mol + 1]; ++t) {
+    const int     i = P->idx[t];
+    const double* q = P->par + 5 * t;
+    double        d[3] = {p[3 * i] - q[0], p[3 * i + 1] - q[1], p[3 * i + 2] - q[2]};
+    const double  dist = sqrt(dot3(d, d)), over = dist - q[3];
+    if (over <= 0.0) continue;
+    e += 0.5 * q[4] * over * over;
+    if (g)
+      for (int c = 0; c < 3; ++c) g[3 * i + c] += over * q[4] / fmax(dist, 1.0e-8) * d[c];
+  }
+  for (int t = A->starts[mol]; t < A->starts[mol + 1]; ++t) {
+    const int     i = A->idx[3 * t], j = A->idx[3 * t + 1], k = A->idx[3 * t + 2];
+    const double* q = A->par + 3 * t;
+    double        r1[3], r2[3], rp[3], c0[3], c1[3];
+    for (int c = 0; c < 3; ++c) {
+      r1[c] = p[3 * i + c] - p[3 * j + c];
+      r2[c] = p[3 * k + c] - p[3 * j + c];
+    }
+    const double l1 = fmax(1.0e-5, dot3(r1, r1)), l2 = fmax(1.0e-5, dot3(r2, r2));
+    const double ang = RAD2DEG * acos(clampd(dot3(r1, r2) / sqrt(l1 * l2), -1.0, 1.0));
+    const double at = ang < q[0] ? ang - q[0] : (ang > q[1] ? ang - q[1] : 0.0);
+    e += q[2] * at * at;
+    if (!g || is_zero(at)) continue;
+    cross(r2, r1, rp);
+    const double pre = 2.0 * RAD2DEG * q[2] * at / fmax(1.0e-5, sqrt(dot3(rp, rp)));
+    cross(r1, rp, c0);
+    cross(r2, rp, c1);
+    for (int c = 0; c < 3; ++c) {
+      const double a = c0[c] * (-pre / l1), b = c1[c] * (pre / l2);
+      g[3 * i + c] += a;
+      g[3 * j + c] -= a + b;
+      g[3 * k + c] += b;
+    }
+  }
+  for (int t = T->starts[mol]; t < T->starts[mol + 1]; ++t) {
+    const int16_t* ix = T->idx + 4 * t;
+    const double*  q = T->par + 3 * t;
+    const double * p1 = p + 3 * ix[0], *p2 = p + 3 * ix[1], *p3 = p + 3 * ix[2], *p4 = p + 3 * ix[3];
+    double         r0[3], r1[3], r2[3], r3[3], tt0[3], tt1[3], t0[3], t1[3], m[3];
+    for (int c = 0; c < 3; ++c) {
+      r0[c] = p1[c] - p2[c];
+      r1[c] = p3[c] - p2[c];
+      r2[c] = -r1[c];
+      r3[c] = p4[c] - p3[c];
+    }
+    cross(r0, r1, tt0);
+    cross(r2, r3, tt1);
+    const double d0 = fmax(sqrt(dot3(tt0, tt0)), 1.0e-5), d1 = fmax(sqrt(dot3(tt1, tt1)), 1.0e-5);
+    for (int c = 0; c < 3; ++c) {
+      t0[c] = tt0[c] / d0;
+      t1[c] = tt1[c] / d1;
+    }
+    const double cosPhi = clampd(dot3(t0, t1), -1.0, 1.0);
+    cross(t0, r1, m);
+    const double phi = RAD2DEG * -atan2(dot3(m, t1) / fmax(sqrt(dot3(m, m)), 1.0e-5), cosPhi);
+    double       target = phi;
+    if (!(phi > q[0] && phi < q[1]) && !(phi > q[0] && q[0] > q[1]) && !(phi < q[1] && q[0] > q[1]))
+      target = fabs(norm_deg(phi - q[0])) < fabs(norm_deg(phi - q[1])) ? q[0] : q[1];
+    const double term = norm_deg(phi - target);
+    e += q[2] * term * term;
+    if (!g || is_zero(term)) continue;
+    double d23[3] = {p2[0] - p3[0], p2[1] - p3[1], p2[2] - p3[2]};
+    const double pre = 2.0 * RAD2DEG * q[2] * term / fmax(sqrt(dot3(d23, d23)), 1.0e-8);
+    double       tmp0[3], tmp1[3], dedt0[3], dedt1[3], r31[3], r42[3], a[3], b[3];
+    cross(tt0, r2, tmp0);
+    cross(tt1, r1, tmp1);
+    const double n0 = fmax(dot3(tt0, tt0), 1.0e-8), n1 = fmax(dot3(tt1, tt1), 1.0e-8);
+    for (int c = 0; c < 3; ++c) {
+      dedt0[c] = tmp0[c] / n0 * pre;
+      dedt1[c] = tmp1[c] / n1 * pre;
+      r31[c] = p3[c] - p1[c];
+      r42[c] = p4[c] - p2[c];
+    }
+    cross(r2, dedt0, a);
+    for (int c = 0; c < 3; ++c) g[3 * ix[0] + c] += a[c];
+    cross(r31, dedt0, a);
+    cross(r3, dedt1, b);
+    for (int c = 0; c < 3; ++c) g[3 * ix[1] + c] += a[c] - b[c];
+    cross(r0, dedt0, a);
+    cross(r42, dedt1, b);
+    for (int c = 0; c < 3; ++c) g[3 * ix[2] + c] += a[c] + b[c];
+    cross(r2, dedt1, a);
+    for (int c = 0; c < 3; ++c) g[3 * ix[3] + c] += a[c];
+  }
+  return e;
+}
+
 double oracle_mmff_energy_grad(const MmffSystem* s, int mol, const double* pos, double* grad, double* perType) {
   double e[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int t = s->bond.starts[mol]; t < s->bond.starts[mol + 1]; ++t)
@@ -290,7 +409,7 @@ double oracle_mmff_energy_grad(const MmffSystem* s, int mol, const double* pos, 
     e[6] += mmff_ele(pos, s->ele.idx[2 * t], s->ele.idx[2 * t + 1], s->ele.par[3 * t], (int)s->ele.par[3 * t + 1],
                      s->ele.par[3 * t + 2] != 0.0, grad);
   if (perType) memcpy(perType, e, sizeof(e));
-  return e[0] + e[1] + e[2] + e[3] + e[4] + e[5] + e[6];
+  return e[0] + e[1] + e[2] + e[3] + e[4] + e[5] + e[6] + restraint_terms(&s->distc, &s->posc, &s->anglec, &s->torsc, mol, pos, grad);
 }
 
 /* =========================================================================================== DG (dim 3 or 4) */
@@ -865,6 +984,7 @@ typedef struct {
   int32_t        nMols;
   const int32_t* atomCounts;
   TermTable      bond, angle, torsion, inversion, vdw;
+  TermTable      distc, posc, anglec, torsc; /* restraints */
 } UffSystem;
 
 double oracle_uff_energy_grad(const UffSystem* s, int mol, const double* p, double* g) {
@@ -1066,6 +1186,7 @@ double oracle_uff_energy_grad(const UffSystem* s, int mol, const double* p, doub
       }
     }
   }
+  e += restraint_terms(&s->distc, &s->posc, &s->anglec, &s->torsc, mol, p, g);
   return e;
 }
 

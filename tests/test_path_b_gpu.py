@@ -439,3 +439,60 @@ def test_uff_energy_gradient_and_minimize_parity(cuda):
     assert (rel < E_RTOL).mean() >= 0.75 and np.median(rel) < E_RTOL and (rel < 0.1).all(), rel
     energies, coords = UFFOptimizeMoleculesConfs(FlatUFFMolecules(system, b2), maxIters=1000)
     assert np.array_equal(np.array(energies).ravel(), eg)  # a second GPU run: the same bits
+
+
+# ------------------------------------------------------------------ RMS pruning on the device
+def test_rms_pruning_equals_cpu(cuda):
+    """b200mol_rms_prune vs the CPU restatement (different alignment algorithm: Horn quaternion eigenproblem by Jacobi
+    there, closed-form 3x3 singular values here): same keep flags; symmetric self matches and invalid slots honoured."""
+    from nvmolkit_b200.pruning import rms_prune
+
+    rng = np.random.default_rng(61)
+    xyz, cas, mcs, matches, counts = [], [0], [0], [], []
+    for m in range(12):
+        n = int(rng.integers(4, 40))
+        base = rng.normal(0, 2.0, (n, 3))
+        n_conf = int(rng.integers(1, 9))
+        for c in range(n_conf):
+            kind = rng.integers(0, 3)
+            if kind == 0 and c:  # rigid copy of an earlier conformer + small noise: must be pruned
+                q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+                q *= np.sign(np.linalg.det(q))
+                x = base @ q.T + rng.normal(0, 3.0, 3) + rng.normal(0, 0.02, (n, 3))
+            elif kind == 1:
+                x = base + rng.normal(0, 0.6, (n, 3))  # around the threshold
+            else:
+                x = rng.normal(0, 2.0, (n, 3))
+            xyz.append(x)
+            cas.append(cas[-1] + n)
+        mcs.append(mcs[-1] + n_conf)
+        counts.append(n)
+        heavy = np.sort(rng.permutation(n)[: max(3, n // 2)])
+        swapped = heavy.copy()
+        swapped[[0, 1]] = swapped[[1, 0]]  # a "symmetry-equivalent" second mapping
+        matches.append(np.stack([heavy, swapped]) if m % 2 else None)
+    xyz = np.concatenate(xyz)
+    valid = (rng.random(len(cas) - 1) < 0.9).astype(np.uint8)
+    for thresh in (0.3, 0.8):
+        for mt in (None, matches):
+            got = rms_prune(torch.from_numpy(xyz).to(cuda), np.array(cas), np.array(mcs), thresh, mt, counts,
+                            valid=torch.from_numpy(valid).to(cuda)).cpu().numpy()
+            want = oracle.rms_prune(xyz, cas, mcs, thresh, mt, valid)
+            assert np.array_equal(got, want), (thresh, mt is None)
+            assert not got[valid == 0].any() and 0 < got.sum() < len(got)
+
+
+def test_embed_with_rms_pruning_on_device_output(cuda):
+    from nvmolkit_b200.embedMolecules import EmbedMolecules, EmbedParameters
+    from nvmolkit_b200.types import CoordinateOutput
+
+    flat, _ = S.random_embed_molecules(6, 5, 10, seed=62)
+    base = EmbedMolecules(flat, EmbedParameters(randomSeed=5), confsPerMolecule=6, maxIterations=30, output=CoordinateOutput.DEVICE)
+    pruned = EmbedMolecules(flat, EmbedParameters(randomSeed=5, pruneRmsThresh=1.5), confsPerMolecule=6, maxIterations=30,
+                            output=CoordinateOutput.DEVICE)  # the reference raises here (src/etkdg.cpp:106-110)
+    assert 0 < pruned.num_conformers <= base.num_conformers
+    for confs in pruned.per_molecule():  # every kept pair is at least 1.5 A apart after alignment
+        pts = [c.cpu().numpy() for c in confs]
+        for i in range(len(pts)):
+            for j in range(i):
+                assert np.sqrt(oracle.best_ssd(pts[i], pts[j]) / len(pts[i])) >= 1.5 - 1e-9
