@@ -119,6 +119,12 @@ def fused_butina(x, cutoff: float, return_centroids: bool = False, stream=None, 
 
     Returns ``(clusters, cluster_sizes[, centroids])`` like the reference: clusters is a list of tuples with the
     centroid first, cluster_sizes the cumulative sizes starting at 0.
+
+    Neighbour predicate: fp64 ``1.0 - c/u <= cutoff`` evaluated exactly (an integer threshold table), the SAME predicate as
+    :func:`butina` on the fp64 distance matrix and as RDKit's ``ClusterData`` on ``1 - BulkTanimotoSimilarity``. The
+    reference's fused path tests ``sim >= float32(1 - cutoff)`` in fp32 (``nvmolkit/_fusedButina.py:172-173``): pairs that
+    sit exactly on the boundary as a ratio of small integers (cutoff 0.3, sim = 7/10: 1 - 0.7 = 0.30000000000000004 > 0.3)
+    are neighbours there and not here. Deliberate: this path agrees with the dense path and with RDKit bit for bit.
     """
     ids, cen = fused_butina_device(x, cutoff, stream=stream, metric=metric)
     clusters, sizes = clusters_from_ids(ids.cpu().numpy(), cen.cpu().numpy())

@@ -186,27 +186,24 @@ __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __
     __syncthreads();
     const unsigned long long c = c0 + warp;
     if (c < nCand) {
-      const int2      rj = cand[c];
-      const uint32_t  j  = static_cast<uint32_t>(rj.y);
-      const uint32_t* yj = y + static_cast<size_t>(j) * words;
-      uint32_t        yw[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) yw[k] = lane + 32 * k < words ? yj[lane + 32 * k] : 0u;
-      for (int s = 0; s < S; ++s) {
-        const uint32_t i = static_cast<uint32_t>(rj.x) * S + s;
-        if (i >= nRows || (symmetric && i >= j)) continue;
-        const uint32_t* xi = x + static_cast<size_t>(i) * words;
-        int             cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (lane + 32 * k < words) cnt += __popc(xi[lane + 32 * k] & yw[k]);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0 && cnt >= thresh[popX[i] + popY[j]]) {
-          atomicAdd(counts + i, sign);
-          if (countsY) atomicAdd(countsY + j, sign);
-          if (edges) hit[atomicAdd(&nHit, 1)] = make_int2(static_cast<int>(i), static_cast<int>(j));
-        }
+      // the S fingerprints of the group side by side: 32 / S lanes each, 128-bit loads, one shuffle tree per group
+      const int2     rj = cand[c];
+      const uint32_t j  = static_cast<uint32_t>(rj.y);
+      const int      G  = 32 / S, sub = lane / G, gl = lane % G;  // S is 1, 2 or 4
+      const uint32_t i  = static_cast<uint32_t>(rj.x) * S + sub;
+      const bool     live = i < nRows && !(symmetric && i >= j);
+      const uint4*   xi = reinterpret_cast<const uint4*>(x + static_cast<size_t>(live ? i : 0) * words);
+      const uint4*   yj = reinterpret_cast<const uint4*>(y + static_cast<size_t>(j) * words);
+      int            cnt = 0;
+      for (int q = gl; q < words / 4; q += G) {
+        const uint4 a = xi[q], b4 = yj[q];
+        cnt += __popc(a.x & b4.x) + __popc(a.y & b4.y) + __popc(a.z & b4.z) + __popc(a.w & b4.w);
+      }
+      for (int o = G >> 1; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (gl == 0 && live && cnt >= thresh[popX[i] + popY[j]]) {
+        atomicAdd(counts + i, sign);
+        if (countsY) atomicAdd(countsY + j, sign);
+        if (edges) hit[atomicAdd(&nHit, 1)] = make_int2(static_cast<int>(i), static_cast<int>(j));
       }
     }
     __syncthreads();
@@ -992,7 +989,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
     g_superposeLast = g_superpose;
     if (!overflow) return true;  // else: the candidate list overflowed (dense graph / loose cutoff), nothing was counted yet
   }
-  g_superposeLast = 1;
+  if (graphPass) g_superposeLast = 1;
   return launchTensorImpl(mode, q, s, 1, nullptr);
 }
 

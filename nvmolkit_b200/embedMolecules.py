@@ -188,6 +188,12 @@ def EmbedMolecules(molecules, params, confsPerMolecule: int = 1, maxIterations: 
     if hardwareOptions is None:
         hardwareOptions = HardwareOptions()
     gpu = int(targetGpu) if targetGpu >= 0 else (hardwareOptions.gpuIds[0] if hardwareOptions.gpuIds else torch.cuda.current_device())
+    if len(hardwareOptions.gpuIds) > 1:
+        import warnings
+
+        warnings.warn("EmbedMolecules runs on one GPU per process (the first of hardwareOptions.gpuIds, or targetGpu); shard "
+                      "molecule ranges over ranks with torch.distributed (nvmolkit_b200.distributed.molecule_range) to use "
+                      f"all of {list(hardwareOptions.gpuIds)}", RuntimeWarning, stacklevel=2)
     if flat_input:
         flat = molecules
     else:

@@ -33,25 +33,39 @@ def _device_result(system: FlatSystem, batch: ConformerBatch, res, gpu: int) -> 
 
 def _optimize(kind_system: FlatSystem, batch: ConformerBatch, max_iters: int, hardwareOptions, output, targetGpu,
               grad_tol: float = 1e-4):
+    """Minimise every conformer. With several ``hardwareOptions.gpuIds`` the size-sorted conformer queue is dealt round-robin
+    to the devices (the reference spreads its batches over all listed GPUs in one process, src/minimizer/bfgs_mmff.cpp:
+    139-157); every device runs its share asynchronously and the results are collected on the target device."""
     if hardwareOptions is None:
         hardwareOptions = HardwareOptions()
-    gpu = int(targetGpu) if targetGpu >= 0 else (hardwareOptions.gpuIds[0] if hardwareOptions.gpuIds else torch.cuda.current_device())
+    gpus = list(hardwareOptions.gpuIds) if hardwareOptions.gpuIds else [torch.cuda.current_device()]
+    gpu = int(targetGpu) if targetGpu >= 0 else gpus[0]
+    order = np.argsort(-np.diff(batch.atom_starts), kind="stable")  # largest conformers first: evens out the persistent CTAs' tail
+    shares = [order[d::len(gpus)] for d in range(len(gpus))]
+    parts = []
+    for dev_id, share in zip(gpus, shares):
+        if len(share) == 0:
+            continue
+        with torch.cuda.device(dev_id):
+            sizes = np.diff(batch.atom_starts)[share]
+            starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+            sub = ConformerBatch(batch.conf_mol[share], starts, batch.positions[rows_of(batch.atom_starts, share)])
+            parts.append((share, starts, minimize(kind_system, sub, max_iters, grad_tol)))  # asynchronous on that device
     with torch.cuda.device(gpu):
-        # size-sorted queue: largest conformers first
-        order = np.argsort(-np.diff(batch.atom_starts), kind="stable")
-        sizes = np.diff(batch.atom_starts)[order]
-        starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
-        rows = rows_of(batch.atom_starts, order)
-        sorted_batch = ConformerBatch(batch.conf_mol[order], starts, batch.positions[rows])
-        res = minimize(kind_system, sorted_batch, max_iters, grad_tol)
-        # back to input order
-        inv = np.argsort(order, kind="stable")
-        pos_sorted = res.positions
-        dev = pos_sorted.device
-        back_rows = rows_of(starts, inv)
-        res.positions = pos_sorted[torch.from_numpy(back_rows).to(dev)]
-        inv_t = torch.from_numpy(inv.astype(np.int64)).to(dev)
-        res.energies, res.status, res.iters = res.energies[inv_t], res.status[inv_t], res.iters[inv_t]
+        dev = torch.device("cuda", gpu)
+        n_conf, n_atoms = batch.n_conf, int(batch.atom_starts[-1])
+        positions = torch.empty((n_atoms, 3), dtype=torch.float64, device=dev)
+        energies = torch.empty(n_conf, dtype=torch.float64, device=dev)
+        status = torch.empty(n_conf, dtype=torch.int8, device=dev)
+        iters = torch.empty(n_conf, dtype=torch.int32, device=dev)
+        for share, starts, r in parts:  # back to input order (peer copies when the part ran on another device)
+            idx = torch.from_numpy(share.astype(np.int64)).to(dev)
+            rows = torch.from_numpy(rows_of(batch.atom_starts, share)).to(dev)
+            positions[rows] = r.positions.reshape(-1, 3).to(dev)
+            energies[idx], status[idx], iters[idx] = r.energies.to(dev), r.status.to(dev), r.iters.to(dev)
+        from nvmolkit_b200.minimizer import MinimizeResult
+
+        res = MinimizeResult(positions, energies, status, iters)
         if output == CoordinateOutput.DEVICE:
             return _device_result(kind_system, batch, res, gpu)
         energies = res.energies.cpu().numpy()
