@@ -114,6 +114,8 @@ def core():
     global _core, _core_tried
     if not _core_tried:
         _core_tried = True
+        if os.environ.get("B200_NO_CORE"):  # (the instrumented builds of tools/ are separate .so files bound through ctypes)
+            return None
         try:
             from nvmolkit_b200 import _core as mod  # noqa: PLC0415
 

@@ -7,6 +7,8 @@ import sys
 
 import numpy as np
 
+os.environ["B200_NO_CORE"] = "1"  # bind the instrumented library through ctypes, not the pybind module of the main one
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nvmolkit_b200 import _lib  # noqa: E402

@@ -8,6 +8,8 @@ import sys
 
 import numpy as np
 
+os.environ["B200_NO_CORE"] = "1"  # bind the instrumented library through ctypes, not the pybind module of the main one
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 out = os.environ.get("B200_TIMING_LIB") or os.path.join(ROOT, "nvmolkit_b200", "lib", "libb200mol_timing.so")
