@@ -183,6 +183,8 @@ def run_b200(args) -> None:
         _lib.set_option("similarity_tensor_cluster", args.tensor_cluster)
     if args.superpose >= 0:
         _lib.set_option("similarity_superpose", args.superpose)
+    if args.superpose_cols >= 0:
+        _lib.set_option("similarity_superpose_cols", args.superpose_cols)
     if args.workload == "conformers":
         legs = run_conformer_legs(args, pool, dev, world, rank)
         if rank == 0:
@@ -327,8 +329,9 @@ def run_b200(args) -> None:
         fp4 = (words * 32) % 256 == 0  # the library's own eligibility rule (tanimoto_tc.cu); else the int8 tile runs
         mult = 4.0 if fp4 else 2.0
         tiles_pairs = unique_pairs(n) / world  # + diagonal-tile overhead (< 0.1 % at 1M)
-        # row superposition: one tensor-core row carries the sum of S fingerprints, so the pass ISSUES 1/S of the
-        # pair-by-pair contraction (the survivors' exact re-count is the separate verify kernel, in phases_ms)
+        # superposition: one tensor-core row (column) carries the sum of S (C) fingerprints, so the pass ISSUES 1/(S C) of
+        # the pair-by-pair contraction (the survivors' exact re-count is the separate verify kernel, in phases_ms);
+        # superS below = S * C = pairs bounded by one accumulator
         superS = max(1, _lib.get_option("similarity_superpose_last")) if fp4_possible(words) else 1
         tops = tiles_pairs / superS * 2.0 * words * 32 / (kernel_ms * 1e-3) / 1e12
         operand_bytes = ((128 + 112) * (words * 32 // 2) / (128.0 * superS * 224.0) if fp4
@@ -337,7 +340,7 @@ def run_b200(args) -> None:
                     "traffic": measured_traffic().get("simTensorKernel<count>") if n == 1_000_000 and world == 1 else None,
                     "kernel": ("simTensorKernel<count, fp4, cluster2> (tcgen05.mma kind::mxf4.block_scale, neighbor_pass_tc)" if fp4
                                else "simTensorKernel<count> (tcgen05.mma kind::i8, neighbor_pass_tc)"),
-                    "kernel_ms": kernel_ms, "ops_per_pair": 2 * words * 32 / superS, "row_superposition": superS,
+                    "kernel_ms": kernel_ms, "ops_per_pair": 2 * words * 32 / superS, "pairs_per_accumulator": superS,
                     "unsuperposed_equivalent_TOPs": tops * superS,
                     "peak_source": f"{mult:.0f} x MEASURED_PEAKS.json bf16_tflops (dense {'fp4' if fp4 else 'u8'} = {mult:.0f} x bf16 rate; of measured)",
                     "hbm_algorithmic_GBps": (n * words * 32 / (2 if fp4 else 1) + 260.0 * n) / (kernel_ms * 1e-3) / 1e9,
@@ -684,6 +687,7 @@ def main() -> None:
     ap.add_argument("--etkdg-cpu-mols", type=int, default=0, help="molecules of that leg's CPU sample (0 = one per host core)")
     ap.add_argument("--tensor-cluster", type=int, default=-1, help="pair-pass tile variant override (testing; -1 = library default)")
     ap.add_argument("--superpose", type=int, default=-1, help="pair-pass row superposition override (testing; -1 = library default)")
+    ap.add_argument("--superpose-cols", type=int, default=-1, help="pair-pass column superposition override (testing; -1 = library default)")
     ap.add_argument("--all-configs", action="store_true", help="run configs 4 and 5 on fewer than 8 GPUs too")
     ap.add_argument("--mmff-mols", type=int, default=100000, help="config 4 size")
     ap.add_argument("--e2e-mols", type=int, default=1000000, help="config 5 size")

@@ -52,13 +52,20 @@ int b200mol_free_async(void* d_ptr, void* stream);
  *   "similarity_superpose"         4 (default), 2 or 1: fingerprints summed into one row operand of the Butina neighbour pass
  *                                  (values 0..4 are exact in fp4): one accumulator then bounds that many pair counts, the
  *                                  few survivors are re-examined exactly by a second kernel; 1 = off
+ *   "similarity_superpose_cols"    4 (default), 2 or 1: the same for the column operand (sums of products stay <= 16,
+ *                                  exact): one accumulator bounds rows x cols pair counts. A pass whose candidate list
+ *                                  overflows (dense graph) reruns with rows only, then unsuperposed - results identical
+ *   "similarity_superpose_auto"    1 (default): a pass over >= 65,536 fingerprints first runs a pilot over a prefix
+ *                                  sample per column factor and keeps the factor a cost model finds cheapest (the
+ *                                  sum of rows x cols random intersections must stay below one true pair's threshold);
+ *                                  0: always start from the configured factors
  *   "butina_min_round_commits"     a parallel Butina round that commits fewer clusters than this hands over to the
  *                                  one-cluster-per-step loop (default 32; 0 = rounds only, >= 1e9 = stepwise only)
  *   "bfgs_ctas_per_sm"             resident CTAs per SM of the minimiser / embedder kernels (default 3 = the register
  *                                  budget they are compiled for) */
 int b200mol_set_option(const char* key, long long value);
-/* Current value of an option; also "similarity_superpose_last": the factor the last neighbour pass really ran with
- * (1 after a candidate-list overflow made it fall back). */
+/* Current value of an option; also "similarity_superpose_last": pairs per accumulator the last neighbour pass really ran with
+ * (1 after a candidate-list overflow made it fall back), and "similarity_candidates_last": how many candidates it listed. */
 int b200mol_get_option(const char* key, long long* value);
 /* Per-phase CUDA-event timing inside the library (off by default). Phases: "neighbor_pass" (the N^2 tile kernel
  * alone), "csr_build", "cluster_loop", "bfgs". b200mol_profile_read waits for the phase's stop event. */

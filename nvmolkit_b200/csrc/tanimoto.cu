@@ -302,6 +302,9 @@ extern int g_tensorFp4;
 extern int g_tensorCluster;
 extern int g_superpose;
 extern int g_superposeLast;
+extern int g_superposeCols;
+extern int g_superposeAuto;
+extern unsigned long long g_candidatesLast;
 long long g_tensorMinPairs = 1ll << 24;  // pair count from which the count mode runs on tcgen05 (< 0: never)
 
 void launchThreshTable(int maxS, double cutoff, uint16_t* thresh, cudaStream_t s) {
@@ -420,6 +423,11 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       B200_REQUIRE(value == 1 || value == 2 || value == 4, "similarity_superpose must be 1, 2 or 4");
       g_superpose = static_cast<int>(value);
     }
+    else if (k == "similarity_superpose_cols") {
+      B200_REQUIRE(value == 1 || value == 2 || value == 4, "similarity_superpose_cols must be 1, 2 or 4");
+      g_superposeCols = static_cast<int>(value);
+    }
+    else if (k == "similarity_superpose_auto") g_superposeAuto = value != 0;
     else if (k == "similarity_tensor_fp4") g_tensorFp4 = value != 0;
     else if (k == "similarity_tensor_cluster") {
       B200_REQUIRE(value >= 0 && value <= 3, "similarity_tensor_cluster must be 0, 1, 2 or 3");
@@ -443,7 +451,10 @@ extern "C" int b200mol_get_option(const char* key, long long* value) {
     else if (k == "similarity_tensor_fp4") *value = g_tensorFp4;
     else if (k == "similarity_tensor_cluster") *value = g_tensorCluster;
     else if (k == "similarity_superpose") *value = g_superpose;
-    else if (k == "similarity_superpose_last") *value = g_superposeLast;  // read-only: the factor the last pass ran with
+    else if (k == "similarity_superpose_cols") *value = g_superposeCols;
+    else if (k == "similarity_superpose_auto") *value = g_superposeAuto;
+    else if (k == "similarity_candidates_last") *value = static_cast<long long>(g_candidatesLast);
+    else if (k == "similarity_superpose_last") *value = g_superposeLast;  // read-only: pairs per accumulator of the last pass
     else if (k == "butina_min_round_commits") *value = g_butinaMinCommits;
     else fail(B200MOL_ERR_INVALID, "unknown option '%s'", key);
   });

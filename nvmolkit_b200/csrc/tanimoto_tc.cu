@@ -68,6 +68,9 @@ struct TcParams {
   // verification kernel. rowSpan = fingerprints per tile row = kTM * superS.
   int                 outTma;  // materialise modes: the epilogue leaves through TMA stores (out 16-byte aligned, nY even)
   int                 superS;
+  int                 superC;   // the same for the columns of the Y operand: one accumulator then bounds superS * superC pair counts
+  uint32_t            colSpan;  // fingerprints per tile column = TN * superC
+  float               alpha;    // (1 - cutoff) / (2 - cutoff), rounded down: a pair can only pass with c >= alpha (|A| + |B|)
   uint32_t            rowSpan;
   uint32_t            groupTiles;  // tile rows per row group (a power of two): kGroupRows fingerprints whatever superS is
   int2*               cand;
@@ -167,17 +170,18 @@ __global__ void superMinPopKernel(const int32_t* __restrict__ pop, size_t n, int
   out[R] = m;
 }
 
-// Exact verification of the candidates of a superposed pass: one warp per (super row R, column j), for each fingerprint
-// i = S R + s of the group the exact count |X_i & Y_j| and the exact integer threshold test; counts for both endpoints
-// and the (i < j) edge list exactly as the unsuperposed epilogue produces them. A CTA gathers the edges of its 8
-// candidates in shared memory and reserves their slots with ONE atomic.
+// Exact verification of the candidates of a superposed pass: one warp per (super row R, super column J), for each of
+// the S * C pairs (i = S R + s, j = C J + c) of the group the exact count |X_i & Y_j| and the exact integer threshold
+// test; counts for both endpoints and the (i < j) edge list exactly as the unsuperposed epilogue produces them. A CTA
+// gathers the edges of its 8 candidates in shared memory and reserves their slots with ONE atomic.
 __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ y, int words,
-                                                             const int2* __restrict__ cand, unsigned long long nCand, int S,
-                                                             uint32_t nRows, int symmetric, const int32_t* __restrict__ popX,
-                                                             const int32_t* __restrict__ popY, const uint16_t* __restrict__ thresh,
-                                                             int sign, int32_t* counts, int32_t* countsY, int2* edges,
-                                                             unsigned long long* edgeCursor, unsigned long long edgeCap) {
-  __shared__ int2               hit[8 * 4];
+                                                             const int2* __restrict__ cand, unsigned long long nCand, int S, int C,
+                                                             uint32_t nRows, uint32_t nCols, int symmetric,
+                                                             const int32_t* __restrict__ popX, const int32_t* __restrict__ popY,
+                                                             const uint16_t* __restrict__ thresh, int sign, int32_t* counts,
+                                                             int32_t* countsY, int2* edges, unsigned long long* edgeCursor,
+                                                             unsigned long long edgeCap) {
+  __shared__ int2               hit[8 * 16];
   __shared__ int                nHit;
   __shared__ unsigned long long base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,14 +190,14 @@ __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __
     __syncthreads();
     const unsigned long long c = c0 + warp;
     if (c < nCand) {
-      // the S fingerprints of the group side by side: 32 / S lanes each, 128-bit loads, one shuffle tree per group
+      // the S * C pairs of the group side by side: 32 / (S C) lanes each, 128-bit loads, one shuffle tree per pair
       const int2     rj = cand[c];
-      const uint32_t j  = static_cast<uint32_t>(rj.y);
-      const int      G  = 32 / S, sub = lane / G, gl = lane % G;  // S is 1, 2 or 4
-      const uint32_t i  = static_cast<uint32_t>(rj.x) * S + sub;
-      const bool     live = i < nRows && !(symmetric && i >= j);
+      const int      G  = 32 / (S * C), sub = lane / G, gl = lane % G;  // S, C are 1, 2 or 4
+      const uint32_t i  = static_cast<uint32_t>(rj.x) * S + sub / C;
+      const uint32_t j  = static_cast<uint32_t>(rj.y) * C + sub % C;
+      const bool     live = i < nRows && j < nCols && !(symmetric && i >= j);
       const uint4*   xi = reinterpret_cast<const uint4*>(x + static_cast<size_t>(live ? i : 0) * words);
-      const uint4*   yj = reinterpret_cast<const uint4*>(y + static_cast<size_t>(j) * words);
+      const uint4*   yj = reinterpret_cast<const uint4*>(y + static_cast<size_t>(live ? j : 0) * words);
       int            cnt = 0;
       for (int q = gl; q < words / 4; q += G) {
         const uint4 a = xi[q], b4 = yj[q];
@@ -345,17 +349,17 @@ struct UnitWalk {
   __device__ void settle(const TcParams& p) {  // make (cycle, inGroup) point at an existing unit, or set done
     const uint32_t unitRows = PAIR ? (p.tilesM + 1) / 2 : p.tilesM;
     for (;;) {
-      if (cycle * p.groupStride * G >= unitRows) {
+      if (static_cast<uint64_t>(cycle) * p.groupStride * G >= unitRows) {
         done = true;
         return;
       }
       group = cycle * p.groupStride + ((cycle & 1u) ? p.groupStride - 1 - p.groupOffset : p.groupOffset);
       units = 0;
-      if (group * G < unitRows) {
+      if (static_cast<uint64_t>(group) * G < unitRows) {
         gRows = min(G, unitRows - group * G);
         // first tile column holding a pair with row < col for the group's top tile row tm0 = group * groupTiles:
-        // (tn + 1) * TN - 1 > tm0 * rowSpan   (rowSpan = fingerprints per tile row)
-        tn0   = p.symmetric ? (group * p.groupTiles * p.rowSpan + 1u) / static_cast<uint32_t>(TN) : 0u;
+        // (tn + 1) * colSpan - 1 > tm0 * rowSpan   (rowSpan / colSpan = fingerprints per tile row / tile column)
+        tn0   = p.symmetric ? (group * p.groupTiles * p.rowSpan + 1u) / p.colSpan : 0u;
         if (tn0 < p.tilesN) units = gRows * ((p.tilesN - tn0 + RUN - 1) / RUN);
       }
       if (inGroup < units) return;
@@ -387,8 +391,8 @@ struct UnitWalk {
     const uint32_t top = PAIR ? 2 * tr : tr;
     // the upper tile decides for both CTAs of a pair (if it has no pair with row < col, neither has the lower one); a
     // lower tile past the end or below the diagonal still runs - its loads are zero-filled / its predicates reject all.
-    // A tile column is useful iff (tn + 1) * TN - 1 > top * rowSpan: monotone in tn, so a run is clipped from the left.
-    if (p.symmetric) tnBeg = max(tnBeg, (top * p.rowSpan + 1u) / static_cast<uint32_t>(TN));
+    // A tile column is useful iff (tn + 1) * colSpan - 1 > top * rowSpan: monotone in tn, so a run is clipped from the left.
+    if (p.symmetric) tnBeg = max(tnBeg, (top * p.rowSpan + 1u) / p.colSpan);
     if (tnBeg >= tnEnd) return false;
     tm = top + (PAIR ? rank : 0u);
     return true;
@@ -401,11 +405,11 @@ uint64_t countUnits(const TcParams& p) {
   const uint32_t G        = PAIR ? p.groupTiles / 2 : p.groupTiles;
   const uint32_t unitRows = PAIR ? (p.tilesM + 1) / 2 : p.tilesM;
   uint64_t       total    = 0;
-  for (uint32_t cycle = 0; cycle * p.groupStride * G < unitRows; ++cycle) {
+  for (uint32_t cycle = 0; static_cast<uint64_t>(cycle) * p.groupStride * G < unitRows; ++cycle) {
     const uint32_t group = cycle * p.groupStride + ((cycle & 1u) ? p.groupStride - 1 - p.groupOffset : p.groupOffset);
-    if (group * G >= unitRows) continue;
+    if (static_cast<uint64_t>(group) * G >= unitRows) continue;
     const uint32_t gRows = std::min(G, unitRows - group * G);
-    const uint32_t tn0   = p.symmetric ? (group * p.groupTiles * p.rowSpan + 1u) / static_cast<uint32_t>(TN) : 0u;
+    const uint32_t tn0   = p.symmetric ? (group * p.groupTiles * p.rowSpan + 1u) / p.colSpan : 0u;
     if (tn0 < p.tilesN) total += static_cast<uint64_t>(gRows) * ((p.tilesN - tn0 + RUN - 1) / RUN);
   }
   return total;
@@ -444,6 +448,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   __shared__ int      popA[2][kTM];
   __shared__ int      colAcc[2][kTN];
   __shared__ int      popBMin[2][kEpiWarps];
+  __shared__ __align__(16) float colAdj[2][FP4 ? kTN : 4];  // fp4 count tile: alpha * |B_j| (rounded down), +inf for columns past the end
 
   const uint32_t smemA    = (smemAddr(smemRaw) + 1023u) & ~1023u;  // (stationary tile: the row operand's K chunks)
   const uint32_t smemBase = smemA + kAResident;                    // the ring
@@ -667,6 +672,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         const int      pb = gc < p.nY ? __ldg(p.popY + gc) : 0;
         popB[as][c]       = pb;
         colAcc[as][c]     = 0;
+        if constexpr (FP4) colAdj[as][c] = gc < p.nY ? __fmul_rd(p.alpha, static_cast<float>(pb)) : 3.0e38f;
         if (gc < p.nY) minPb = min(minPb, pb);
       }
       tnOf[as] = tn;
@@ -693,8 +699,12 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         for (int k = 1; k < kEpiWarps; ++k) mpb = min(mpb, popBMin[as][k]);
         thMin = (gr < p.n && mpb < 0x3fffffff) ? static_cast<int>(threshLoS[pa + mpb]) : 0x3fffffff;  // no valid pair: all out
       }
-      const float fThMin = static_cast<float>(thMin);
-      (void)fThMin;
+      // fp4 count tile: a pair (or a superposed group of pairs) can only pass with c >= alpha (|A| + |B|) (the exact
+      // threshold is the smallest integer the fp64 predicate accepts, never below alpha S - 1e-12), so the pre-filter is
+      //   acc - alpha |B_j|  >=  alpha |A_i| - 1/2        (both products rounded down: conservative)
+      // per column, instead of one bound from the smallest |B| of the whole tile.
+      const float fRowTh = gr < p.n ? __fmul_rd(p.alpha, static_cast<float>(pa)) - 0.5f : 3.0e38f;
+      (void)fRowTh;
       {
         TC_T0();
         mbarWait(&tmemFull[as], accPhase);
@@ -813,14 +823,28 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         uint32_t maybe = 0;
         bool     hot;
         if constexpr (FP4) {
+          const float4* adj4 = reinterpret_cast<const float4*>(&colAdj[as][cb * 32]);
+          float         vv[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = adj4[j];  // (the same address for every lane: a broadcast read)
+            vv[4 * j]     = __uint_as_float(r[4 * j]) - a.x;
+            vv[4 * j + 1] = __uint_as_float(r[4 * j + 1]) - a.y;
+            vv[4 * j + 2] = __uint_as_float(r[4 * j + 2]) - a.z;
+            vv[4 * j + 3] = __uint_as_float(r[4 * j + 3]) - a.w;
+          }
           float m[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 16]));
+          for (int j = 0; j < 16; ++j) m[j] = fmaxf(vv[j], vv[j + 16]);
 #pragma unroll
           for (int w = 8; w >= 1; w >>= 1)
 #pragma unroll
             for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
-          hot = m[0] >= fThMin;
+          hot = m[0] >= fRowTh;
+          if (hot) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) maybe |= (vv[j] >= fRowTh ? 1u : 0u) << j;
+          }
         } else {
           int m[16];
 #pragma unroll
@@ -830,23 +854,23 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
 #pragma unroll
             for (int j = 0; j < w; ++j) m[j] = max(m[j], m[j + w]);
           hot = m[0] >= thMin;
-        }
-        if (hot) {
+          if (hot) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if constexpr (FP4) maybe |= (__uint_as_float(r[j]) >= fThMin ? 1u : 0u) << j;
-            else maybe |= (static_cast<int>(r[j]) >= thMin ? 1u : 0u) << j;
+            for (int j = 0; j < 32; ++j) maybe |= (static_cast<int>(r[j]) >= thMin ? 1u : 0u) << j;
           }
         }
         uint32_t mask = 0;
-        if (p.superS > 1) {
-          // superposed rows: the accumulator is the SUM of superS pair counts, so "sum < smallest threshold of the group"
-          // rejected all of them above; what is left goes to the exact verification kernel as (super row, column)
+        if (p.superS * p.superC > 1) {
+          // superposed operands: the accumulator is the SUM of superS * superC pair counts, so "sum below the smallest
+          // threshold any pair of the group can have" rejected all of them above; what is left goes to the exact
+          // verification kernel as (super row, super column)
           while (maybe) {
             const int j = __ffs(maybe) - 1;
             maybe &= maybe - 1;
             const uint32_t gc = tn * TN + cb * 32 + j;
-            if (gr < p.n && gc < p.nY && (!p.symmetric || gr * static_cast<uint32_t>(p.superS) < gc)) mask |= 1u << j;
+            if (gr < p.n && gc < p.nY &&
+                (!p.symmetric || gr * static_cast<uint32_t>(p.superS) + 1u < (gc + 1u) * static_cast<uint32_t>(p.superC)))
+              mask |= 1u << j;
           }
           if (__ballot_sync(0xffffffffu, mask != 0)) {
             const int mine = __popc(mask);
@@ -972,28 +996,71 @@ extern "C" void b200mol_debug_clocks_tc(unsigned long long* out8) {
 }
 #endif
 
-int g_superpose = 4;  // fingerprints summed into one row of the count pass (option "similarity_superpose": 1, 2 or 4)
-int g_superposeLast = 0;  // what the last tensor count pass really ran with (1 after an overflow fallback); b200mol_get_option
+int g_superpose = 4;      // fingerprints summed into one row of the count pass (option "similarity_superpose": 1, 2 or 4)
+int g_superposeCols = 4;  // ... and into one column ("similarity_superpose_cols": 1, 2 or 4); 4 x 4 sums stay <= 16, exact
+int g_superposeLast = 0;  // pairs per accumulator the last graph pass really ran with (1 after an overflow fallback)
 
-static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, int superS, bool* overflow);
+int g_superposeAuto = 1;  // 1: a large graph pass picks rows x cols from a pilot over one row group ("similarity_superpose_auto")
+unsigned long long g_candidatesLast = 0;  // candidates the last superposed pass listed ("similarity_candidates_last")
+
+static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, int superS, int superC, bool* overflow,
+                             unsigned long long* pilotCand = nullptr);
 
 // Count / materialise modes on tensor cores. Returns false when the problem shape is not eligible (caller uses the SIMT tile).
 bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
-  // Row superposition serves the Butina passes (symmetric and / or with an edge list): they synchronise for their edge
+  // Superposition serves the Butina passes (symmetric and / or with an edge list): they synchronise for their edge
   // total anyway, and the superposed pass needs one host read of its candidate count. The plain thresholded count
   // (b200mol_tanimoto_count_ge) stays asynchronous on the unsuperposed tile.
   const bool graphPass = mode == kCountTanimoto && (q.symmetric || q.edges != nullptr);
-  if (graphPass && g_superpose > 1) {
-    bool overflow = false;
-    if (!launchTensorImpl(mode, q, s, g_superpose, &overflow)) return false;
-    g_superposeLast = g_superpose;
-    if (!overflow) return true;  // else: the candidate list overflowed (dense graph / loose cutoff), nothing was counted yet
+  if (!graphPass || g_superpose * g_superposeCols == 1) {
+    if (graphPass) g_superposeLast = 1;
+    return launchTensorImpl(mode, q, s, 1, 1, nullptr);
   }
-  if (graphPass) g_superposeLast = 1;
-  return launchTensorImpl(mode, q, s, 1, nullptr);
+  int S = g_superpose, C = g_superposeCols;
+  // How far superposition pays depends on the data: the sum of S C random intersections must stay below the threshold
+  // ONE true neighbour pair reaches, or every accumulator is a candidate. A pilot over a prefix sample of the
+  // fingerprints (at most 1/64 of the pairs; candidates listed but nothing counted) measures the candidate rate of each
+  // column factor, widest first; the model
+  //   time(S, C) = pairs / (S C) * tPair + candidates * S C * tVerify
+  // (tile and verify rates measured on B200, profiles/r02_path_a_summary.md) picks the cheapest. A narrower factor can
+  // only win while the wider one spends more time verifying than multiplying, so the search stops as soon as it does not.
+  if (g_superposeAuto && q.nX >= 8 * static_cast<size_t>(kGroupRows) && C > 1) {
+    const double nX = static_cast<double>(q.nX), nY = static_cast<double>(q.nY);
+    SimLaunch pilot   = q;
+    pilot.groupOffset = 0;
+    pilot.groupStride = 1;
+    pilot.nX          = std::min<size_t>(65536, std::max<size_t>(2 * kGroupRows, q.nX / 8));
+    pilot.nY          = q.symmetric ? pilot.nX : std::min<size_t>(q.nY, std::max<size_t>(pilot.nX, q.nY / 8));
+    const double sX = static_cast<double>(pilot.nX), sY = static_cast<double>(pilot.nY);
+    const double pilotPairs = q.symmetric ? sX * (sX - 1) / 2.0 : sX * sY;
+    const double totalPairs = (q.symmetric ? nX * (nX - 1) / 2.0 : nX * nY) / (q.groupStride < 1 ? 1 : q.groupStride);
+    constexpr double tPair = 0.85e-12, tVerify = 0.1e-9;  // seconds per unsuperposed pair / per verified pair
+    double bestT = totalPairs * tPair;  // unsuperposed
+    int    bestS = 1, bestC = 1;
+    for (int c = C; c >= 1; c >>= 1) {
+      unsigned long long got = 0;
+      if (!launchTensorImpl(mode, pilot, s, S, c, nullptr, &got)) return false;
+      const double tPass = totalPairs / (S * c) * tPair;
+      const double tVer  = static_cast<double>(got) * totalPairs / pilotPairs * S * c * tVerify;
+      if (tPass + tVer < bestT) bestT = tPass + tVer, bestS = S, bestC = c;
+      if (tVer <= tPass) break;
+    }
+    S = bestS, C = bestC;
+  }
+  while (S * C > 1) {
+    bool overflow = false;
+    if (!launchTensorImpl(mode, q, s, S, C, &overflow)) return false;
+    g_superposeLast = S * C;
+    if (!overflow) return true;  // else: the candidate list overflowed (dense graph / loose cutoff), nothing was counted yet
+    if (C > 1) C = 1;            // second chance: rows only
+    else S = 1;
+  }
+  g_superposeLast = 1;
+  return launchTensorImpl(mode, q, s, 1, 1, nullptr);
 }
 
-static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, int superS, bool* overflow) {
+static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, int superS, int superC, bool* overflow,
+                             unsigned long long* pilotCand) {
   if (mode == kCountCosine) return false;
   const int bits = q.words * 32;
   if (bits % kTK != 0 || bits > 4096) return false;
@@ -1006,18 +1073,22 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   const bool fp4   = count && g_tensorFp4 && bits % (2 * kTK) == 0;
   const int  tn    = fp4 ? kTNFp4 : kTN;
   const int  rowBytes = fp4 ? bits / 2 : bits;  // bytes of one expanded fingerprint
-  if (superS > 1 && !fp4) superS = 1;  // the superposed sums need the fp4 value set {0..4}
-  const size_t nSuper = (q.nX + superS - 1) / superS;  // rows of the X operand
+  if (!fp4) superS = superC = 1;  // the superposed sums need the fp4 value set {0..4}
+  const bool   super  = superS * superC > 1;
+  const size_t nSuper = (q.nX + superS - 1) / superS;   // rows of the X operand
+  const size_t nSuperY = (q.nY + superC - 1) / superC;  // rows of the Y operand (tile columns)
 
   TcParams p{};
   p.n         = static_cast<uint32_t>(nSuper);
-  p.nY        = static_cast<uint32_t>(q.nY);
+  p.nY        = static_cast<uint32_t>(nSuperY);
   p.kChunks   = rowBytes / kTK;
   p.tilesM    = static_cast<uint32_t>((nSuper + kTM - 1) / kTM);
   p.superS    = superS;
+  p.superC    = superC;
   p.rowSpan   = static_cast<uint32_t>(kTM * superS);
+  p.colSpan   = static_cast<uint32_t>(tn * superC);
   p.groupTiles = static_cast<uint32_t>(kGroupRows / (kTM * superS));
-  p.tilesN    = static_cast<uint32_t>((q.nY + tn - 1) / tn);
+  p.tilesN    = static_cast<uint32_t>((nSuperY + tn - 1) / tn);
   p.symmetric = q.symmetric ? 1 : 0;
   p.groupOffset = q.groupOffset;
   p.groupStride = q.groupStride < 1 ? 1 : q.groupStride;
@@ -1029,47 +1100,58 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   p.edgeCap   = q.edgeCap;
   p.out       = q.out;
   p.recipLen  = 2 * bits;
-
-  // 0/1 expansion of the fingerprints: bytes (2 KB per 2048-bit row) or packed fp4 (1 KB); with superposition the X
-  // operand is the sum of superS consecutive expansions and the Y operand always the plain one
-  const bool       ownY = !same || superS > 1;
-  Scratch<uint8_t> expX(nSuper * static_cast<size_t>(rowBytes), s);
-  Scratch<uint8_t> expYown(ownY ? q.nY * static_cast<size_t>(rowBytes) : 0, s);
-  if (superS > 1) {
-    const size_t nw = nSuper * static_cast<size_t>(q.words);
-    expandBitsFp4SuperKernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(q.x, q.nX, q.words, superS, nSuper,
-                                                                                      reinterpret_cast<uint4*>(expX.get()));
-    B200_LAUNCHED();
-    const size_t nwy = q.nY * static_cast<size_t>(q.words);
-    expandBitsFp4Kernel<<<static_cast<unsigned>((nwy + 255) / 256), 256, 0, s>>>(q.y, nwy, reinterpret_cast<uint4*>(expYown.get()));
-    B200_LAUNCHED();
-  } else {
-    auto expand = [&](const uint32_t* src, size_t rows, uint8_t* dst) {
-      const size_t nw = rows * static_cast<size_t>(q.words);
-      if (fp4) expandBitsFp4Kernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(src, nw, reinterpret_cast<uint4*>(dst));
-      else expandBitsKernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, s>>>(src, nw, reinterpret_cast<uint4*>(dst));
-      B200_LAUNCHED();
-    };
-    expand(q.x, q.nX, expX.get());
-    if (!same) expand(q.y, q.nY, expYown.get());
+  {
+    // a pair passes iff 1 - c / (|A| + |B| - c) <= cutoff, i.e. c >= alpha (|A| + |B|); the pre-filter's alpha is rounded
+    // DOWN (and its products too), so it never rejects what the exact fp64 table accepts
+    const double a  = q.cutoff < 2.0 ? (1.0 - q.cutoff) / (2.0 - q.cutoff) : 0.0;
+    float        af = static_cast<float>(a);
+    if (static_cast<double>(af) > a) af = nextafterf(af, -1.0f);
+    p.alpha = nextafterf(af, -1.0f);  // (one more ulp: fp64 rounding inside the table's predicate)
   }
+
+  // 0/1 expansion of the fingerprints: bytes (2 KB per 2048-bit row) or packed fp4 (1 KB); a superposed operand is the
+  // sum of superS (superC) consecutive expansions. X and Y share one buffer when they are the same set, summed alike.
+  const bool       ownY = !same || superS != superC;
+  Scratch<uint8_t> expX(nSuper * static_cast<size_t>(rowBytes), s);
+  Scratch<uint8_t> expYown(ownY ? nSuperY * static_cast<size_t>(rowBytes) : 0, s);
+  auto expand = [&](const uint32_t* src, size_t rows, int S, size_t superRows, uint8_t* dst) {
+    const size_t nw = superRows * static_cast<size_t>(q.words);
+    const auto   grid = static_cast<unsigned>((nw + 255) / 256);
+    if (S > 1) expandBitsFp4SuperKernel<<<grid, 256, 0, s>>>(src, rows, q.words, S, superRows, reinterpret_cast<uint4*>(dst));
+    else if (fp4) expandBitsFp4Kernel<<<grid, 256, 0, s>>>(src, nw, reinterpret_cast<uint4*>(dst));
+    else expandBitsKernel<<<grid, 256, 0, s>>>(src, nw, reinterpret_cast<uint4*>(dst));
+    B200_LAUNCHED();
+  };
+  expand(q.x, q.nX, superS, nSuper, expX.get());
+  if (ownY) expand(q.y, q.nY, superC, nSuperY, expYown.get());
   const uint8_t* expY = ownY ? expYown.get() : expX.get();
 
-  Scratch<int32_t> popX(q.nX, s), popYown(same ? 0 : q.nY, s), popSuper(superS > 1 ? nSuper : 0, s);
+  Scratch<int32_t> popX(q.nX, s), popYown(same ? 0 : q.nY, s);
+  Scratch<int32_t> popSuper(superS > 1 ? nSuper : 0, s), popSuperY(superC > 1 && ownY ? nSuperY : 0, s);
   launchRowPopcount(q.x, q.nX, q.words, popX.get(), s);
   if (!same) launchRowPopcount(q.y, q.nY, q.words, popYown.get(), s);
+  const int32_t* popYExact = same ? popX.get() : popYown.get();
   p.popX = popX.get();
-  p.popY = same ? popX.get() : popYown.get();
-  // candidates of a superposed pass: (super row, column) pairs the exact kernel re-examines. Sized for the neighbour
-  // graphs this pass is used on (tens of edges per point); a denser graph overflows it and the caller falls back.
-  unsigned long long          candCap = 0;
-  Scratch<int2>               cand;
-  Scratch<unsigned long long> candCursor;
+  p.popY = popYExact;
   if (superS > 1) {
     superMinPopKernel<<<static_cast<unsigned>((nSuper + 255) / 256), 256, 0, s>>>(popX.get(), q.nX, superS, nSuper, popSuper.get());
     B200_LAUNCHED();
     p.popX = popSuper.get();
-    const unsigned long long all = static_cast<unsigned long long>(nSuper) * q.nY;
+  }
+  if (superC > 1) {
+    if (ownY) {
+      superMinPopKernel<<<static_cast<unsigned>((nSuperY + 255) / 256), 256, 0, s>>>(popYExact, q.nY, superC, nSuperY, popSuperY.get());
+      B200_LAUNCHED();
+      p.popY = popSuperY.get();
+    } else p.popY = popSuper.get();
+  }
+  // candidates of a superposed pass: (super row, super column) pairs the exact kernel re-examines. Sized for the
+  // neighbour graphs this pass is used on (tens of edges per point); a denser graph overflows it and the caller falls back.
+  unsigned long long          candCap = 0;
+  Scratch<int2>               cand;
+  Scratch<unsigned long long> candCursor;
+  if (super) {
+    const unsigned long long all = static_cast<unsigned long long>(nSuper) * nSuperY;
     candCap                      = std::min<unsigned long long>(all, std::max<unsigned long long>(1ull << 22, 64ull * q.nX));
     cand                         = Scratch<int2>(candCap, s);
     candCursor                   = Scratch<unsigned long long>(1, s);
@@ -1091,7 +1173,7 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   const bool cluster = fp4 && g_tensorCluster != 0;  // CTA pairs: 1 = multicast column operand, 2 = cta_group::2 MMAs,
   const bool pairMma = cluster && g_tensorCluster == 2;  // 3 = multicast column operand + stationary row operand
   const bool stationary = cluster && g_tensorCluster == 3 && p.kChunks <= kMaxChunksStat;
-  makeTensorMap2D(&tmB, expY, q.nY, rowBytes, cluster ? tn / 2 : tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  makeTensorMap2D(&tmB, expY, nSuperY, rowBytes, cluster ? tn / 2 : tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
 
   CUtensorMap tmOut = tmA;  // (unused in the count mode)
   if (!count) {
@@ -1158,11 +1240,16 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, tmOut, p);
   }
   B200_LAUNCHED();
-  if (superS > 1) {
+  if (super) {
     // the one host read of a superposed pass: how many candidates (the callers synchronise for their edge total anyway)
     unsigned long long nCand = 0;
     B200_CUDA(cudaMemcpyAsync(&nCand, candCursor.get(), sizeof(nCand), cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaStreamSynchronize(s));
+    if (pilotCand) {  // dry run over one row group: the candidate count is the result
+      *pilotCand = nCand;
+      return true;
+    }
+    g_candidatesLast = nCand;
     if (nCand > candCap) {
       if (overflow) *overflow = true;  // nothing has been counted yet: the caller reruns without superposition
       return true;
@@ -1170,10 +1257,10 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     if (nCand) {
       PhaseTimer         t("verify_candidates", s);
       const unsigned int blocks2 = static_cast<unsigned int>(std::min<unsigned long long>((nCand + 7) / 8, static_cast<unsigned long long>(smCount()) * 16));
-      verifyCandidatesKernel<<<blocks2, 256, 0, s>>>(q.x, q.y, q.words, cand.get(), nCand, superS, static_cast<uint32_t>(q.nX),
-                                                     q.symmetric ? 1 : 0, popX.get(), same ? popX.get() : popYown.get(),
-                                                     thresh.get(), q.sign, q.rowCounts, q.symmetric ? q.rowCounts : nullptr,
-                                                     q.edges, q.edgeCursor, q.edgeCap);
+      verifyCandidatesKernel<<<blocks2, 256, 0, s>>>(q.x, q.y, q.words, cand.get(), nCand, superS, superC,
+                                                     static_cast<uint32_t>(q.nX), static_cast<uint32_t>(q.nY), q.symmetric ? 1 : 0,
+                                                     popX.get(), popYExact, thresh.get(), q.sign, q.rowCounts,
+                                                     q.symmetric ? q.rowCounts : nullptr, q.edges, q.edgeCursor, q.edgeCap);
       B200_LAUNCHED();
     }
   }

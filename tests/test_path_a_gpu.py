@@ -281,22 +281,26 @@ def test_butina_parallel_rounds_keep_the_greedy_order(cuda, min_commits, n, degr
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05 int8) path of the count pass
-@pytest.fixture(params=[(1, 4), (0, 4), (2, 4), (3, 4), (1, 1), (3, 1), (0, 2)],
-                ids=["multicast_pair-super4", "single_cta-super4", "pair_mma-super4", "row_stationary-super4",
-                     "multicast_pair-plain", "row_stationary-plain", "single_cta-super2"])
+@pytest.fixture(params=[(1, 4, 4), (0, 4, 4), (2, 4, 4), (3, 4, 4), (1, 1, 1), (3, 1, 1), (0, 2, 1), (1, 4, 1), (1, 1, 4),
+                        (0, 2, 4)],
+                ids=["multicast_pair-super4x4", "single_cta-super4x4", "pair_mma-super4x4", "row_stationary-super4x4",
+                     "multicast_pair-plain", "row_stationary-plain", "single_cta-super2x1", "multicast_pair-super4x1",
+                     "multicast_pair-super1x4", "single_cta-super2x4"])
 def force_tensor_path(cuda, request):
     """Every test that takes this fixture runs on all four tile variants of the fp4 count pass:
     similarity_tensor_cluster = 1 (CTA pair, multicast column operand), 0 (one CTA per tile),
     2 (CTA pair with tcgen05 cta_group::2 MMAs), 3 (CTA pair, multicast column operand, row operand stationary) - crossed
-    with the row superposition of the Butina neighbour pass (4 = default, 2, 1 = off)."""
+    with the row x column superposition of the Butina neighbour pass (4 x 4 = default ... 1 x 1 = off)."""
     from nvmolkit_b200 import _lib
 
     _lib.set_option("similarity_tensor_min_pairs", 0)
     _lib.set_option("similarity_tensor_cluster", request.param[0])
     _lib.set_option("similarity_superpose", request.param[1])
+    _lib.set_option("similarity_superpose_cols", request.param[2])
     yield request.param
     _lib.set_option("similarity_tensor_cluster", 1)
     _lib.set_option("similarity_superpose", 4)
+    _lib.set_option("similarity_superpose_cols", 4)
     _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
 
 
@@ -337,19 +341,49 @@ def test_tensor_neighbor_counts_on_a_many_tile_problem(cuda, force_tensor_path):
     assert (ids.cpu().numpy() == ids_cpu).all() and (cen.cpu().numpy() == cen_cpu).all()
 
 
-def test_superposed_pass_falls_back_when_its_candidate_list_overflows(cuda):
-    """6,000 identical fingerprints: every pair is an edge, so the superposed pass lists ~4.5 M candidates, more than its
-    list holds; nothing may have been counted when it notices, and the unsuperposed rerun must give the exact answer."""
+def test_pilot_chosen_superposition_gives_the_unsuperposed_answer(cuda):
+    """70,000 points: the neighbour pass first runs its pilot over a prefix sample per column factor, picks a factor,
+    then runs; cluster ids and centroids must equal those of the unsuperposed pass (which the smaller tests pin
+    to the oracle). Dense (p = 0.08) and sparse (p = 0.02) fingerprints make the pilot choose differently."""
     from nvmolkit_b200 import _lib
     from nvmolkit_b200.clustering import fused_butina_device
 
-    one = np.repeat(S.random_fingerprints(1, seed=3), 6000, axis=0)
+    _lib.set_option("similarity_tensor_min_pairs", 0)
+    try:
+        chosen = []
+        for dens in (0.08, 0.02):
+            fp = S.random_fingerprints(70_000, p=dens, seed=5, near_dups=30_000)
+            dev = _dev(fp, cuda)
+            ids, cen = fused_butina_device(dev, 0.35)
+            chosen.append(_lib.get_option("similarity_superpose_last"))
+            _lib.set_option("similarity_superpose", 1)
+            _lib.set_option("similarity_superpose_cols", 1)
+            ids1, cen1 = fused_butina_device(dev, 0.35)
+            _lib.set_option("similarity_superpose", 4)
+            _lib.set_option("similarity_superpose_cols", 4)
+            assert torch.equal(ids, ids1) and torch.equal(cen, cen1)
+        assert chosen == [4, 16], chosen  # sparse rows carry 4 x 4 sums, dense ones only rows
+    finally:
+        _lib.set_option("similarity_superpose", 4)
+        _lib.set_option("similarity_superpose_cols", 4)
+        _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
+
+
+def test_superposed_pass_falls_back_when_its_candidate_list_overflows(cuda):
+    """12,000 identical fingerprints: every pair is an edge, so the 4 x 4 superposed pass lists ~4.5 M candidates and its
+    4 x 1 rerun ~18 M, both more than the list holds; nothing may have been counted when they notice, and the unsuperposed
+    rerun must give the exact answer."""
+    from nvmolkit_b200 import _lib
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    one = np.repeat(S.random_fingerprints(1, seed=3), 12000, axis=0)
     _lib.set_option("similarity_tensor_min_pairs", 0)
     try:
         ids, cen = fused_butina_device(_dev(one, cuda), 0.3)
+        assert _lib.get_option("similarity_superpose_last") == 1
     finally:
         _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
-    assert (ids.cpu().numpy() == 0).all() and cen.cpu().numpy().tolist() == [5999]
+    assert (ids.cpu().numpy() == 0).all() and cen.cpu().numpy().tolist() == [11999]
 
 
 def test_tensor_and_simt_paths_agree_on_identical_rows(cuda, force_tensor_path):
