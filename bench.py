@@ -183,6 +183,8 @@ def run_b200(args) -> None:
         _lib.set_option("similarity_tensor_cluster", args.tensor_cluster)
     if args.superpose >= 0:
         _lib.set_option("similarity_superpose", args.superpose)
+    if args.bfgs_l2_persist:
+        _lib.set_option("bfgs_l2_persist", 1)
     if args.superpose_cols >= 0:
         _lib.set_option("similarity_superpose_cols", args.superpose_cols)
     if args.workload == "conformers":
@@ -687,6 +689,7 @@ def main() -> None:
     ap.add_argument("--etkdg-cpu-mols", type=int, default=0, help="molecules of that leg's CPU sample (0 = one per host core)")
     ap.add_argument("--tensor-cluster", type=int, default=-1, help="pair-pass tile variant override (testing; -1 = library default)")
     ap.add_argument("--superpose", type=int, default=-1, help="pair-pass row superposition override (testing; -1 = library default)")
+    ap.add_argument("--bfgs-l2-persist", action="store_true", help="mark the minimisers' inverse-Hessian slabs persisting in L2 (experiment)")
     ap.add_argument("--superpose-cols", type=int, default=-1, help="pair-pass column superposition override (testing; -1 = library default)")
     ap.add_argument("--all-configs", action="store_true", help="run configs 4 and 5 on fewer than 8 GPUs too")
     ap.add_argument("--mmff-mols", type=int, default=100000, help="config 4 size")

@@ -344,14 +344,14 @@ def test_tensor_neighbor_counts_on_a_many_tile_problem(cuda, force_tensor_path):
 def test_pilot_chosen_superposition_gives_the_unsuperposed_answer(cuda):
     """70,000 points: the neighbour pass first runs its pilot over a prefix sample per column factor, picks a factor,
     then runs; cluster ids and centroids must equal those of the unsuperposed pass (which the smaller tests pin
-    to the oracle). Dense (p = 0.08) and sparse (p = 0.02) fingerprints make the pilot choose differently."""
+    to the oracle). Dense (p = 0.08) and sparse (p = 0.012) fingerprints make the pilot choose differently."""
     from nvmolkit_b200 import _lib
     from nvmolkit_b200.clustering import fused_butina_device
 
     _lib.set_option("similarity_tensor_min_pairs", 0)
     try:
         chosen = []
-        for dens in (0.08, 0.02):
+        for dens in (0.08, 0.012):
             fp = S.random_fingerprints(70_000, p=dens, seed=5, near_dups=30_000)
             dev = _dev(fp, cuda)
             ids, cen = fused_butina_device(dev, 0.35)
