@@ -343,6 +343,7 @@ def run_b200(args) -> None:
                     "kernel": ("simTensorKernel<count, fp4, cluster2> (tcgen05.mma kind::mxf4.block_scale, neighbor_pass_tc)" if fp4
                                else "simTensorKernel<count> (tcgen05.mma kind::i8, neighbor_pass_tc)"),
                     "kernel_ms": kernel_ms, "ops_per_pair": 2 * words * 32 / superS, "pairs_per_accumulator": superS,
+                    "candidates_verified": _lib.get_option("similarity_candidates_last") if superS > 1 else 0,
                     "unsuperposed_equivalent_TOPs": tops * superS,
                     "peak_source": f"{mult:.0f} x MEASURED_PEAKS.json bf16_tflops (dense {'fp4' if fp4 else 'u8'} = {mult:.0f} x bf16 rate; of measured)",
                     "hbm_algorithmic_GBps": (n * words * 32 / (2 if fp4 else 1) + 260.0 * n) / (kernel_ms * 1e-3) / 1e9,

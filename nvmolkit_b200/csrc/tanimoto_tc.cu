@@ -172,8 +172,9 @@ __global__ void superMinPopKernel(const int32_t* __restrict__ pop, size_t n, int
 
 // Exact verification of the candidates of a superposed pass: one warp per (super row R, super column J), for each of
 // the S * C pairs (i = S R + s, j = C J + c) of the group the exact count |X_i & Y_j| and the exact integer threshold
-// test; counts for both endpoints and the (i < j) edge list exactly as the unsuperposed epilogue produces them. A CTA
-// gathers the edges of its 8 candidates in shared memory and reserves their slots with ONE atomic.
+// test; counts for both endpoints and the (i < j) edge list exactly as the unsuperposed epilogue produces them.
+// Warps are independent (no block barrier): each keeps two candidates in flight (all of their 128-bit loads are issued
+// before the first popcount) and parks its edges in 64 shared-memory slots that leave with ONE global atomic per flush.
 __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ y, int words,
                                                              const int2* __restrict__ cand, unsigned long long nCand, int S, int C,
                                                              uint32_t nRows, uint32_t nCols, int symmetric,
@@ -181,43 +182,79 @@ __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __
                                                              const uint16_t* __restrict__ thresh, int sign, int32_t* counts,
                                                              int32_t* countsY, int2* edges, unsigned long long* edgeCursor,
                                                              unsigned long long edgeCap) {
-  __shared__ int2               hit[8 * 16];
-  __shared__ int                nHit;
-  __shared__ unsigned long long base;
+  constexpr int kStage = 64, kFlight = 1, kChunk = 64;  // a block takes 64 consecutive candidates at a time: the epilogue
+  // warp that listed them worked on ONE quarter of a tile row (32 super rows = 32 KB of fingerprints), so most of their
+  // row operands are L1 hits for the block
+  __shared__ int2 stage[8][kStage];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (unsigned long long c0 = static_cast<unsigned long long>(blockIdx.x) * 8; c0 < nCand; c0 += static_cast<unsigned long long>(gridDim.x) * 8) {
-    if (threadIdx.x == 0) nHit = 0;
-    __syncthreads();
-    const unsigned long long c = c0 + warp;
-    if (c < nCand) {
-      // the S * C pairs of the group side by side: 32 / (S C) lanes each, 128-bit loads, one shuffle tree per pair
-      const int2     rj = cand[c];
-      const int      G  = 32 / (S * C), sub = lane / G, gl = lane % G;  // S, C are 1, 2 or 4
-      const uint32_t i  = static_cast<uint32_t>(rj.x) * S + sub / C;
-      const uint32_t j  = static_cast<uint32_t>(rj.y) * C + sub % C;
-      const bool     live = i < nRows && j < nCols && !(symmetric && i >= j);
-      const uint4*   xi = reinterpret_cast<const uint4*>(x + static_cast<size_t>(live ? i : 0) * words);
-      const uint4*   yj = reinterpret_cast<const uint4*>(y + static_cast<size_t>(live ? j : 0) * words);
-      int            cnt = 0;
-      for (int q = gl; q < words / 4; q += G) {
-        const uint4 a = xi[q], b4 = yj[q];
-        cnt += __popc(a.x & b4.x) + __popc(a.y & b4.y) + __popc(a.z & b4.z) + __popc(a.w & b4.w);
+  const int G = 32 / (S * C), sub = lane / G, gl = lane % G;  // S, C are 1, 2 or 4: G lanes per pair
+  const int chunks = words / 4;                                // uint4 per fingerprint
+  int       nStaged = 0;
+  auto flush = [&]() {
+    if (nStaged == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(edgeCursor, static_cast<unsigned long long>(nStaged));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (int k = lane; k < nStaged; k += 32)
+      if (base + k < edgeCap) edges[base + k] = stage[warp][k];
+    __syncwarp();
+    nStaged = 0;
+  };
+  for (unsigned long long chunk = static_cast<unsigned long long>(blockIdx.x) * kChunk; chunk < nCand; chunk += static_cast<unsigned long long>(gridDim.x) * kChunk)
+  for (int it = 0; it < kChunk / (8 * kFlight); ++it) {
+    const unsigned long long c0 = chunk + static_cast<unsigned long long>(it) * 8 * kFlight + warp * kFlight;
+    if (c0 >= nCand) break;
+    uint32_t     iOf[kFlight], jOf[kFlight];
+    bool         live[kFlight];
+    const uint4 *xi[kFlight], *yj[kFlight];
+#pragma unroll
+    for (int f = 0; f < kFlight; ++f) {
+      const bool have = c0 + f < nCand;
+      const int2 rj   = have ? cand[c0 + f] : make_int2(0, 0);
+      iOf[f]          = static_cast<uint32_t>(rj.x) * S + sub / C;
+      jOf[f]          = static_cast<uint32_t>(rj.y) * C + sub % C;
+      live[f]         = have && iOf[f] < nRows && jOf[f] < nCols && !(symmetric && iOf[f] >= jOf[f]);
+      xi[f]           = reinterpret_cast<const uint4*>(x + static_cast<size_t>(live[f] ? iOf[f] : 0) * words);
+      yj[f]           = reinterpret_cast<const uint4*>(y + static_cast<size_t>(live[f] ? jOf[f] : 0) * words);
+    }
+    int cnt[kFlight] = {};
+    for (int q = gl; q < chunks; q += 4 * G) {  // (4 chunks per lane and candidate in flight)
+      uint4 a[kFlight][4], b4[kFlight][4];
+#pragma unroll
+      for (int f = 0; f < kFlight; ++f)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q + u * G < chunks) a[f][u] = xi[f][q + u * G], b4[f][u] = yj[f][q + u * G];
+#pragma unroll
+      for (int f = 0; f < kFlight; ++f)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q + u * G < chunks)
+            cnt[f] += __popc(a[f][u].x & b4[f][u].x) + __popc(a[f][u].y & b4[f][u].y) + __popc(a[f][u].z & b4[f][u].z) +
+                      __popc(a[f][u].w & b4[f][u].w);
+    }
+#pragma unroll
+    for (int f = 0; f < kFlight; ++f) {
+      int v = cnt[f];
+      for (int o = G >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const bool hit = gl == 0 && live[f] && v >= thresh[popX[iOf[f]] + popY[jOf[f]]];
+      if (hit) {
+        atomicAdd(counts + iOf[f], sign);
+        if (countsY) atomicAdd(countsY + jOf[f], sign);
       }
-      for (int o = G >> 1; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (gl == 0 && live && cnt >= thresh[popX[i] + popY[j]]) {
-        atomicAdd(counts + i, sign);
-        if (countsY) atomicAdd(countsY + j, sign);
-        if (edges) hit[atomicAdd(&nHit, 1)] = make_int2(static_cast<int>(i), static_cast<int>(j));
+      if (edges) {
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        if (hits) {
+          const int total = __popc(hits);  // <= 16
+          if (nStaged + total > kStage) flush();
+          if (hit) stage[warp][nStaged + __popc(hits & ((1u << lane) - 1u))] = make_int2(static_cast<int>(iOf[f]), static_cast<int>(jOf[f]));
+          nStaged += total;
+        }
       }
     }
-    __syncthreads();
-    if (edges && nHit) {
-      if (threadIdx.x == 0) base = atomicAdd(edgeCursor, static_cast<unsigned long long>(nHit));
-      __syncthreads();
-      if (threadIdx.x < nHit && base + threadIdx.x < edgeCap) edges[base + threadIdx.x] = hit[threadIdx.x];
-    }
-    __syncthreads();
   }
+  if (edges) flush();
 }
 
 // lo[S] = min(thresh[S..len-1]): the threshold table need not be monotone (cutoff 0 admits only even |A|+|B|), its
@@ -427,7 +464,14 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   simTensorKernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smemRaw[];
-  constexpr int kEpiWarps = epiWarps(MODE), kThreadsTC = threadsTC(MODE), kParts = kEpiWarps / 4;
+  constexpr int kEpiWarps = epiWarps(MODE), kThreadsTC = threadsTC(MODE);
+  // Count mode: the two warps of a TMEM lane quarter ALTERNATE tiles (warps 2..5 take the even accumulator buffer, warps
+  // 6..9 the odd one) instead of splitting the column blocks of one tile. A tile's epilogue is a chain of latencies (column
+  // popcounts from L2, a barrier, seven TMEM reads one after the other) of ~7.7k clocks against ~4.7k of MMA issue; two
+  // tiles in flight hide it. The materialise modes keep all their warps on one tile (bound by the fp64 output stream).
+  constexpr bool ALT   = MODE == kTcCount;
+  constexpr int  kGrp  = ALT ? 4 : kEpiWarps;          // warps that share one tile
+  constexpr int  kParts = ALT ? 1 : kEpiWarps / 4;     // ... and how many of them share one TMEM lane quarter
   constexpr int TN      = FP4 ? kTNFp4 : kTN;  // tile columns; the accumulator stages sit TN TMEM columns apart
   constexpr int kBBytes = TN * kTK;
   static_assert(!FP4 || MODE == kTcCount, "the fp4 tile serves the count mode");
@@ -448,6 +492,11 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   __shared__ int      popA[2][kTM];
   __shared__ int      colAcc[2][kTN];
   __shared__ int      popBMin[2][kEpiWarps];
+  // candidates of a superposed pass wait here, per epilogue warp, and leave 64 at a time: one global atomic per flush
+  // instead of one per 32 x 32 block that holds a candidate (a ~1k-clock round trip most blocks paid: with 8 pairs per
+  // accumulator more than half of the blocks have a survivor; profiles/r02_path_a_summary.md)
+  constexpr int kCandStage = 64;
+  __shared__ int2 candStage[FP4 ? kEpiWarps : 1][FP4 ? kCandStage : 1];
   __shared__ __align__(16) float colAdj[2][FP4 ? kTN : 4];  // fp4 count tile: alpha * |B_j| (rounded down), +inf for columns past the end
 
   const uint32_t smemA    = (smemAddr(smemRaw) + 1023u) & ~1023u;  // (stationary tile: the row operand's K chunks)
@@ -471,7 +520,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       }
     for (int s = 0; s < 2; ++s) {
       mbarInit(&tmemFull[s], 1);
-      mbarInit(&tmemEmpty[s], P2 ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (pair MMA: of both CTAs, at the leader)
+      mbarInit(&tmemEmpty[s], P2 ? 2 * kGrp : kGrp);  // one arrival per warp working on the tile (pair MMA: of both CTAs, at the leader)
     }
     fenceBarrierInit();
   }
@@ -646,10 +695,26 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     // ===================== epilogue (warps 2..5) =====================
     const int      ew      = warp - 2;             // 0..kEpiWarps-1
     const int      quarter = warp & 3;             // TMEM lane quarter this warp may read
-    const int      part    = ew >> 2;              // which share of the column blocks this warp takes
-    const int      et      = ew * 32 + lane;       // thread index among the epilogue warps
+    const int      part    = ew >> 2;              // count: which accumulator buffer this warp serves; else its share of the column blocks
+    const int      gw      = ALT ? (ew & 3) : ew;  // warp index among the warps sharing the tile
+    const int      et      = gw * 32 + lane;       // thread index among them
+    const int      barId   = ALT ? 1 + part : 1;   // their named barrier
     uint32_t       local   = 0;
     uint32_t       tnOf[2] = {0, 0};  // tile column each accumulator-side buffer last served
+    int            nStaged = 0;       // entries of candStage[ew] (the same in every lane)
+    auto flushCandidates = [&]() {
+      if constexpr (FP4) {
+        if (nStaged == 0) return;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.candCursor, static_cast<unsigned long long>(nStaged));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int k = lane; k < nStaged; k += 32)
+          if (base + k < p.candCap) p.cand[base + k] = candStage[ew][k];
+        __syncwarp();
+        nStaged = 0;
+      }
+    };
 #ifdef B200_TC_TIMING
     long long       tcAcc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tcStart  = clock64();
@@ -659,12 +724,19 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       if (!w.coords(p, rank, tm, tnBeg, tnEnd)) continue;
       for (uint32_t tn = tnBeg; tn < tnEnd; ++tn) {
       const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
+      if (ALT && static_cast<int>(as) != part) {  // the other four warps' tile
+        ++local;
+        continue;
+      }
+      const uint32_t gr = tm * kTM + quarter * 32 + lane;
+      const int      pa = gr < p.n ? __ldg(p.popX + gr) : 0;  // (issued ahead of the staging loads: one latency, not two)
+      if (ALT && p.countsY && local >= 2)  // the four warps are done with this buffer's previous tile (its column counts)
+        asm volatile("bar.sync %0, %1;" ::"r"(barId), "n"(32 * kGrp) : "memory");
       // stage this tile's column popcounts
       int minPb = 0x3fffffff;  // smallest |B| among this tile's valid columns (pre-filter of the threshold test)
-      for (int c = et; c < TN; c += 32 * kEpiWarps) {
+      for (int c = et; c < TN; c += 32 * kGrp) {
         if (MODE == kTcCount && p.countsY && local >= 2) {
-          // column counts this buffer collected two tiles ago: every warp finished that tile before it passed the
-          // staging barrier of the tile in between, so no barrier of its own is needed for the flush
+          // column counts this buffer collected two tiles ago
           const int v = colAcc[as][c];
           if (v) atomicAdd(p.countsY + tnOf[as] * TN + c, p.sign * v);
         }
@@ -679,7 +751,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       if constexpr (MODE == kTcCount) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) minPb = min(minPb, __shfl_xor_sync(0xffffffffu, minPb, o));
-        if (lane == 0) popBMin[as][ew] = minPb;
+        if (lane == 0) popBMin[as][gw] = minPb;
       }
       if (MODE != kTcCount && et < kTM) {
         const uint32_t ga = tm * kTM + et;
@@ -687,16 +759,14 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       }
       {
         TC_T0();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(barId), "n"(32 * kGrp) : "memory");
         TC_T1(5);
       }
-      const uint32_t gr = tm * kTM + quarter * 32 + lane;
-      const int      pa = gr < p.n ? __ldg(p.popX + gr) : 0;
       int thMin = 0;
       if constexpr (MODE == kTcCount) {
         int mpb = popBMin[as][0];
 #pragma unroll
-        for (int k = 1; k < kEpiWarps; ++k) mpb = min(mpb, popBMin[as][k]);
+        for (int k = 1; k < kGrp; ++k) mpb = min(mpb, popBMin[as][k]);
         thMin = (gr < p.n && mpb < 0x3fffffff) ? static_cast<int>(threshLoS[pa + mpb]) : 0x3fffffff;  // no valid pair: all out
       }
       // fp4 count tile: a pair (or a superposed group of pairs) can only pass with c >= alpha (|A| + |B|) (the exact
@@ -705,6 +775,10 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       // per column, instead of one bound from the smallest |B| of the whole tile.
       const float fRowTh = gr < p.n ? __fmul_rd(p.alpha, static_cast<float>(pa)) - 0.5f : 3.0e38f;
       (void)fRowTh;
+      // every (row, column) of the tile is a pair with row fingerprints < column fingerprints: the tile's last row group
+      // ends before its first column group starts
+      const bool interior = !p.symmetric || (static_cast<uint64_t>(tm) * kTM + kTM) * p.superS <= static_cast<uint64_t>(tn) * TN * p.superC;
+      (void)interior;
       {
         TC_T0();
         mbarWait(&tmemFull[as], accPhase);
@@ -713,7 +787,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       tcFenceAfter();
       int rowHits = 0;
       constexpr int kCb = TN / 32, kCbPer = (kCb + kParts - 1) / kParts;  // column blocks of 32; the warps of a quarter split them
-      for (int cb = part * kCbPer; cb < min(kCb, (part + 1) * kCbPer); ++cb) {
+      for (int cb = ALT ? 0 : part * kCbPer; cb < (ALT ? kCb : min(kCb, (part + 1) * kCbPer)); ++cb) {
         uint32_t r[32];
         tmemLoad32(tmem + as * TN + cb * 32 + (static_cast<uint32_t>(quarter * 32) << 16), r);
         if constexpr (MODE != kTcCount) {
@@ -842,8 +916,16 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
             for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
           hot = m[0] >= fRowTh;
           if (hot) {
+            // 32 independent compare-selects and an OR tree: a chain of 32 dependent ORs is ~150 clocks of latency for
+            // the one or two warps a scheduler has here
+            uint32_t b[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) maybe |= (vv[j] >= fRowTh ? 1u : 0u) << j;
+            for (int j = 0; j < 32; ++j) b[j] = vv[j] >= fRowTh ? (1u << j) : 0u;
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1)
+#pragma unroll
+              for (int j = 0; j < w; ++j) b[j] |= b[j + w];
+            maybe = b[0];
           }
         } else {
           int m[16];
@@ -864,24 +946,49 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
           // superposed operands: the accumulator is the SUM of superS * superC pair counts, so "sum below the smallest
           // threshold any pair of the group can have" rejected all of them above; what is left goes to the exact
           // verification kernel as (super row, super column)
-          while (maybe) {
-            const int j = __ffs(maybe) - 1;
-            maybe &= maybe - 1;
-            const uint32_t gc = tn * TN + cb * 32 + j;
-            if (gr < p.n && gc < p.nY &&
-                (!p.symmetric || gr * static_cast<uint32_t>(p.superS) + 1u < (gc + 1u) * static_cast<uint32_t>(p.superC)))
-              mask |= 1u << j;
-          }
-          if (__ballot_sync(0xffffffffu, mask != 0)) {
-            const int mine = __popc(mask);
-            int       incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int v = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += v;
+          // (rows and columns past the end never get here: their thresholds / adjustments are +inf; only a tile the
+          // diagonal crosses has to look at each survivor)
+          if (FP4 && interior) mask = maybe;
+          else
+            while (maybe) {
+              const int j = __ffs(maybe) - 1;
+              maybe &= maybe - 1;
+              const uint32_t gc = tn * TN + cb * 32 + j;
+              if (gr < p.n && gc < p.nY &&
+                  (!p.symmetric || gr * static_cast<uint32_t>(p.superS) + 1u < (gc + 1u) * static_cast<uint32_t>(p.superC)))
+                mask |= 1u << j;
             }
-            const int          total = __shfl_sync(0xffffffffu, incl, 31);
-            unsigned long long base  = 0;
+          const unsigned holders = __ballot_sync(0xffffffffu, mask != 0);
+          if (holders) {
+            const int mine = __popc(mask);
+            int       incl, total;
+            if (__ballot_sync(0xffffffffu, mine > 1) == 0) {  // the usual case, one survivor per row: no scan needed
+              incl  = __popc(holders & (0xffffffffu >> (31 - lane)));
+              total = __popc(holders);
+            } else {
+              incl = mine;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+              }
+              total = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if constexpr (FP4) {
+              if (total <= kCandStage) {
+                if (nStaged + total > kCandStage) flushCandidates();
+                int at = nStaged + incl - mine;
+                while (mask) {
+                  const int j = __ffs(mask) - 1;
+                  mask &= mask - 1;
+                  candStage[ew][at++] = make_int2(static_cast<int>(gr), static_cast<int>(tn * TN + cb * 32 + j));
+                }
+                nStaged += total;
+                continue;
+              }
+            }
+            // (a block with more survivors than the staging holds: straight to the list)
+            unsigned long long base = 0;
             if (lane == 31) base = atomicAdd(p.candCursor, static_cast<unsigned long long>(total));
             base                  = __shfl_sync(0xffffffffu, base, 31);
             unsigned long long at = base + incl - mine;
@@ -959,15 +1066,13 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
       atomicAdd(&g_tcClk[5], static_cast<unsigned long long>(tcAcc[5]));
     }
 #endif
+    flushCandidates();
     if (MODE != kTcCount && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA stores
-    if (MODE == kTcCount && p.countsY) {  // the last two tiles' column counts
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      for (uint32_t back = 1; back <= 2 && back <= local; ++back) {
-        const uint32_t b = (local - back) & 1;
-        for (int c = et; c < TN; c += 32 * kEpiWarps) {
-          const int v = colAcc[b][c];
-          if (v) atomicAdd(p.countsY + tnOf[b] * TN + c, p.sign * v);
-        }
+    if (MODE == kTcCount && p.countsY && static_cast<int>(local) > part) {  // the column counts of this buffer's last tile
+      asm volatile("bar.sync %0, %1;" ::"r"(barId), "n"(32 * kGrp) : "memory");
+      for (int c = et; c < TN; c += 32 * kGrp) {
+        const int v = colAcc[part][c];
+        if (v) atomicAdd(p.countsY + tnOf[part] * TN + c, p.sign * v);
       }
     }
   }
@@ -1185,18 +1290,24 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
                : (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
                           : static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK)) +
                    (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8 + 1024 + kEpiWarpsMat * 4096) + 1024 + 64;
+  // each variant may use what its static shared memory leaves of the 227 KB a CTA can have
   static bool configured[kMaxDevices] = {};
+  auto optIn = [](auto kernel) {
+    cudaFuncAttributes a{};
+    B200_CUDA(cudaFuncGetAttributes(&a, kernel));
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - static_cast<int>(a.sharedSizeBytes)));
+  };
   if (!configured[currentDeviceSlot()]) {
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCount, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcTanimoto, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(simTensorKernel<kTcCosine, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 219 * 1024));
+    optIn(simTensorKernel<kTcCount, false, 0>);
+    optIn(simTensorKernel<kTcCount, true, 0>);
+    optIn(simTensorKernel<kTcCount, true, 1>);
+    optIn(simTensorKernel<kTcCount, true, 2>);
+    optIn(simTensorKernel<kTcCount, true, 3>);
+    optIn(simTensorKernel<kTcTanimoto, false, 0>);
+    optIn(simTensorKernel<kTcCosine, false, 0>);
     configured[currentDeviceSlot()] = true;
   }
-  B200_REQUIRE(smemBytes <= 219 * 1024, "tensor similarity tile does not fit shared memory");
+  B200_REQUIRE(smemBytes <= 215 * 1024, "tensor similarity tile does not fit shared memory");  // (+ <= 12 KB static)
   // units this call owns: tiles, or vertical tile pairs (same enumeration as the kernel's UnitWalk)
   const uint64_t total = stationary ? countUnits<kTNFp4, true, kRunStat>(p)
                          : cluster  ? countUnits<kTNFp4, true>(p)
@@ -1256,7 +1367,7 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     }
     if (nCand) {
       PhaseTimer         t("verify_candidates", s);
-      const unsigned int blocks2 = static_cast<unsigned int>(std::min<unsigned long long>((nCand + 7) / 8, static_cast<unsigned long long>(smCount()) * 16));
+      const unsigned int blocks2 = static_cast<unsigned int>(std::min<unsigned long long>((nCand + 63) / 64, static_cast<unsigned long long>(smCount()) * 16));
       verifyCandidatesKernel<<<blocks2, 256, 0, s>>>(q.x, q.y, q.words, cand.get(), nCand, superS, superC,
                                                      static_cast<uint32_t>(q.nX), static_cast<uint32_t>(q.nY), q.symmetric ? 1 : 0,
                                                      popX.get(), popYExact, thresh.get(), q.sign, q.rowCounts,

@@ -25,6 +25,8 @@ fp = torch.from_numpy(synthetic.clustered_fingerprints(n_centres, 50).view(np.in
 L = _lib.load()
 buf = (C.c_ulonglong * 8)()
 _lib.profile_enable(True)
+_lib.set_option("similarity_superpose_auto", 0)  # no pilot passes in the attribution
+_lib.set_option("similarity_superpose_cols", int(os.environ.get("SUPER_COLS", "2")))
 for v in variants:
     _lib.set_option("similarity_tensor_cluster", v)
     for _ in range(2):
