@@ -584,11 +584,13 @@ def run_conformer_legs(args, pool, dev, world, rank):
 
     ms_e2e, _ = _event_timed(e2e_step, dev, world)
     h2d = flat.nbytes() + mmff.nbytes()
-    roof = _conformer_roofline(stats, phases, peak, peak_src, traffic)
+    # (the ncu traffic capture is of THIS workload at its default size on one GPU: not quoted for anything else)
+    roof = _conformer_roofline(stats, phases, peak, peak_src, traffic if (n3 == 10000 and args.confs == 10 and world == 1) else {})
     out["etkdg_mmff"] = {
         "metric": "etkdg_mmff_mols_per_s", "value": n3 / (ms * 1e-3), "unit": "mols/s", "ms_per_step": ms, "n_gpus": world,
         "scaling": "strong",
-        "dtype": "f64 energies / gradients / line search; inverse Hessian f32 in the embedder, f64 in MMFF",
+        "dtype": "f64 energies / gradients / line search; inverse Hessian f32 in the embedder (option etkdg_hessian_fp64: f64, "
+                 "measured beside it under embedder_hessian_f32_vs_f64), f64 in MMFF",
         "config": {"workload": f"config 3: {n3} drug-like pseudo-mols ({min(n3, n_pool)} distinct, 20-50 heavy atoms + H, mean "
                                f"{float(flat.atom_counts.mean()):.1f} atoms) x {args.confs} conformers, ETKDG embed (max attempts = "
                                f"10 x atoms, the API default) + MMFF94 200-iteration BFGS", "data": "synthetic",
@@ -606,6 +608,21 @@ def run_conformer_legs(args, pool, dev, world, rank):
                      "conformer runs all 200",
     }
 
+    # ---- the same path with the embedder's inverse Hessian in fp64 (the reference's storage type) beside the fp32 default,
+    # on a bounded subset of config 3 (both timed on the same molecules)
+    if world == 1 and args.hessian_compare_mols > 0:
+        nh = min(n3, args.hessian_compare_mols)
+        idsh = ids3[:nh]
+        cmp_ = {"mols": int(nh), "confs": int(args.confs)}
+        for name, flag in (("f32", 0), ("f64", 1)):
+            _lib.set_option("etkdg_hessian_fp64", flag)
+            msh, (rawh, _resh) = _event_timed(lambda: leg.step(idsh, args.confs), dev, world)
+            cmp_[name] = {"mols_per_s": nh / (msh * 1e-3), "etkdg_ms": _lib.profile_read("etkdg"), "bfgs_ms": _lib.profile_read("bfgs"),
+                          "embedded_frac": float(rawh.ok.float().mean().item()),
+                          "mean_attempts": float(rawh.attempts.float().mean().item())}
+        _lib.set_option("etkdg_hessian_fp64", 0)
+        out["etkdg_mmff"]["embedder_hessian_f32_vs_f64"] = cmp_
+
     # ---- configs 4 and 5 (BASELINE: 8 GPUs)
     if world == 8 or args.all_configs:
         n4 = args.mmff_mols
@@ -616,7 +633,7 @@ def run_conformer_legs(args, pool, dev, world, rank):
         _lib.stats_read(reset=True)
         ms4, (_r4, res4) = _event_timed(lambda: leg.step(ids4, 1, embed=False, start_xyz=(atom_offs, xyz4)), dev, world)
         st4 = _lib.stats_read(reset=True)
-        roof4 = _conformer_roofline(st4, {"bfgs": _lib.profile_read("bfgs")}, peak, peak_src, traffic)
+        roof4 = _conformer_roofline(st4, {"bfgs": _lib.profile_read("bfgs")}, peak, peak_src, {})
         out["config4_mmff"] = {
             "metric": "mmff_mols_per_s", "value": n4 / (ms4 * 1e-3), "unit": "mols/s", "ms_per_step": ms4, "n_gpus": world,
             "config": {"workload": f"config 4: {n4} mols ({min(n4, n_pool)} distinct) MMFF94 200-iteration BFGS from pre-embedded "
@@ -627,7 +644,7 @@ def run_conformer_legs(args, pool, dev, world, rank):
         _lib.stats_read(reset=True)
         ms5, (raw5, res5) = _event_timed(lambda: leg.step(ids5, 1), dev, world)
         st5 = _lib.stats_read(reset=True)
-        roof5 = _conformer_roofline(st5, {"etkdg": _lib.profile_read("etkdg"), "bfgs": _lib.profile_read("bfgs")}, peak, peak_src, traffic)
+        roof5 = _conformer_roofline(st5, {"etkdg": _lib.profile_read("etkdg"), "bfgs": _lib.profile_read("bfgs")}, peak, peak_src, {})
         out["config5_etkdg_mmff"] = {
             "metric": "etkdg_mmff_mols_per_s", "value": n5 / (ms5 * 1e-3), "unit": "mols/s", "ms_per_step": ms5, "n_gpus": world,
             "config": {"workload": f"config 5: {n5} mols ({min(n5, n_pool)} distinct, config 3 generator cycled) x 1 conformer, ETKDG "
@@ -692,6 +709,8 @@ def main() -> None:
     ap.add_argument("--superpose", type=int, default=-1, help="pair-pass row superposition override (testing; -1 = library default)")
     ap.add_argument("--bfgs-l2-persist", action="store_true", help="mark the minimisers' inverse-Hessian slabs persisting in L2 (experiment)")
     ap.add_argument("--superpose-cols", type=int, default=-1, help="pair-pass column superposition override (testing; -1 = library default)")
+    ap.add_argument("--hessian-compare-mols", type=int, default=2000,
+                    help="config-3 subset on which the fp64 embedder Hessian is timed beside the fp32 default (0 = skip)")
     ap.add_argument("--all-configs", action="store_true", help="run configs 4 and 5 on fewer than 8 GPUs too")
     ap.add_argument("--mmff-mols", type=int, default=100000, help="config 4 size")
     ap.add_argument("--e2e-mols", type=int, default=1000000, help="config 5 size")

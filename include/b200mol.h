@@ -61,6 +61,10 @@ int b200mol_free_async(void* d_ptr, void* stream);
  *                                  0: always start from the configured factors
  *   "butina_min_round_commits"     a parallel Butina round that commits fewer clusters than this hands over to the
  *                                  one-cluster-per-step loop (default 32; 0 = rounds only, >= 1e9 = stepwise only)
+ *   "etkdg_hessian_fp64"           0 (default): the embedder keeps its BFGS inverse Hessian in fp32 (products accumulated
+ *                                  in fp64; half the slab traffic); 1: in fp64, the reference's storage type. The MMFF /
+ *                                  UFF minimiser always uses fp64
+ *   "bfgs_l2_persist"              1: mark the inverse-Hessian slabs persisting in L2 (measured slower on B200; default 0)
  *   "bfgs_ctas_per_sm"             resident CTAs per SM of the minimiser / embedder kernels (default 3 = the register
  *                                  budget they are compiled for) */
 int b200mol_set_option(const char* key, long long value);

@@ -26,6 +26,7 @@
 namespace b200 {
 extern int g_bfgsCtasPerSm;
 extern int g_bfgsL2Persist;
+int        g_etkdgHessianFp64 = 0;  // option "etkdg_hessian_fp64": the embedder's inverse Hessian in fp64 (default fp32)
 unsigned long long* pathBStats();
 namespace {
 
@@ -44,7 +45,8 @@ struct EmbedArgs {
   int32_t*                attempts;       // [nSlots]
   double*                 energy;         // [nSlots] DG energy (first-stage weights) of the accepted attempt
   unsigned long long*     stageFailures;  // [kNumStages] (may be NULL)
-  float*                  hessWs;  // fp32 inverse-Hessian slabs (fp64 accumulation): half the traffic, L2-resident
+  void*                   hessWs;  // inverse-Hessian slabs: fp32 by default (fp64 accumulation; half the traffic), fp64 with
+                                   // option "etkdg_hessian_fp64" (the reference's storage type)
   size_t                  hessStride;
   int*                    queue;
   int                     maxN;
@@ -274,11 +276,12 @@ __device__ unsigned finalChecks(const EmbedArgs& a, int mol, const double* pos, 
   return m;
 }
 
+template <class HT>
 __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double                     red[kRed];
   __shared__ double                     colBuf[kColBuf];
-  const BfgsWorkT<float> w = carveWork<float>(sm, a.maxN, a.hessWs + static_cast<size_t>(blockIdx.x) * a.hessStride, red, colBuf, a.stats);
+  const BfgsWorkT<HT> w = carveWork<HT>(sm, a.maxN, static_cast<HT*>(a.hessWs) + static_cast<size_t>(blockIdx.x) * a.hessStride, red, colBuf, a.stats);
   double*        ref = sm + kBfgsVectors * a.maxN;  // ETK reference geometry
   const int      tid = threadIdx.x;
   // Work item = one ATTEMPT of one slot. A CTA first works through the slot queue, retrying its own slot while it fails;
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
       // 1: first minimisation
       if (failedStage < 0) {
         const auto        v = ff::Dg<4>::view(a.dg, mol, {1.0, 0.1});
-        const BfgsOutcome o = bfgsMinimize<ff::Dg<4>, float>(v, w, n, a.par.dgIters, a.par.optimizerForceTol, true, a.par.maxRestarts);
+        const BfgsOutcome o = bfgsMinimize<ff::Dg<4>, HT>(v, w, n, a.par.dgIters, a.par.optimizerForceTol, true, a.par.maxRestarts);
         eAccepted           = o.energy;
         if (o.energy / nA >= 0.05) failedStage = 1;
       }
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
       // 4: fourth-dimension collapse
       if (failedStage < 0) {
         const auto v = ff::Dg<4>::view(a.dg, mol, {0.2, 1.0});
-        bfgsMinimize<ff::Dg<4>, float>(v, w, n, a.par.fourthIters, a.par.optimizerForceTol, true, 0);
+        bfgsMinimize<ff::Dg<4>, HT>(v, w, n, a.par.fourthIters, a.par.optimizerForceTol, true, 0);
       }
       // 5: ETK refinement + planarity
       if (failedStage < 0 && (a.par.useExpTorsions || a.par.useBasicKnowledge)) {
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) etkdgKernel(const EmbedArgs a) {
         __syncthreads();
         auto v   = ff::Etk::view(a.etk, mol, {a.par.useBasicKnowledge ? 0 : 1, 1});
         v.refPos = ref;
-        bfgsMinimize<ff::Etk, float>(v, w, n, a.par.etkIters, a.par.optimizerForceTol, true, 0);
+        bfgsMinimize<ff::Etk, HT>(v, w, n, a.par.etkIters, a.par.optimizerForceTol, true, 0);
         if (a.par.useBasicKnowledge && planarityFails(a.etk, a.chk.numImpropers, mol, w.pos, red)) failedStage = 5;
       }
       // 6-10: final checks
@@ -478,19 +481,23 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
     const int    maxN = 4 * max_atoms;
     const size_t smem = static_cast<size_t>(kBfgsVectors + 1) * maxN * sizeof(double);
     B200_REQUIRE(max_atoms > 0 && smem <= 200 * 1024, "molecule too large for the shared-memory embedder (%d atoms)", max_atoms);
+    const bool wide = g_etkdgHessianFp64 != 0;
     static bool configured[kMaxDevices] = {};
     if (!configured[currentDeviceSlot()]) {
-      B200_CUDA(cudaFuncSetAttribute(etkdgKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(etkdgKernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(etkdgKernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured[currentDeviceSlot()] = true;
     }
     int perSm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, etkdgKernel, kT, smem));
+    if (wide) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, etkdgKernel<double>, kT, smem));
+    else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, etkdgKernel<float>, kT, smem));
     B200_REQUIRE(perSm >= 1, "embedding kernel does not fit");
     perSm      = perSm > g_bfgsCtasPerSm ? g_bfgsCtasPerSm : perSm;
     int blocks = smCount() * perSm;
     if (blocks > nSlots) blocks = nSlots;
-    const size_t    stride = static_cast<size_t>(maxN) * bfgsLd<float>(maxN);
-    Scratch<float>  hess(stride * blocks, s);
+    const size_t    stride  = static_cast<size_t>(maxN) * (wide ? bfgsLd<double>(maxN) : bfgsLd<float>(maxN));  // elements
+    const size_t    hessBytes = stride * blocks * (wide ? sizeof(double) : sizeof(float));
+    Scratch<uint8_t> hess(hessBytes, s);
     Scratch<int>    queue(1, s);
     B200_CUDA(cudaMemsetAsync(queue.get(), 0, sizeof(int), s));
     if (d_stage_failures) B200_CUDA(cudaMemsetAsync(d_stage_failures, 0, kNumStages * sizeof(uint64_t), s));
@@ -501,9 +508,10 @@ extern "C" int b200mol_etkdg_embed(const b200mol_dg_system* dg, const b200mol_et
                 reinterpret_cast<unsigned long long*>(d_stage_failures), hess.get(), stride, queue.get(), maxN,
                 state.get(), state.get() + nSlots, state.get() + 2 * static_cast<size_t>(nSlots), state.get() + 3 * static_cast<size_t>(nSlots),
                 pathBStats()};
-    L2Persist  keep(s, hess.get(), stride * blocks * sizeof(float), g_bfgsL2Persist != 0);
+    L2Persist  keep(s, hess.get(), hessBytes, g_bfgsL2Persist != 0);
     PhaseTimer t("etkdg", s);
-    etkdgKernel<<<blocks, kT, smem, s>>>(a);
+    if (wide) etkdgKernel<double><<<blocks, kT, smem, s>>>(a);
+    else etkdgKernel<float><<<blocks, kT, smem, s>>>(a);
     B200_LAUNCHED();
   });
 }

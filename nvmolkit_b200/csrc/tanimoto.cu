@@ -297,6 +297,7 @@ void launchTile(const CUtensorMap& tmX, const CUtensorMap& tmY, const TileParams
 bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s);
 extern int g_bfgsCtasPerSm;
 extern int g_bfgsL2Persist;
+extern int g_etkdgHessianFp64;
 extern int g_butinaMinCommits;
 extern int g_tensorFp4;
 extern int g_tensorCluster;
@@ -419,6 +420,7 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       g_bfgsCtasPerSm = static_cast<int>(value);
     }
     else if (k == "bfgs_l2_persist") g_bfgsL2Persist = value != 0;
+    else if (k == "etkdg_hessian_fp64") g_etkdgHessianFp64 = value != 0;
     else if (k == "similarity_superpose") {
       B200_REQUIRE(value == 1 || value == 2 || value == 4, "similarity_superpose must be 1, 2 or 4");
       g_superpose = static_cast<int>(value);
@@ -448,6 +450,7 @@ extern "C" int b200mol_get_option(const char* key, long long* value) {
     if (k == "similarity_tensor_min_pairs") *value = g_tensorMinPairs;
     else if (k == "bfgs_ctas_per_sm") *value = g_bfgsCtasPerSm;
     else if (k == "bfgs_l2_persist") *value = g_bfgsL2Persist;
+    else if (k == "etkdg_hessian_fp64") *value = g_etkdgHessianFp64;
     else if (k == "similarity_tensor_fp4") *value = g_tensorFp4;
     else if (k == "similarity_tensor_cluster") *value = g_tensorCluster;
     else if (k == "similarity_superpose") *value = g_superpose;

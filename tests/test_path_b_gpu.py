@@ -294,7 +294,17 @@ def test_etkdg_acceptance_checks_equal_cpu(cuda):
     assert len(set(want.tolist())) > 2
 
 
-def test_etkdg_embed_produces_conformers_the_cpu_accepts(cuda):
+@pytest.fixture(params=[0, 1], ids=["hessian_f32", "hessian_f64"])
+def embedder_hessian(request):
+    """The embedder's BFGS inverse Hessian in fp32 (default) and in fp64 (option etkdg_hessian_fp64, the reference's type)."""
+    from nvmolkit_b200 import _lib
+
+    _lib.set_option("etkdg_hessian_fp64", request.param)
+    yield request.param
+    _lib.set_option("etkdg_hessian_fp64", 0)
+
+
+def test_etkdg_embed_produces_conformers_the_cpu_accepts(cuda, embedder_hessian):
     from nvmolkit_b200.embedMolecules import EmbedMolecules, EmbedParameters, embed_slots
     from nvmolkit_b200.types import CoordinateOutput
 
