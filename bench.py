@@ -187,6 +187,8 @@ def run_b200(args) -> None:
         _lib.set_option("bfgs_l2_persist", 1)
     if args.superpose_cols >= 0:
         _lib.set_option("similarity_superpose_cols", args.superpose_cols)
+    if args.superpose_auto >= 0:
+        _lib.set_option("similarity_superpose_auto", args.superpose_auto)
     if args.workload == "conformers":
         legs = run_conformer_legs(args, pool, dev, world, rank)
         if rank == 0:
@@ -708,6 +710,7 @@ def main() -> None:
     ap.add_argument("--tensor-cluster", type=int, default=-1, help="pair-pass tile variant override (testing; -1 = library default)")
     ap.add_argument("--superpose", type=int, default=-1, help="pair-pass row superposition override (testing; -1 = library default)")
     ap.add_argument("--bfgs-l2-persist", action="store_true", help="mark the minimisers' inverse-Hessian slabs persisting in L2 (experiment)")
+    ap.add_argument("--superpose-auto", type=int, default=-1, help="0: no pilot passes, run the configured factors (profiling; -1 = library default)")
     ap.add_argument("--superpose-cols", type=int, default=-1, help="pair-pass column superposition override (testing; -1 = library default)")
     ap.add_argument("--hessian-compare-mols", type=int, default=2000,
                     help="config-3 subset on which the fp64 embedder Hessian is timed beside the fp32 default (0 = skip)")
