@@ -201,22 +201,28 @@ __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __
     __syncwarp();
     nStaged = 0;
   };
-  for (unsigned long long chunk = static_cast<unsigned long long>(blockIdx.x) * kChunk; chunk < nCand; chunk += static_cast<unsigned long long>(gridDim.x) * kChunk)
+  __shared__ int2 chunkCand[kChunk];
+  for (unsigned long long chunk = static_cast<unsigned long long>(blockIdx.x) * kChunk; chunk < nCand; chunk += static_cast<unsigned long long>(gridDim.x) * kChunk) {
+  // the block's 64 candidates in one coalesced load (a warp fetching its own entry would start every candidate with a
+  // dependent L2 round trip)
+  __syncthreads();
+  if (threadIdx.x < kChunk) chunkCand[threadIdx.x] = chunk + threadIdx.x < nCand ? cand[chunk + threadIdx.x] : make_int2(-1, -1);
+  __syncthreads();
   for (int it = 0; it < kChunk / (8 * kFlight); ++it) {
-    const unsigned long long c0 = chunk + static_cast<unsigned long long>(it) * 8 * kFlight + warp * kFlight;
-    if (c0 >= nCand) break;
     uint32_t     iOf[kFlight], jOf[kFlight];
     bool         live[kFlight];
+    int          popSum[kFlight];
     const uint4 *xi[kFlight], *yj[kFlight];
 #pragma unroll
     for (int f = 0; f < kFlight; ++f) {
-      const bool have = c0 + f < nCand;
-      const int2 rj   = have ? cand[c0 + f] : make_int2(0, 0);
+      const int2 rj   = chunkCand[it * 8 * kFlight + warp * kFlight + f];
+      const bool have = rj.x >= 0;
       iOf[f]          = static_cast<uint32_t>(rj.x) * S + sub / C;
       jOf[f]          = static_cast<uint32_t>(rj.y) * C + sub % C;
       live[f]         = have && iOf[f] < nRows && jOf[f] < nCols && !(symmetric && iOf[f] >= jOf[f]);
       xi[f]           = reinterpret_cast<const uint4*>(x + static_cast<size_t>(live[f] ? iOf[f] : 0) * words);
       yj[f]           = reinterpret_cast<const uint4*>(y + static_cast<size_t>(live[f] ? jOf[f] : 0) * words);
+      popSum[f]       = (gl == 0 && live[f]) ? popX[iOf[f]] + popY[jOf[f]] : 0;  // (in flight together with the rows)
     }
     int cnt[kFlight] = {};
     for (int q = gl; q < chunks; q += 4 * G) {  // (4 chunks per lane and candidate in flight)
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __
     for (int f = 0; f < kFlight; ++f) {
       int v = cnt[f];
       for (int o = G >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      const bool hit = gl == 0 && live[f] && v >= thresh[popX[iOf[f]] + popY[jOf[f]]];
+      const bool hit = gl == 0 && live[f] && v >= thresh[popSum[f]];
       if (hit) {
         atomicAdd(counts + iOf[f], sign);
         if (countsY) atomicAdd(countsY + jOf[f], sign);
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __
         }
       }
     }
+  }
   }
   if (edges) flush();
 }
