@@ -27,7 +27,11 @@ namespace {
 constexpr int kTM       = 128;
 constexpr int kTN       = 256;
 constexpr int kTK       = 128;  // bytes (= bits of the fingerprint) per K chunk
-constexpr int kStagesCount = 4;  // smem ring depth of the count mode
+constexpr int kStagesCount = 4;  // smem ring depth of the count mode (int8 tile)
+#ifndef B200_STAGES_FP4
+#define B200_STAGES_FP4 4
+#endif
+constexpr int kStagesCountFp4 = B200_STAGES_FP4;  // ... of the fp4 count tile
 constexpr int kStagesMat   = 2;  // (the materialise modes are bound by the fp64 output; their shared memory also holds the
                                  //  reciprocal table and 16 x 4 KB of staging for the TMA stores of the epilogue)
 constexpr int kStagesPair  = 6;  // pair-MMA count mode: 30 KB per stage and CTA  // materialise modes: one stage less, the space holds the reciprocal table
@@ -36,7 +40,10 @@ constexpr int kEpiWarpsMat   = 16;  // materialise modes: four per quarter (the 
 constexpr int epiWarps(int mode) { return mode == 0 ? kEpiWarpsCount : kEpiWarpsMat; }
 constexpr int threadsTC(int mode) { return 64 + 32 * epiWarps(mode); }  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kABytes   = kTM * kTK;
-constexpr int kTNFp4    = 224;  // fp4 count mode: 2 x 224 accumulator columns leave TMEM columns 448..511 for the scale factors
+#ifndef B200_TN_FP4
+#define B200_TN_FP4 224
+#endif
+constexpr int kTNFp4    = B200_TN_FP4;  // fp4 count mode: 2 x 224 accumulator columns leave TMEM columns 448..511 for the scale factors
 constexpr int kGroupRows = 8192;  // fingerprints per row group: the unit of L2 reuse of the column operand AND of the
                                   // multi-GPU row split (independent of the tile variant and of the superposition factor)
 constexpr int kRunStat   = 16;  // tile columns per unit of the A-stationary tile (the row operand is loaded once per unit)
@@ -83,6 +90,18 @@ enum TcMode : int { kTcCount = 0, kTcTanimoto = 1, kTcCosine = 2 };
 int g_tensorCluster = 1;  // fp4 count tile in clusters of two CTAs with a multicast column operand (option "similarity_tensor_cluster")
 int g_tensorFp4 = 1;  // count mode on block-scaled fp4 operands (option "similarity_tensor_fp4"; 0 = int8 tile)
 namespace {
+// -DB200_TC_MMAONLY (with B200_TC_TIMING; tools/pair_pass_timing.py): nothing is loaded, nothing waits, no epilogue - the
+// MMA thread issues the same instruction stream on whatever shared memory holds. Results are garbage; the time per tile
+// is the tensor pipe's own rate for this instruction mix (the floor the real kernel is compared with).
+// -DB200_TC_MMAONLY=2: the same with the TMA producer and the operand waits back in (still no epilogue): what the operand
+// stream alone costs the tensor pipe.
+#ifdef B200_TC_MMAONLY
+constexpr bool kMmaOnly = true;
+constexpr bool kMmaFed  = (B200_TC_MMAONLY + 0) == 2;
+#else
+constexpr bool kMmaOnly = false;
+constexpr bool kMmaFed  = false;
+#endif
 #ifdef B200_TC_TIMING
 // clock64() attribution of the count tile: [0] MMA thread total, [1] its wait for operands (fullBar / aFull), [2] its wait for a
 // free accumulator (tmemEmpty), [3] epilogue warp 0 total, [4] its wait for a finished accumulator (tmemFull), [5] its
@@ -490,7 +509,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   using Walk                 = UnitWalk<TN, CL != 0, ST ? kRunStat : 1>;
   constexpr int  kBStage     = P2 ? kBBytes / 2 : kBBytes;  // bytes of the column operand one CTA stages per K chunk
   constexpr int  kStageBytes = ST ? kBStage : kABytes + kBStage;
-  constexpr int  kStagesTC   = ST ? kStagesStat : (P2 ? kStagesPair : (MODE == kTcCount ? kStagesCount : kStagesMat));
+  constexpr int  kStagesTC   = ST ? kStagesStat : (P2 ? kStagesPair : (MODE == kTcCount ? (FP4 ? kStagesCountFp4 : kStagesCount) : kStagesMat));
   constexpr int  kAResident  = ST ? kMaxChunksStat * kABytes : 0;  // the stationary row tile, ahead of the ring
   __shared__ uint64_t fullBar[kStagesTC], emptyBar[kStagesTC], tmemFull[2], tmemEmpty[2];
   __shared__ uint64_t aFull[ST ? kMaxChunksStat : 1], aEmpty[ST ? kMaxChunksStat : 1];
@@ -502,7 +521,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   // candidates of a superposed pass wait here, per epilogue warp, and leave 64 at a time: one global atomic per flush
   // instead of one per 32 x 32 block that holds a candidate (a ~1k-clock round trip most blocks paid: with 8 pairs per
   // accumulator more than half of the blocks have a survivor; profiles/r02_path_a_summary.md)
-  constexpr int kCandStage = 64;
+  constexpr int kCandStage = kStagesCountFp4 > 4 ? 32 : 64;
   __shared__ int2 candStage[FP4 ? kEpiWarps : 1][FP4 ? kCandStage : 1];
   __shared__ __align__(16) float colAdj[2][FP4 ? kTN : 4];  // fp4 count tile: alpha * |B_j| (rounded down), +inf for columns past the end
 
@@ -525,6 +544,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         mbarInit(&aFull[s], 1);
         mbarInit(&aEmpty[s], 1);
       }
+    else if (kMmaOnly) mbarInit(&aFull[0], 1);
     for (int s = 0; s < 2; ++s) {
       mbarInit(&tmemFull[s], 1);
       mbarInit(&tmemEmpty[s], P2 ? 2 * kGrp : kGrp);  // one arrival per warp working on the tile (pair MMA: of both CTAs, at the leader)
@@ -572,7 +592,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && (!kMmaOnly || kMmaFed)) {
 #ifdef B200_TC_TIMING
       long long tcAcc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -650,7 +670,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         const uint32_t as = local & 1, accPhase = (local >> 1) & 1;
         {
           TC_T0();
-          mbarWait(&tmemEmpty[as], accPhase ^ 1);
+          if (!kMmaOnly) mbarWait(&tmemEmpty[as], accPhase ^ 1);
           TC_T1(2);
         }
         tcFenceAfter();
@@ -661,7 +681,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
             if constexpr (ST) {
               if (tn == tnBeg) mbarWait(&aFull[kc], aPhase);
             }
-            mbarWait(&fullBar[stage], phase);
+            if (!kMmaOnly || kMmaFed) mbarWait(&fullBar[stage], phase);
             TC_T1(1);
           }
           tcFenceAfter();
@@ -690,6 +710,10 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         ++local;
         }
         aPhase ^= 1;
+      }
+      if (kMmaOnly && !ST) {  // everything issued has retired before the clock is read
+        ummaCommit(&aFull[0]);
+        mbarWait(&aFull[0], 0);
       }
 #ifdef B200_TC_TIMING
       atomicAdd(&g_tcClk[0], static_cast<unsigned long long>(clock64() - tcStart));
@@ -726,7 +750,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     long long       tcAcc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tcStart  = clock64();
 #endif
-    for (Walk w(p, firstUnit, unitStep); !w.done; w.next(p)) {
+    for (Walk w(p, firstUnit, unitStep); !w.done && !kMmaOnly; w.next(p)) {
       uint32_t tm, tnBeg, tnEnd;
       if (!w.coords(p, rank, tm, tnBeg, tnEnd)) continue;
       for (uint32_t tn = tnBeg; tn < tnEnd; ++tn) {
@@ -1295,7 +1319,7 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   const size_t smemBytes =
     stationary ? static_cast<size_t>(kMaxChunksStat) * kABytes + static_cast<size_t>(kStagesStat) * tn * kTK + 1024 + 64
                : (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
-                          : static_cast<size_t>(count ? kStagesCount : kStagesMat) * (kABytes + tn * kTK)) +
+                          : static_cast<size_t>(count ? (fp4 ? kStagesCountFp4 : kStagesCount) : kStagesMat) * (kABytes + tn * kTK)) +
                    (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8 + 1024 + kEpiWarpsMat * 4096) + 1024 + 64;
   // each variant may use what its static shared memory leaves of the 227 KB a CTA can have
   static bool configured[kMaxDevices] = {};
@@ -1314,7 +1338,8 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     optIn(simTensorKernel<kTcCosine, false, 0>);
     configured[currentDeviceSlot()] = true;
   }
-  B200_REQUIRE(smemBytes <= 215 * 1024, "tensor similarity tile does not fit shared memory");  // (+ <= 12 KB static)
+  constexpr size_t kStaticMax = kStagesCountFp4 > 4 ? 9472 : 12288;  // static shared memory of the largest variant
+  B200_REQUIRE(smemBytes + kStaticMax <= 227 * 1024, "tensor similarity tile does not fit shared memory");
   // units this call owns: tiles, or vertical tile pairs (same enumeration as the kernel's UnitWalk)
   const uint64_t total = stationary ? countUnits<kTNFp4, true, kRunStat>(p)
                          : cluster  ? countUnits<kTNFp4, true>(p)

@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nvmolkit_b200 import _lib  # noqa: E402
 
-_lib.LIB_PATH = os.path.join(ROOT, "nvmolkit_b200", "lib", "libb200mol_tctiming.so")
+# B200_TC_LIB=mmaonly: the library built by `make mmaonly` (MMA instruction stream alone; results are garbage)
+_lib.LIB_PATH = os.path.join(ROOT, "nvmolkit_b200", "lib", f"libb200mol_{os.environ.get('B200_TC_LIB', 'tctiming')}.so")
 import torch  # noqa: E402
 
 from nvmolkit_b200 import synthetic  # noqa: E402
