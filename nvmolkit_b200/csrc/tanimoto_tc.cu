@@ -32,8 +32,16 @@ constexpr int kStagesCount = 4;  // smem ring depth of the count mode (int8 tile
 #define B200_STAGES_FP4 4
 #endif
 constexpr int kStagesCountFp4 = B200_STAGES_FP4;  // ... of the fp4 count tile
-constexpr int kStagesMat   = 2;  // (the materialise modes are bound by the fp64 output; their shared memory also holds the
-                                 //  reciprocal table and 16 x 4 KB of staging for the TMA stores of the epilogue)
+// RN(1/u) of the materialise epilogue: from the table (one 8-byte gather per element through L1) or computed
+// (__drcp_rn). Same value either way; measured at 32k x 32k: table 2.75 ms, computed 3.10 ms.
+#ifndef B200_RECIP_TABLE
+#define B200_RECIP_TABLE 1
+#endif
+constexpr bool kRecipTable = B200_RECIP_TABLE != 0;
+constexpr int kStagesMat   = 3;  // the materialise modes are bound by the fp64 output (11.4k clocks of HBM write per tile and SM),
+                                 // but with TWO stages the 16 operand chunks of a tile took 16 L2 round trips / 2 = 16k clocks:
+                                 // three stages bring the operand stream under the write time. Shared memory also holds 16 x 4 KB
+                                 // of staging for the TMA stores; the reciprocal table moved to global memory (L1) to make room
 constexpr int kStagesPair  = 6;  // pair-MMA count mode: 30 KB per stage and CTA  // materialise modes: one stage less, the space holds the reciprocal table
 constexpr int kEpiWarpsCount = 8;   // count mode: two warps per TMEM lane quarter share the column blocks
 constexpr int kEpiWarpsMat   = 16;  // materialise modes: four per quarter (the fp64 epilogue is the long pole there)
@@ -69,6 +77,7 @@ struct TcParams {
   unsigned long long  edgeCap;
   double*         out;  // materialise modes: [n][nY] fp64
   int             recipLen;  // 2 * bits (materialise Tanimoto)
+  const double*   recipG;    // RN(1/u), u = 0 .. recipLen (global memory, 32 KB: L1-resident)
   // Row superposition (count mode): a row of the X operand is the SUM of superS consecutive fingerprints (values 0..4,
   // exact in E2M1), so one accumulator bounds superS pair counts at once; n / tilesM then count SUPER rows, popX holds
   // the smallest popcount of each super row, and the epilogue only lists candidates (super row, column) for the exact
@@ -281,6 +290,11 @@ __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __
   }
   }
   if (edges) flush();
+}
+
+__global__ void recipTableKernel(double* __restrict__ r, int len) {  // r[u] = RN(1 / u), r[0] = 0
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u <= len) r[u] = u ? __drcp_rn(static_cast<double>(u)) : 0.0;
 }
 
 // lo[S] = min(thresh[S..len-1]): the threshold table need not be monotone (cutoff 0 admits only even |A|+|B|), its
@@ -566,13 +580,10 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   // per surviving pair)
   const uint16_t* threshT   = ST ? p.thresh : threshS;
   const uint16_t* threshLoS = threshT + p.threshLen;
-  double* recipS = reinterpret_cast<double*>(threshS);  // materialise Tanimoto: RN(1/u), u = |A u B| <= 2 * bits
+  const double* __restrict__ recipS = p.recipG;  // materialise Tanimoto: RN(1/u), u = |A u B| <= 2 * bits
   // materialise modes: one [32 rows][128 B] box per epilogue warp, written with the 128-byte swizzle the output tensor map
   // expects and handed to cp.async.bulk.tensor (store)
-  const uint32_t stagingAddr = (smemAddr(threshS) + static_cast<uint32_t>(p.recipLen + 1) * 8u + 1023u) & ~1023u;
-  if constexpr (MODE == kTcTanimoto) {
-    for (int u = threadIdx.x; u <= p.recipLen; u += kThreadsTC) recipS[u] = u ? __drcp_rn(static_cast<double>(u)) : 0.0;
-  }
+  const uint32_t stagingAddr = (smemAddr(threshS) + 1023u) & ~1023u;
   tcFenceBefore();
   __syncthreads();
   tcFenceAfter();
@@ -832,11 +843,11 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
             const int      pak = popA[as][quarter * 32 + lane];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous box has been read
-              __syncwarp();
+              // the 16 values of this lane's row first, in registers: they do not need the staging box, so the TMA
+              // engine reads the previous box while they are computed (the wait used to come first and serialised the two)
+              double v2[8][2];
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                double v2[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int j   = 16 * h + 2 * c + e;
@@ -848,16 +859,21 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
                       const int    u  = pak + pb - cnt;
                       const double dc = __hiloint2double(0x43300000, cnt) - 4503599627370496.0;
                       const double du = __hiloint2double(0x43300000, u) - 4503599627370496.0;
-                      const double rc = recipS[u], q0 = __dmul_rn(dc, rc);
+                      const double rc = kRecipTable ? __ldg(recipS + u) : __drcp_rn(du), q0 = __dmul_rn(dc, rc);
                       v               = __fma_rn(__fma_rn(-q0, du, dc), rc, q0);
                     } else {
                       v = __ddiv_rn(static_cast<double>(cnt), __dsqrt_rn(__dmul_rn(static_cast<double>(pak), static_cast<double>(pb))));
                     }
                   }
-                  v2[e] = v;
+                  v2[c][e] = v;
                 }
+              }
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous box has been read
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
                 const uint32_t at = stg + static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
-                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(at), "d"(v2[0]), "d"(v2[1]) : "memory");
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(at), "d"(v2[c][0]), "d"(v2[c][1]) : "memory");
               }
               fenceProxyAsync();
               __syncwarp();
@@ -906,7 +922,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
                   const int    u  = pak + pb - c;
                   const double dc = __hiloint2double(0x43300000, c) - 4503599627370496.0;
                   const double du = __hiloint2double(0x43300000, u) - 4503599627370496.0;
-                  const double rc = recipS[u], q0 = __dmul_rn(dc, rc);
+                  const double rc = kRecipTable ? __ldg(recipS + u) : __drcp_rn(du), q0 = __dmul_rn(dc, rc);
                   v               = __fma_rn(__fma_rn(-q0, du, dc), rc, q0);
                 } else {
                   v = __ddiv_rn(static_cast<double>(c), __dsqrt_rn(__dmul_rn(static_cast<double>(pak), static_cast<double>(pb))));
@@ -1236,6 +1252,12 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   p.edgeCap   = q.edgeCap;
   p.out       = q.out;
   p.recipLen  = 2 * bits;
+  Scratch<double> recip(mode == kMaterialiseTanimoto ? static_cast<size_t>(p.recipLen) + 1 : 0, s);
+  if (mode == kMaterialiseTanimoto) {
+    recipTableKernel<<<(p.recipLen + 256) / 256, 256, 0, s>>>(recip.get(), p.recipLen);
+    B200_LAUNCHED();
+    p.recipG = recip.get();
+  }
   {
     // a pair passes iff 1 - c / (|A| + |B| - c) <= cutoff, i.e. c >= alpha (|A| + |B|); the pre-filter's alpha is rounded
     // DOWN (and its products too), so it never rejects what the exact fp64 table accepts
@@ -1320,7 +1342,7 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     stationary ? static_cast<size_t>(kMaxChunksStat) * kABytes + static_cast<size_t>(kStagesStat) * tn * kTK + 1024 + 64
                : (pairMma ? static_cast<size_t>(kStagesPair) * (kABytes + tn / 2 * kTK)
                           : static_cast<size_t>(count ? (fp4 ? kStagesCountFp4 : kStagesCount) : kStagesMat) * (kABytes + tn * kTK)) +
-                   (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(maxS + 1) * 8 + 1024 + kEpiWarpsMat * 4096) + 1024 + 64;
+                   (count ? static_cast<size_t>(maxS + 1) * 4 : static_cast<size_t>(1024 + kEpiWarpsMat * 4096)) + 1024 + 64;
   // each variant may use what its static shared memory leaves of the 227 KB a CTA can have
   static bool configured[kMaxDevices] = {};
   auto optIn = [](auto kernel) {

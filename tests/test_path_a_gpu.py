@@ -330,6 +330,19 @@ def test_tensor_fused_butina_equals_rdkit_definition(cuda, force_tensor_path, ce
     assert (ids.cpu().numpy() == ids_cpu).all() and (cen.cpu().numpy() == cen_cpu).all()
 
 
+@pytest.mark.parametrize("n", [2, 3, 5, 127, 129, 897, 1023])
+def test_tensor_fused_butina_on_ragged_sizes(cuda, force_tensor_path, n):
+    """Sizes that are no multiple of the superposition factors, the tile rows (128) or the tile columns (224 / 448): the
+    last super row / super column sums fewer fingerprints, the last tile is clipped."""
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    fp = S.clustered_fingerprints(26, 40, seed=n)[:n].copy()
+    for cutoff in (0.3, 0.62):
+        ids, cen = fused_butina_device(_dev(fp, cuda), cutoff)
+        ids_cpu, cen_cpu = oracle.butina_fp(fp, cutoff)
+        assert (ids.cpu().numpy() == ids_cpu).all() and (cen.cpu().numpy() == cen_cpu).all(), (n, cutoff)
+
+
 def test_tensor_neighbor_counts_on_a_many_tile_problem(cuda, force_tensor_path):
     """9,000 points = 71 tile rows x 41 tile columns: several row groups and, for the row-stationary tile, several runs of
     16 tile columns per row with a row-operand reload between them."""
