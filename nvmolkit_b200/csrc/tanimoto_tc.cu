@@ -201,8 +201,13 @@ __global__ void superMinPopKernel(const int32_t* __restrict__ pop, size_t n, int
 // Exact verification of the candidates of a superposed pass: one warp per (super row R, super column J), for each of
 // the S * C pairs (i = S R + s, j = C J + c) of the group the exact count |X_i & Y_j| and the exact integer threshold
 // test; counts for both endpoints and the (i < j) edge list exactly as the unsuperposed epilogue produces them.
-// Warps are independent (no block barrier): each keeps two candidates in flight (all of their 128-bit loads are issued
-// before the first popcount) and parks its edges in 64 shared-memory slots that leave with ONE global atomic per flush.
+// (Measured and rejected: reading a 512-bit prefix of both rows first and dropping pairs whose exact upper bound
+// cq + min(|X| - xa, |Y| - yb) is below the threshold - 7 of 8 pairs leave after a quarter of the bytes, but the second,
+// dependent round of loads costs more than the traffic saved: 9.7 ms against 8.2.)
+// A block takes 64 consecutive candidates at a time (one coalesced load; the warp that listed them worked on one quarter
+// of a tile row, so their row operands are L1 / L2 hits), a warp one candidate: all of its 128-bit row loads and the two
+// popcount loads are in flight together; edges are parked in 64 shared-memory slots per warp that leave with ONE global
+// atomic per flush.
 __global__ void __launch_bounds__(256) verifyCandidatesKernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ y, int words,
                                                              const int2* __restrict__ cand, unsigned long long nCand, int S, int C,
                                                              uint32_t nRows, uint32_t nCols, int symmetric,
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   constexpr int  kParts = ALT ? 1 : kEpiWarps / 4;     // ... and how many of them share one TMEM lane quarter
   constexpr int TN      = FP4 ? kTNFp4 : kTN;  // tile columns; the accumulator stages sit TN TMEM columns apart
   constexpr int kBBytes = TN * kTK;
-  static_assert(!FP4 || MODE == kTcCount, "the fp4 tile serves the count mode");
+  constexpr bool FP4C = FP4 && MODE == kTcCount;  // the count-mode extras of the fp4 tile (pre-filter, candidate list)
   static_assert(!CL || FP4, "the two-CTA cluster is wired for the fp4 count tile");
   const uint32_t rank      = CL ? clusterCtaRank() : 0u;
   const uint32_t firstUnit = CL ? blockIdx.x / 2 : blockIdx.x, unitStep = CL ? gridDim.x / 2 : gridDim.x;
@@ -536,8 +541,8 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
   // instead of one per 32 x 32 block that holds a candidate (a ~1k-clock round trip most blocks paid: with 8 pairs per
   // accumulator more than half of the blocks have a survivor; profiles/r02_path_a_summary.md)
   constexpr int kCandStage = kStagesCountFp4 > 4 ? 32 : 64;
-  __shared__ int2 candStage[FP4 ? kEpiWarps : 1][FP4 ? kCandStage : 1];
-  __shared__ __align__(16) float colAdj[2][FP4 ? kTN : 4];  // fp4 count tile: alpha * |B_j| (rounded down), +inf for columns past the end
+  __shared__ int2 candStage[FP4C ? kEpiWarps : 1][FP4C ? kCandStage : 1];
+  __shared__ __align__(16) float colAdj[2][FP4C ? kTN : 4];  // fp4 count tile: alpha * |B_j| (rounded down), +inf for columns past the end
 
   const uint32_t smemA    = (smemAddr(smemRaw) + 1023u) & ~1023u;  // (stationary tile: the row operand's K chunks)
   const uint32_t smemBase = smemA + kAResident;                    // the ring
@@ -745,7 +750,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
     uint32_t       tnOf[2] = {0, 0};  // tile column each accumulator-side buffer last served
     int            nStaged = 0;       // entries of candStage[ew] (the same in every lane)
     auto flushCandidates = [&]() {
-      if constexpr (FP4) {
+      if constexpr (FP4C) {
         if (nStaged == 0) return;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(p.candCursor, static_cast<unsigned long long>(nStaged));
@@ -786,7 +791,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         const int      pb = gc < p.nY ? __ldg(p.popY + gc) : 0;
         popB[as][c]       = pb;
         colAcc[as][c]     = 0;
-        if constexpr (FP4) colAdj[as][c] = gc < p.nY ? __fmul_rd(p.alpha, static_cast<float>(pb)) : 3.0e38f;
+        if constexpr (FP4C) colAdj[as][c] = gc < p.nY ? __fmul_rd(p.alpha, static_cast<float>(pb)) : 3.0e38f;
         if (gc < p.nY) minPb = min(minPb, pb);
       }
       tnOf[as] = tn;
@@ -851,7 +856,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int j   = 16 * h + 2 * c + e;
-                  const int cnt = static_cast<int>(r[j]);
+                  const int cnt = FP4 ? __float2int_rn(__uint_as_float(r[j])) : static_cast<int>(r[j]);
                   const int pb  = popB[as][cb * 32 + j];
                   double    v   = 0.0;
                   if (cnt != 0) {
@@ -911,7 +916,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
               if (row0 + k >= p.n) break;
-              const int c   = static_cast<int>(r[k]);
+              const int c   = FP4 ? __float2int_rn(__uint_as_float(r[k])) : static_cast<int>(r[k]);
               const int pak = popA[as][quarter * 32 + k];
               double    v   = 0.0;
               if (c != 0) {
@@ -943,7 +948,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
         // (profiles/r02_path_a_summary.md).
         uint32_t maybe = 0;
         bool     hot;
-        if constexpr (FP4) {
+        if constexpr (FP4C) {
           const float4* adj4 = reinterpret_cast<const float4*>(&colAdj[as][cb * 32]);
           float         vv[32];
 #pragma unroll
@@ -1021,7 +1026,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
               }
               total = __shfl_sync(0xffffffffu, incl, 31);
             }
-            if constexpr (FP4) {
+            if constexpr (FP4C) {
               if (total <= kCandStage) {
                 if (nStaged + total > kCandStage) flushCandidates();
                 int at = nStaged + incl - mine;
@@ -1219,13 +1224,13 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   const bool same = (q.x == q.y && q.nX == q.nY);
   if (q.symmetric && !same) return false;
 
-  // count mode: block-scaled fp4 operands (twice the int8 MMA rate, half the operand bytes) when the fingerprint is a
-  // whole number of 256-bit chunks; the materialise modes (HBM-bound on the fp64 output) keep the int8 tile
+  // block-scaled fp4 operands (twice the int8 MMA rate, half the operand bytes through shared memory) when the
+  // fingerprint is a whole number of 256-bit chunks, in every mode; else the int8 tile
   const bool count = mode == kCountTanimoto;
-  const bool fp4   = count && g_tensorFp4 && bits % (2 * kTK) == 0;
+  const bool fp4   = g_tensorFp4 && bits % (2 * kTK) == 0;
   const int  tn    = fp4 ? kTNFp4 : kTN;
   const int  rowBytes = fp4 ? bits / 2 : bits;  // bytes of one expanded fingerprint
-  if (!fp4) superS = superC = 1;  // the superposed sums need the fp4 value set {0..4}
+  if (!fp4 || !count) superS = superC = 1;  // the superposed sums need the fp4 value set {0..4}; only the count mode verifies
   const bool   super  = superS * superC > 1;
   const size_t nSuper = (q.nX + superS - 1) / superS;   // rows of the X operand
   const size_t nSuperY = (q.nY + superC - 1) / superC;  // rows of the Y operand (tile columns)
@@ -1328,7 +1333,7 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
 
   CUtensorMap tmA, tmB;
   makeTensorMap2D(&tmA, expX.get(), nSuper, rowBytes, kTM, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
-  const bool cluster = fp4 && g_tensorCluster != 0;  // CTA pairs: 1 = multicast column operand, 2 = cta_group::2 MMAs,
+  const bool cluster = fp4 && count && g_tensorCluster != 0;  // CTA pairs: 1 = multicast column operand, 2 = cta_group::2 MMAs,
   const bool pairMma = cluster && g_tensorCluster == 2;  // 3 = multicast column operand + stationary row operand
   const bool stationary = cluster && g_tensorCluster == 3 && p.kChunks <= kMaxChunksStat;
   makeTensorMap2D(&tmB, expY, nSuperY, rowBytes, cluster ? tn / 2 : tn, kTK, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
@@ -1358,6 +1363,8 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     optIn(simTensorKernel<kTcCount, true, 3>);
     optIn(simTensorKernel<kTcTanimoto, false, 0>);
     optIn(simTensorKernel<kTcCosine, false, 0>);
+    optIn(simTensorKernel<kTcTanimoto, true, 0>);
+    optIn(simTensorKernel<kTcCosine, true, 0>);
     configured[currentDeviceSlot()] = true;
   }
   constexpr size_t kStaticMax = kStagesCountFp4 > 4 ? 9472 : 12288;  // static shared memory of the largest variant
@@ -1399,10 +1406,12 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, tmOut, p);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcTanimoto, false, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, tmOut, p);
+    if (fp4) simTensorKernel<kTcTanimoto, true, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, tmOut, p);
+    else simTensorKernel<kTcTanimoto, false, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, tmOut, p);
   } else {
     PhaseTimer t("cross_tc", s);
-    simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, tmOut, p);
+    if (fp4) simTensorKernel<kTcCosine, true, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, tmOut, p);
+    else simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, tmOut, p);
   }
   B200_LAUNCHED();
   if (super) {
