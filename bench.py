@@ -160,6 +160,7 @@ def run_b200(args) -> None:
 
     from nvmolkit_b200 import _lib, synthetic
     from nvmolkit_b200.clustering import fused_butina_device, fused_butina_sharded
+    from nvmolkit_b200.distributed import sharded_upload
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,7 +217,9 @@ def run_b200(args) -> None:
         return fused_butina_sharded(x, CUTOFF)
 
     def step_e2e():
-        x = h_fp.to(dev, non_blocking=True)
+        # one GPU: the whole array over PCIe; several: each rank uploads 1/world of the rows and the ranks all-gather the
+        # slices over NVLink (nvmolkit_b200.distributed.sharded_upload) - the public multi-GPU entry for host fingerprints
+        x = sharded_upload(h_fp, dev) if world > 1 else h_fp.to(dev, non_blocking=True)
         ids, cen = step_device(x)
         h_ids.copy_(ids, non_blocking=True)
         stream.synchronize()
@@ -295,6 +298,20 @@ def run_b200(args) -> None:
                                   "frac": bytes_c / (ms_c * 1e-3) / 1e9 / peak_c, "algorithmic_bytes": bytes_c,
                                   "kernel": "simTensorKernel<materialise> (cross_tc)", "peak_source": src_c}}
         del res
+        # BASELINE config 1: 1k x 1k (whole call through the public function, CUDA events on the current stream)
+        ya, yb = d_fp[:1000], d_fp[1000:2000]
+        for _ in range(5):
+            crossTanimotoSimilarity(ya, yb)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            crossTanimotoSimilarity(ya, yb)
+        e1.record()
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / 50
+        if cross is not None:
+            cross["config1_1k_x_1k"] = {"ms_per_call": ms1, "pairs_per_s": 1e6 / (ms1 * 1e-3),
+                                        "algorithmic_GBps": (8.0e6 + 256.0 * 2000) / (ms1 * 1e-3) / 1e9}
 
     # second half of the BASELINE metric: ETKDG + MMFF mols/s on config 3 (and configs 4 / 5 on eight GPUs)
     legs = run_conformer_legs(args, pool, dev, world, rank) if pool is not None else {}
@@ -364,7 +381,9 @@ def run_b200(args) -> None:
                    "n_fingerprints": n, "fp_bits": words * 32, "cutoff": CUTOFF, "pairs_counted": "unique n(n-1)/2",
                    "l2": "inputs (256 MB) larger than L2", "parallelism": f"row-group x{world}" if world > 1 else "1gpu"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(n * words * 4), "d2h_bytes_per_step": int(n * 4),
-                "ms_per_step": ms_e2e},
+                "ms_per_step": ms_e2e,
+                "h2d": ("whole job: every rank copies 1/world of the rows from pinned host memory, the slices are all-gathered "
+                        "over NVLink (distributed.sharded_upload)") if world > 1 else "pinned host -> device, whole array"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roofline if roofline is not None else {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -170,6 +170,10 @@ static inline void readBfgsClocks(unsigned long long* out) {
 // together by one exchange-halving butterfly (9 shuffles for 8 values instead of 40). Columns [n, ld) hold zeros, so
 // only the chunk that contains the diagonal needs per-element masks. The sweep is issue-bound, not latency-bound
 // (profiles/r01_path_b_summary.md), hence the instruction diet.
+#ifndef B200_SWEEP_PREFETCH
+#define B200_SWEEP_PREFETCH 2
+#endif
+constexpr int kSweepPrefetch = B200_SWEEP_PREFETCH;  // batches ahead the sweep asks its rows into L2 (0 = off)
 template <class HT, bool FRESH, bool PENDING>
 __device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT cfac, HT cfad, HT cfae, const HT* px, const HT* ph,
                                            const HT* pu, const HT* vD, const HT* vG, double* outD, double* outG, double* colBuf) {
@@ -267,9 +271,25 @@ __device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT
       }
     };
     // rows above the chunk's diagonal block: no masks; rows inside it (CW is a multiple of 4): masked
+    // The slabs live in HBM (444 of them do not fit L2 next to the streaming term tables) and a warp has four row packs
+    // in flight: while it works on a batch, the rows of its batch after next are asked into L2 (no registers: keeping
+    // the next batch in registers spills at the 80-register budget of three CTAs per SM).
+    // lanes 8 q + l, l < 4: row q of the batch, 128-byte line l of its 512 bytes in this chunk
+    const int  pfCol = c0 + (lane & 7) * static_cast<int>(128 / sizeof(HT));
+    const bool pfOn  = !FRESH && kSweepPrefetch > 0 && (lane & 7) < 4 && pfCol < ld;
+    const HT*  pfAt  = H + static_cast<size_t>(lane >> 3) * ld + pfCol;
+    auto ahead = [&](int i) {
+      if (pfOn && i + (lane >> 3) < rowEnd) asm volatile("prefetch.global.L2 [%0];" ::"l"(pfAt + static_cast<size_t>(i) * ld));
+    };
     int i0 = 4 * warp;
-    for (; i0 < min(c0, rowEnd); i0 += 4 * kWarps) batch(i0, std::false_type{});
-    for (; i0 < rowEnd; i0 += 4 * kWarps) batch(i0, std::true_type{});
+    for (; i0 < min(c0, rowEnd); i0 += 4 * kWarps) {
+      ahead(i0 + kSweepPrefetch * 4 * kWarps);
+      batch(i0, std::false_type{});
+    }
+    for (; i0 < rowEnd; i0 += 4 * kWarps) {
+      ahead(i0 + kSweepPrefetch * 4 * kWarps);
+      batch(i0, std::true_type{});
+    }
     // column sums of the chunk: every warp parks its partials, then one thread per column adds the kWarps of them in a
     // fixed order (no atomics: bit-reproducible)
     HT* colD = reinterpret_cast<HT*>(colBuf);

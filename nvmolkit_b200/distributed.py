@@ -45,6 +45,26 @@ def all_gather_v(t: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tenso
     return torch.cat(parts, dim=0), sizes_h
 
 
+def sharded_upload(h: torch.Tensor, device, group=None) -> torch.Tensor:
+    """Host rows that EVERY rank needs on its device (the fingerprints of a sharded Butina pass): each rank copies only
+    its 1/world of the rows over PCIe and the ranks all-gather the slices over NVLink, instead of every rank pulling the
+    whole array through the host at the same time (8 x 256 MB at 1M fingerprints). `h` is the same host tensor on every
+    rank (pinned for an asynchronous copy). Returns the full [n, ...] device tensor; the copies are stream-ordered."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return h.to(device, non_blocking=True)
+    n = h.shape[0]
+    chunk = (n + world - 1) // world  # equal slices for all_gather_into_tensor; the last one is padded
+    full = torch.empty((world * chunk,) + tuple(h.shape[1:]), dtype=h.dtype, device=device)
+    lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+    mine = full[rank * chunk:(rank + 1) * chunk]
+    mine[: hi - lo].copy_(h[lo:hi], non_blocking=True)
+    if hi - lo < chunk:
+        mine[hi - lo:].zero_()
+    dist.all_gather_into_tensor(full, mine.clone() if full.device.type == "cpu" else mine, group=group)
+    return full[:n]
+
+
 def map_molecule_range(n_items: int, compute, group=None) -> torch.Tensor:
     """Run `compute(lo, hi) -> tensor[hi - lo, ...]` on this rank's contiguous share of `n_items` independent items
     (molecules, fingerprint rows) and return the results of all ranks, concatenated in item order, on every rank.

@@ -48,6 +48,10 @@ _WORKER = textwrap.dedent("""
     assert rows.ravel().tolist() == [10 * i for i in range(11)]  # item order preserved, every rank has everything
     rows = map_molecule_range(1, lambda lo, hi: torch.arange(lo, hi, dtype=torch.int64).reshape(-1, 1))  # one rank gets nothing
     assert rows.ravel().tolist() == [0]
+    from nvmolkit_b200.distributed import sharded_upload
+    for n in (1, 7, 8, 13):
+        h = torch.arange(n * 3, dtype=torch.int32).reshape(n, 3)
+        assert torch.equal(sharded_upload(h, "cpu"), h)  # every rank ends up with all rows although it copied only its slice
     dist.destroy_process_group()
     print("rank", rank, "ok")
 """)

@@ -15,6 +15,8 @@ from nvmolkit_b200.similarity import crossTanimotoSimilarity  # noqa: E402
 
 sizes = [int(a) for a in sys.argv[1:]] or [1000, 4096, 16384, 32768]
 _lib.profile_enable(True)
+if os.environ.get("B200_MIN_PAIRS"):  # e.g. 0: the tensor tile for every size (default: from 2^24 pairs up)
+    _lib.set_option("similarity_tensor_min_pairs", int(os.environ["B200_MIN_PAIRS"]))
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 for n in sizes:
     a = torch.from_numpy(synthetic.random_fingerprints(n, seed=1, near_dups=n // 8).view(np.int32)).cuda()
@@ -31,7 +33,7 @@ for n in sizes:
     torch.cuda.synchronize()
     ms_call = e0.elapsed_time(e1) / reps
     try:
-        ms_k, phase = _lib.profile_read("cross_tc"), "cross_tc (tcgen05 i8 tile)"
+        ms_k, phase = _lib.profile_read("cross_tc"), "cross_tc (tcgen05 tile: fp4 operands when the fingerprint is a multiple of 256 bits, else int8)"
     except ValueError:
         ms_k, phase = ms_call, "whole call (SIMT popcount tile; below similarity_tensor_min_pairs)"
     bytes_ = 8.0 * n * n + 512.0 * n
