@@ -171,7 +171,7 @@ static inline void readBfgsClocks(unsigned long long* out) {
 // only the chunk that contains the diagonal needs per-element masks. The sweep is issue-bound, not latency-bound
 // (profiles/r01_path_b_summary.md), hence the instruction diet.
 #ifndef B200_SWEEP_PREFETCH
-#define B200_SWEEP_PREFETCH 2
+#define B200_SWEEP_PREFETCH 0
 #endif
 constexpr int kSweepPrefetch = B200_SWEEP_PREFETCH;  // batches ahead the sweep asks its rows into L2 (0 = off)
 template <class HT, bool FRESH, bool PENDING>
@@ -272,8 +272,9 @@ __device__ __noinline__ void hessianSweepT(HT* __restrict__ H, int ld, int n, HT
     };
     // rows above the chunk's diagonal block: no masks; rows inside it (CW is a multiple of 4): masked
     // The slabs live in HBM (444 of them do not fit L2 next to the streaming term tables) and a warp has four row packs
-    // in flight: while it works on a batch, the rows of its batch after next are asked into L2 (no registers: keeping
-    // the next batch in registers spills at the 80-register budget of three CTAs per SM).
+    // in flight. Two ways of getting further ahead were measured and rejected (profiles/r02_path_b_summary.md): the next
+    // batch in registers spills at the 80-register budget of three CTAs per SM; asking the rows of a later batch into L2
+    // with prefetch.global.L2 (B200_SWEEP_PREFETCH = batches ahead) is 3-5 % SLOWER than nothing (0, the default).
     // lanes 8 q + l, l < 4: row q of the batch, 128-byte line l of its 512 bytes in this chunk
     const int  pfCol = c0 + (lane & 7) * static_cast<int>(128 / sizeof(HT));
     const bool pfOn  = !FRESH && kSweepPrefetch > 0 && (lane & 7) < 4 && pfCol < ld;
