@@ -6,7 +6,10 @@
 
 namespace b200 {
 
-constexpr int kT     = 256;  // threads per CTA
+#ifndef B200_BFGS_THREADS
+#define B200_BFGS_THREADS 256
+#endif
+constexpr int kT     = B200_BFGS_THREADS;  // threads per CTA (one conformer per CTA)
 constexpr int kWarps = kT / 32;
 #ifndef B200_BFGS_MIN_CTAS
 #define B200_BFGS_MIN_CTAS 3

@@ -5,7 +5,10 @@
 
 namespace b200 {
 
-constexpr int kEigT = 256;  // threads per CTA of every caller
+#ifndef B200_BFGS_THREADS
+#define B200_BFGS_THREADS 256
+#endif
+constexpr int kEigT = B200_BFGS_THREADS;  // threads per CTA of every caller (the embedder's CTA shape)
 
 __device__ __forceinline__ double warpSumD(double v) {
 #pragma unroll
