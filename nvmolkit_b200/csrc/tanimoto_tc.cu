@@ -1,19 +1,29 @@
-// Thresholded popcount similarity on the 5th-generation tensor cores (tcgen05), sm_100a.
+// Popcount similarity on the 5th-generation tensor cores (tcgen05), sm_100a: the thresholded neighbour pass of the fused
+// Butina path and the materialised Tanimoto / cosine matrices.
 //
-// |A & B| of two bit vectors is the dot product of their 0/1 expansions, so the N x M intersection-count matrix is an
-// unsigned-int8 GEMM with s32 accumulation (exact). The SIMT tile (tanimoto.cu) sits on the POPC issue roof
-// (64 POPC per 2048-bit pair, 16 lanes/clk/SM -> 7e10 pairs/s, profiles/r01_path_a_summary.md); the reference reaches
-// its tensor path through `mma.sync ... b1 ... and.popc`, which ptxas lowers on sm_100a to bit-slicing LOP3s plus
-// eight IMMA.16832.U8.U8 per 256-bit step — i.e. it already runs this contraction as an int8 MMA, through the legacy
-// warp-level path. Here it is issued natively:
+// |A & B| of two bit vectors is the dot product of their 0/1 expansions, so the N x M intersection-count matrix is a
+// GEMM with exact small-integer sums. The SIMT tile (tanimoto.cu) sits on the POPC issue roof (64 POPC per 2048-bit
+// pair, 16 lanes/clk/SM -> 7e10 pairs/s, profiles/r01_path_a_summary.md); the reference reaches its tensor path through
+// `mma.sync ... b1 ... and.popc`, which ptxas lowers on sm_100a to bit-slicing LOP3s plus eight IMMA.16832.U8.U8 per
+// 256-bit step - the legacy warp-level path. Here the contraction is issued natively:
 //
-//   pre-pass   bits -> bytes (0/1) once per fingerprint set, [n][bits] u8 in HBM (2 KB per 2048-bit row)
-//   tile       128 (rows of X) x 256 (rows of Y) pairs per step of a persistent CTA
-//   warp 0     TMA producer: [128|256 rows][128 B] K-chunks, SWIZZLE_128B, 4-stage mbarrier ring
-//   warp 1     one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (M128 N256 K32), accumulators in TMEM
-//              (2 x 256 columns: the next tile's MMAs overlap this tile's epilogue), tcgen05.commit -> mbarriers
-//   warps 2-5  epilogue: tcgen05.ld 32x32b, integer threshold test c >= thresh[|A|+|B|] (bit-exact with the fp64
-//              predicate, see tanimoto.cu), neighbour counts for both endpoints, warp-aggregated edge append
+//   pre-pass   bits -> packed E2M1 (fp4) once per fingerprint set, 1 KB per 2048-bit row; for the neighbour pass a row
+//              operand is the SUM of S = 4 fingerprints and a column operand the sum of C = 1, 2 or 4 (values <= 4 and
+//              products <= 16 are exact), so one accumulator bounds S * C pair counts. Fingerprints that are no multiple
+//              of 256 bits take the int8 tile (0/1 bytes, kind::i8, 128 x 256).
+//   tile       128 x 224 accumulators per step of a persistent CTA (CTA pairs share the column operand: TMA multicast)
+//   warp 0     TMA producer: [128 | 224 rows][128 B] K-chunks, SWIZZLE_128B, mbarrier ring (4 stages; 3 when materialising)
+//   warp 1     one elected thread issues tcgen05.mma.cta_group::1.kind::mxf4.block_scale (M128 N224 K64, every scale
+//              factor 1.0), accumulators in TMEM (2 x 224 columns: the next tile's MMAs overlap this tile's epilogue)
+//   warps 2-9  count epilogue: the two warps of a TMEM lane quarter alternate tiles; tcgen05.ld 32x32b, one subtract and
+//              one max tree per 32 columns decide "no pair of this group can reach its threshold"; survivors go to a
+//              candidate list (staged per warp in shared memory) that verifyCandidatesKernel re-counts exactly with the
+//              integer threshold table (bit-exact with the fp64 predicate, see tanimoto.cu). Unsuperposed (S = C = 1) the
+//              same warps apply the exact test themselves: neighbour counts for both endpoints + warp-aggregated edges.
+//   warps 2-17 materialise epilogue: fp64 Tanimoto / cosine values staged per warp with the 128-byte swizzle and stored
+//              by TMA (cp.async.bulk.tensor store).
+// A pilot over a prefix sample picks C for the data at hand; a candidate-list overflow reruns with fewer pairs per
+// accumulator before anything has been counted. Measurements: profiles/r02_path_a_summary.md.
 //
 // Replaces crossSimilarityKernelTensorOp (src/similarity_kernels.cu:104-240) + the Triton count kernel
 // (nvmolkit/_fusedButina.py:99-179) for the fused Butina pass.
@@ -739,7 +749,7 @@ __global__ void __launch_bounds__(threadsTC(MODE), 1)
 #endif
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2 .. 2 + kEpiWarps) =====================
     const int      ew      = warp - 2;             // 0..kEpiWarps-1
     const int      quarter = warp & 3;             // TMEM lane quarter this warp may read
     const int      part    = ew >> 2;              // count: which accumulator buffer this warp serves; else its share of the column blocks
