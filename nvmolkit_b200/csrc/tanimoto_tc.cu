@@ -1196,7 +1196,7 @@ bool launchSimilarityTensor(SimMode mode, const SimLaunch& q, cudaStream_t s) {
     SimLaunch pilot   = q;
     pilot.groupOffset = 0;
     pilot.groupStride = 1;
-    pilot.nX          = std::min<size_t>(65536, std::max<size_t>(2 * kGroupRows, q.nX / 8));
+    pilot.nX          = std::min<size_t>(32768, std::max<size_t>(2 * kGroupRows, q.nX / 8));
     pilot.nY          = q.symmetric ? pilot.nX : std::min<size_t>(q.nY, std::max<size_t>(pilot.nX, q.nY / 8));
     const double sX = static_cast<double>(pilot.nX), sY = static_cast<double>(pilot.nY);
     const double pilotPairs = q.symmetric ? sX * (sX - 1) / 2.0 : sX * sY;
