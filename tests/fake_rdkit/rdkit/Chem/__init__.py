@@ -73,6 +73,20 @@ class Atom:
     def GetHybridization(self):
         return self._m.hyb[self._i]
 
+    # what the Morgan invariant generator asks for (src/morgan_fingerprint_common.cpp:43-124); hydrogens are explicit
+    # atoms in the synthetic molecules, charges / isotopes come from optional per-atom arrays of the dict
+    def GetNumExplicitHs(self):
+        return 0
+
+    def GetNumImplicitHs(self):
+        return int(self._m.d.get("implicit_hs", [0] * self._m.GetNumAtoms())[self._i])
+
+    def GetFormalCharge(self):
+        return int(self._m.d.get("formal_charge", [0] * self._m.GetNumAtoms())[self._i])
+
+    def GetMass(self):
+        return GetPeriodicTable().GetAtomicWeight(self.GetAtomicNum()) + float(self._m.d.get("isotope_delta", [0] * self._m.GetNumAtoms())[self._i])
+
     def GetChiralTag(self):
         return self._m.chiral.get(self._i, ChiralType.CHI_UNSPECIFIED)
 
@@ -173,6 +187,17 @@ class Mol:
 
     def GetSubstructMatches(self, query):  # the default torsion-bond SMARTS: bonds whose two atoms both have degree > 1
         return [(i, j) for i, j in self.d["bonds"] if len(self.d["nbrs"][i]) > 1 and len(self.d["nbrs"][j]) > 1]
+
+
+class _PeriodicTable:
+    _W = {1: 1.008, 6: 12.011, 7: 14.007, 8: 15.999, 9: 18.998, 15: 30.974, 16: 32.06, 17: 35.45, 35: 79.904}
+
+    def GetAtomicWeight(self, z):
+        return self._W.get(int(z), 2.0 * int(z))
+
+
+def GetPeriodicTable():
+    return _PeriodicTable()
 
 
 def MolFromSmarts(s):

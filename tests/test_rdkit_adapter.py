@@ -70,6 +70,40 @@ def _mols(n, seed, with_uff=False):
     return flat, mols
 
 
+def test_morgan_invariant_adapter_feeds_the_fingerprint_path(fake_rdkit):
+    """molgraph.from_rdkit walks atoms / bonds / ring info the way MorganInvariantsGenerator does
+    (src/morgan_fingerprint_common.cpp:43-124) and its CSR batch is what b200mol_morgan / the oracle consume."""
+    from nvmolkit_b200.molgraph import atom_invariant, from_rdkit
+
+    Chem = fake_rdkit
+    _flat, mols = S.random_embed_molecules(5, 5, 12, seed=17)
+    mols[1]["formal_charge"] = [1 if a == 0 else 0 for a in range(len(mols[1]["z"]))]
+    mols[2]["isotope_delta"] = [1.0 if a == 1 else 0.0 for a in range(len(mols[2]["z"]))]
+    mols[3]["implicit_hs"] = [2 if a == 0 else 0 for a in range(len(mols[3]["z"]))]
+    ring = [(0, 1, 2)]  # (only membership matters to the invariant)
+    rd = [Chem.Mol(m, rings=ring if k == 4 else (), bond_types=[Chem.BondType.DOUBLE if b == 0 else Chem.BondType.SINGLE
+                                                                for b in range(len(m["bonds"]))]) for k, m in enumerate(mols)]
+    batch = from_rdkit(rd)
+    assert batch.atom_starts.tolist() == np.concatenate([[0], np.cumsum([len(m["z"]) for m in mols])]).tolist()
+    assert batch.bond_starts.tolist() == np.concatenate([[0], np.cumsum([len(m["bonds"]) for m in mols])]).tolist()
+    for k, m in enumerate(mols):
+        a0, b0 = batch.atom_starts[k], batch.bond_starts[k]
+        for a in range(len(m["z"])):
+            nbr_h = sum(1 for j in m["nbrs"][a] if m["z"][j] == 1)
+            hs = m.get("implicit_hs", [0] * len(m["z"]))[a]
+            want = atom_invariant(int(m["z"][a]), hs + len(m["nbrs"][a]), hs + nbr_h, m.get("formal_charge", [0] * len(m["z"]))[a],
+                                  int(m.get("isotope_delta", [0] * len(m["z"]))[a]), k == 4 and a in ring[0])
+            assert batch.atom_inv[a0 + a] == want, (k, a)
+        for b, (i, j) in enumerate(m["bonds"]):
+            assert (batch.bond_a[b0 + b], batch.bond_b[b0 + b]) == (i, j)
+            assert batch.bond_inv[b0 + b] == (2 if b == 0 else 1)
+    # the batch goes straight into the fingerprint path (CPU twin here; the GPU kernel is pinned to it bit for bit)
+    bits = oracle.morgan(batch.atom_starts, batch.bond_starts, batch.atom_inv, batch.bond_inv, batch.bond_a, batch.bond_b, 2, 2048)
+    assert bits.shape == (5, 64) and all(int(np.unpackbits(r.view(np.uint8)).sum()) > 0 for r in bits)
+    with pytest.raises(ValueError):
+        from_rdkit([None])
+
+
 def test_mmff_adapter_reproduces_the_parameter_tables(fake_rdkit):
     Chem = fake_rdkit
     from nvmolkit_b200 import rdkit_adapter as A
