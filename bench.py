@@ -188,6 +188,8 @@ def run_b200(args) -> None:
         _lib.set_option("bfgs_l2_persist", 1)
     if args.superpose_cols >= 0:
         _lib.set_option("similarity_superpose_cols", args.superpose_cols)
+    if args.pipeline_chunks >= 0:
+        _lib.set_option("similarity_pipeline_chunks", args.pipeline_chunks)
     if args.superpose_auto >= 0:
         _lib.set_option("similarity_superpose_auto", args.superpose_auto)
     if args.workload == "conformers":
@@ -267,8 +269,11 @@ def run_b200(args) -> None:
             pass
         if tensor_path:
             phases["neighbor_pass_tc"] = _lib.profile_read("neighbor_pass_tc")
-        step_e2e()
-        ms_e2e, _ = timed(step_e2e, args.steps)
+    # end to end after the clock sampler has stopped (nvidia-smi queries take the driver for a while; this loop is host-driven:
+    # a pinned 256 MB copy, the call, a 4 MB copy back). Its time depends on the box's host link: 59-70 ms per step on most
+    # boxes of the pool, 115 ms on some (profiles/r02_path_a_summary.md)
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
 
     # materialised cross-similarity (the reference's crossTanimotoSimilarity output format): HBM-write bound, 8 B / pair
     cross = None
@@ -729,6 +734,7 @@ def main() -> None:
     ap.add_argument("--tensor-cluster", type=int, default=-1, help="pair-pass tile variant override (testing; -1 = library default)")
     ap.add_argument("--superpose", type=int, default=-1, help="pair-pass row superposition override (testing; -1 = library default)")
     ap.add_argument("--bfgs-l2-persist", action="store_true", help="mark the minimisers' inverse-Hessian slabs persisting in L2 (experiment)")
+    ap.add_argument("--pipeline-chunks", type=int, default=-1, help="chunks of the pipelined pass / verification (testing; -1 = library default, 1 = off)")
     ap.add_argument("--superpose-auto", type=int, default=-1, help="0: no pilot passes, run the configured factors (profiling; -1 = library default)")
     ap.add_argument("--superpose-cols", type=int, default=-1, help="pair-pass column superposition override (testing; -1 = library default)")
     ap.add_argument("--hessian-compare-mols", type=int, default=2000,

@@ -55,6 +55,9 @@ int b200mol_free_async(void* d_ptr, void* stream);
  *   "similarity_superpose_cols"    4 (default), 2 or 1: the same for the column operand (sums of products stay <= 16,
  *                                  exact): one accumulator bounds rows x cols pair counts. A pass whose candidate list
  *                                  overflows (dense graph) reruns with rows only, then unsuperposed - results identical
+ *   "similarity_pipeline_chunks"   4 (default): from 16 row groups (131,072 fingerprints) up a superposed pass runs as that
+ *                                  many chunks of its row groups; the exact verification of a chunk overlaps the tensor
+ *                                  pass of the next on a second stream. 1 = off. Results identical
  *   "similarity_superpose_auto"    1 (default): a pass over >= 65,536 fingerprints first runs a pilot over a prefix
  *                                  sample per column factor and keeps the factor a cost model finds cheapest (the
  *                                  sum of rows x cols random intersections must stay below one true pair's threshold);

@@ -313,6 +313,7 @@ extern int g_superpose;
 extern int g_superposeLast;
 extern int g_superposeCols;
 extern int g_superposeAuto;
+extern int g_pipelineChunks;
 extern unsigned long long g_candidatesLast;
 long long g_tensorMinPairs = 1ll << 24;  // pair count from which the count mode runs on tcgen05 (< 0: never)
 
@@ -438,6 +439,10 @@ extern "C" int b200mol_set_option(const char* key, long long value) {
       g_superposeCols = static_cast<int>(value);
     }
     else if (k == "similarity_superpose_auto") g_superposeAuto = value != 0;
+    else if (k == "similarity_pipeline_chunks") {
+      B200_REQUIRE(value >= 1 && value <= 8, "similarity_pipeline_chunks must be in [1, 8]");
+      g_pipelineChunks = static_cast<int>(value);
+    }
     else if (k == "similarity_tensor_fp4") g_tensorFp4 = value != 0;
     else if (k == "similarity_tensor_cluster") {
       B200_REQUIRE(value >= 0 && value <= 3, "similarity_tensor_cluster must be 0, 1, 2 or 3");
@@ -464,6 +469,7 @@ extern "C" int b200mol_get_option(const char* key, long long* value) {
     else if (k == "similarity_superpose") *value = g_superpose;
     else if (k == "similarity_superpose_cols") *value = g_superposeCols;
     else if (k == "similarity_superpose_auto") *value = g_superposeAuto;
+    else if (k == "similarity_pipeline_chunks") *value = g_pipelineChunks;
     else if (k == "similarity_candidates_last") *value = static_cast<long long>(g_candidatesLast);
     else if (k == "similarity_superpose_last") *value = g_superposeLast;  // read-only: pairs per accumulator of the last pass
     else if (k == "butina_min_round_commits") *value = g_butinaMinCommits;

@@ -1167,6 +1167,9 @@ int g_superpose = 4;      // fingerprints summed into one row of the count pass 
 int g_superposeCols = 4;  // ... and into one column ("similarity_superpose_cols": 1, 2 or 4); 4 x 4 sums stay <= 16, exact
 int g_superposeLast = 0;  // pairs per accumulator the last graph pass really ran with (1 after an overflow fallback)
 
+constexpr int kMaxPipeline = 8;
+int g_pipelineChunks = 4;  // chunks of a superposed pass whose verification overlaps the next chunk's tensor pass
+                           // (option "similarity_pipeline_chunks"; 1 = off)
 int g_superposeAuto = 1;  // 1: a large graph pass picks rows x cols from a pilot over one row group ("similarity_superpose_auto")
 unsigned long long g_candidatesLast = 0;  // candidates the last superposed pass listed ("similarity_candidates_last")
 
@@ -1327,8 +1330,8 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     const unsigned long long all = static_cast<unsigned long long>(nSuper) * nSuperY;
     candCap                      = std::min<unsigned long long>(all, std::max<unsigned long long>(1ull << 22, 64ull * q.nX));
     cand                         = Scratch<int2>(candCap, s);
-    candCursor                   = Scratch<unsigned long long>(1, s);
-    B200_CUDA(cudaMemsetAsync(candCursor.get(), 0, sizeof(unsigned long long), s));
+    candCursor                   = Scratch<unsigned long long>(kMaxPipeline, s);
+    B200_CUDA(cudaMemsetAsync(candCursor.get(), 0, kMaxPipeline * sizeof(unsigned long long), s));
     p.cand = cand.get(), p.candCursor = candCursor.get(), p.candCap = candCap;
   }
   const int         maxS = 2 * bits;
@@ -1379,15 +1382,16 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
   }
   constexpr size_t kStaticMax = kStagesCountFp4 > 4 ? 9472 : 12288;  // static shared memory of the largest variant
   B200_REQUIRE(smemBytes + kStaticMax <= 227 * 1024, "tensor similarity tile does not fit shared memory");
-  // units this call owns: tiles, or vertical tile pairs (same enumeration as the kernel's UnitWalk)
-  const uint64_t total = stationary ? countUnits<kTNFp4, true, kRunStat>(p)
-                         : cluster  ? countUnits<kTNFp4, true>(p)
-                                    : (fp4 ? countUnits<kTNFp4, false>(p) : countUnits<kTN, false>(p));
-  if (total == 0) return true;  // nothing owned by this rank (more ranks than row groups)
-  int            blocks  = smCount();
-  if (static_cast<uint64_t>(blocks) > total) blocks = static_cast<int>(total);
-  if (mode == kCountTanimoto) {
-    PhaseTimer t("neighbor_pass_tc", s);
+  // units a call owns: tiles, or vertical tile pairs (same enumeration as the kernel's UnitWalk)
+  auto unitsOf = [&](const TcParams& pk) -> uint64_t {
+    return stationary ? countUnits<kTNFp4, true, kRunStat>(pk)
+           : cluster  ? countUnits<kTNFp4, true>(pk)
+                      : (fp4 ? countUnits<kTNFp4, false>(pk) : countUnits<kTN, false>(pk));
+  };
+  // the count kernel over the row groups `pk` selects (false: none of them is owned by this call)
+  auto launchCount = [&](const TcParams& pk) -> bool {
+    const uint64_t units = unitsOf(pk);
+    if (units == 0) return false;
     if (cluster) {
       cudaLaunchConfig_t cfg{};
       cudaLaunchAttribute attr[1];
@@ -1407,13 +1411,90 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
       else B200_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, simTensorKernel<kTcCount, true, 1>, &cfg));
       B200_REQUIRE(maxClusters >= 1, "no CTA pair fits the device");
       uint64_t pairs = maxClusters;  // persistent: one resident cluster per schedulable SM pair
-      if (pairs > total) pairs = total;
+      if (pairs > units) pairs = units;
       cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-      if (stationary) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 3>, tmA, tmB, tmOut, p));
-      else if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, tmOut, p));
-      else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, tmOut, p));
-    } else if (fp4) simTensorKernel<kTcCount, true, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, tmOut, p);
-    else simTensorKernel<kTcCount, false, 0><<<blocks, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, tmOut, p);
+      if (stationary) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 3>, tmA, tmB, tmOut, pk));
+      else if (pairMma) B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 2>, tmA, tmB, tmOut, pk));
+      else B200_CUDA(cudaLaunchKernelEx(&cfg, simTensorKernel<kTcCount, true, 1>, tmA, tmB, tmOut, pk));
+    } else {
+      const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(smCount()), units));
+      if (fp4) simTensorKernel<kTcCount, true, 0><<<grid, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, tmOut, pk);
+      else simTensorKernel<kTcCount, false, 0><<<grid, threadsTC(kTcCount), smemBytes, s>>>(tmA, tmB, tmOut, pk);
+    }
+    B200_LAUNCHED();
+    return true;
+  };
+  auto launchVerify = [&](const int2* list, unsigned long long nCand, cudaStream_t on) {
+    PhaseTimer         t("verify_candidates", on);
+    const unsigned int blocks2 = static_cast<unsigned int>(std::min<unsigned long long>((nCand + 63) / 64, static_cast<unsigned long long>(smCount()) * 16));
+    verifyCandidatesKernel<<<blocks2, 256, 0, on>>>(q.x, q.y, q.words, list, nCand, superS, superC, static_cast<uint32_t>(q.nX),
+                                                    static_cast<uint32_t>(q.nY), q.symmetric ? 1 : 0, popX.get(), popYExact,
+                                                    thresh.get(), q.sign, q.rowCounts, q.symmetric ? q.rowCounts : nullptr, q.edges,
+                                                    q.edgeCursor, q.edgeCap);
+    B200_LAUNCHED();
+  };
+
+  // Superposed pass in a PIPELINE of K chunks of the row groups (chunk k = groups k, k + K, ... of this call's): the exact
+  // verification of chunk k runs on a second stream while the tensor pass of chunk k + 1 has the SMs - a pass CTA leaves
+  // room for one verify block per SM - so only the last chunk's verification is exposed (8 ms of a 59 ms step were).
+  // A chunk whose candidate list overflowed is redone on its own with fewer pairs per accumulator after the others.
+  const uint64_t ownedGroups = ((q.nX + kGroupRows - 1) / kGroupRows + p.groupStride - 1) / p.groupStride;
+  const int      K = (super && !pilotCand && g_pipelineChunks > 1 && ownedGroups >= 4ull * g_pipelineChunks) ? g_pipelineChunks : 1;
+  if (K > 1) {
+    static cudaStream_t side[kMaxDevices] = {};
+    cudaStream_t&       s2 = side[currentDeviceSlot()];
+    if (!s2) B200_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    const unsigned long long capK = candCap / K;
+    cudaEvent_t              ev[kMaxPipeline];
+    {
+      PhaseTimer t("neighbor_pass_tc", s);  // the K tensor passes, back to back on the caller's stream
+      for (int k = 0; k < K; ++k) {
+        TcParams pk    = p;
+        pk.groupOffset = p.groupOffset + static_cast<uint32_t>(k) * p.groupStride;
+        pk.groupStride = static_cast<uint32_t>(K) * p.groupStride;
+        pk.cand        = cand.get() + static_cast<size_t>(k) * capK;
+        pk.candCursor  = candCursor.get() + k;
+        pk.candCap     = capK;
+        launchCount(pk);
+        B200_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+        B200_CUDA(cudaEventRecord(ev[k], s));
+      }
+    }
+    unsigned long long listed = 0;
+    int                redo[kMaxPipeline], nRedo = 0;
+    for (int k = 0; k < K; ++k) {
+      unsigned long long nk = 0;
+      B200_CUDA(cudaStreamWaitEvent(s2, ev[k], 0));
+      B200_CUDA(cudaMemcpyAsync(&nk, candCursor.get() + k, sizeof(nk), cudaMemcpyDeviceToHost, s2));
+      B200_CUDA(cudaStreamSynchronize(s2));  // (waits for chunk k's pass and for the verifications queued before it)
+      listed += nk;
+      if (nk > capK) redo[nRedo++] = k;
+      else if (nk) launchVerify(cand.get() + static_cast<size_t>(k) * capK, nk, s2);
+      cudaEventDestroy(ev[k]);
+    }
+    cudaEvent_t done;
+    B200_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    B200_CUDA(cudaEventRecord(done, s2));
+    B200_CUDA(cudaStreamWaitEvent(s, done, 0));  // the caller's stream continues after the last verification
+    cudaEventDestroy(done);
+    g_candidatesLast = listed;
+    for (int r = 0; r < nRedo; ++r) {
+      SimLaunch qk   = q;
+      qk.groupOffset = p.groupOffset + static_cast<uint32_t>(redo[r]) * p.groupStride;
+      qk.groupStride = static_cast<uint32_t>(K) * p.groupStride;
+      bool again     = false;
+      if (!launchTensorImpl(mode, qk, s, superS, 1, &again)) return false;
+      if (again && !launchTensorImpl(mode, qk, s, 1, 1, nullptr)) return false;
+    }
+    return true;
+  }
+
+  if (unitsOf(p) == 0) return true;  // nothing owned by this rank (more ranks than row groups)
+  int blocks = smCount();
+  if (static_cast<uint64_t>(blocks) > unitsOf(p)) blocks = static_cast<int>(unitsOf(p));
+  if (mode == kCountTanimoto) {
+    PhaseTimer t("neighbor_pass_tc", s);
+    launchCount(p);
   } else if (mode == kMaterialiseTanimoto) {
     PhaseTimer t("cross_tc", s);
     if (fp4) simTensorKernel<kTcTanimoto, true, 0><<<blocks, threadsTC(kTcTanimoto), smemBytes, s>>>(tmA, tmB, tmOut, p);
@@ -1423,7 +1504,7 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
     if (fp4) simTensorKernel<kTcCosine, true, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, tmOut, p);
     else simTensorKernel<kTcCosine, false, 0><<<blocks, threadsTC(kTcCosine), smemBytes, s>>>(tmA, tmB, tmOut, p);
   }
-  B200_LAUNCHED();
+  if (mode != kCountTanimoto) B200_LAUNCHED();
   if (super) {
     // the one host read of a superposed pass: how many candidates (the callers synchronise for their edge total anyway)
     unsigned long long nCand = 0;
@@ -1438,15 +1519,7 @@ static bool launchTensorImpl(SimMode mode, const SimLaunch& q, cudaStream_t s, i
       if (overflow) *overflow = true;  // nothing has been counted yet: the caller reruns without superposition
       return true;
     }
-    if (nCand) {
-      PhaseTimer         t("verify_candidates", s);
-      const unsigned int blocks2 = static_cast<unsigned int>(std::min<unsigned long long>((nCand + 63) / 64, static_cast<unsigned long long>(smCount()) * 16));
-      verifyCandidatesKernel<<<blocks2, 256, 0, s>>>(q.x, q.y, q.words, cand.get(), nCand, superS, superC,
-                                                     static_cast<uint32_t>(q.nX), static_cast<uint32_t>(q.nY), q.symmetric ? 1 : 0,
-                                                     popX.get(), popYExact, thresh.get(), q.sign, q.rowCounts,
-                                                     q.symmetric ? q.rowCounts : nullptr, q.edges, q.edgeCursor, q.edgeCap);
-      B200_LAUNCHED();
-    }
+    if (nCand) launchVerify(cand.get(), nCand, s);
   }
   return true;
 }

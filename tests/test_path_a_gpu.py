@@ -382,6 +382,32 @@ def test_pilot_chosen_superposition_gives_the_unsuperposed_answer(cuda):
         _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
 
 
+def test_pipelined_verification_gives_the_same_graph(cuda):
+    """From 16 row groups up the superposed pass runs as a pipeline of 4 chunks (the verification of one chunk overlaps
+    the tensor pass of the next, on a second stream). Same cluster ids and centroids as the one-chunk pass - also when
+    every chunk's candidate list overflows (clusters of 400: ~27 M edges) and each chunk is redone with fewer pairs per
+    accumulator after the others."""
+    from nvmolkit_b200 import _lib
+    from nvmolkit_b200.clustering import fused_butina_device
+
+    _lib.set_option("similarity_tensor_min_pairs", 0)
+    try:
+        for centres, members, auto in ((2700, 50, 1), (338, 400, 0)):
+            dev = _dev(S.clustered_fingerprints(centres, members, seed=centres), cuda)
+            _lib.set_option("similarity_superpose_auto", auto)
+            _lib.set_option("similarity_pipeline_chunks", 4)
+            ids, cen = fused_butina_device(dev, 0.3)
+            listed = _lib.get_option("similarity_candidates_last")
+            _lib.set_option("similarity_pipeline_chunks", 1)
+            ids1, cen1 = fused_butina_device(dev, 0.3)
+            assert torch.equal(ids, ids1) and torch.equal(cen, cen1), (centres, members)
+            assert listed > 0
+    finally:
+        _lib.set_option("similarity_superpose_auto", 1)
+        _lib.set_option("similarity_pipeline_chunks", 4)
+        _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
+
+
 def test_superposed_pass_falls_back_when_its_candidate_list_overflows(cuda):
     """12,000 identical fingerprints: every pair is an edge, so the 4 x 4 superposed pass lists ~4.5 M candidates and its
     4 x 1 rerun ~18 M, both more than the list holds; nothing may have been counted when they notice, and the unsuperposed
