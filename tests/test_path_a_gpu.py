@@ -487,6 +487,32 @@ def _sharded_butina_one_gpu(fp, cutoff, world, cuda):
     return ids.cpu().numpy(), cen[:k].cpu().numpy(), all_edges.cpu().numpy(), deg.cpu().numpy(), per_rank
 
 
+def test_sharded_pipelined_pass_equals_the_plain_pass(cuda):
+    """270,000 points over two "ranks": each owns 17 row groups, enough for its superposed pass to run as a pipeline of
+    four chunks (group stride 2 x 4). Degrees, edge set and clusters must equal those of ONE unsuperposed, unpipelined
+    pass over everything (the path the small tests pin to the oracle)."""
+    from nvmolkit_b200 import _lib
+
+    fp = S.clustered_fingerprints(5400, 50, seed=11)
+    _lib.set_option("similarity_tensor_min_pairs", 0)
+    try:
+        ids, cen, edges, deg, per_rank = _sharded_butina_one_gpu(fp, 0.3, 2, cuda)
+        assert all(c > 0 for c in per_rank)
+        _lib.set_option("similarity_pipeline_chunks", 1)
+        _lib.set_option("similarity_superpose", 1)
+        _lib.set_option("similarity_superpose_cols", 1)
+        ids1, cen1, edges1, deg1, _ = _sharded_butina_one_gpu(fp, 0.3, 1, cuda)
+    finally:
+        _lib.set_option("similarity_pipeline_chunks", 4)
+        _lib.set_option("similarity_superpose", 4)
+        _lib.set_option("similarity_superpose_cols", 4)
+        _lib.set_option("similarity_tensor_min_pairs", 1 << 24)
+    assert (deg == deg1).all() and (ids == ids1).all() and (cen == cen1).all()
+    key = np.sort(edges[:, 0].astype(np.int64) * len(fp) + edges[:, 1])
+    key1 = np.sort(edges1[:, 0].astype(np.int64) * len(fp) + edges1[:, 1])
+    assert (edges[:, 0] < edges[:, 1]).all() and len(key) == len(key1) and (key == key1).all()
+
+
 @pytest.mark.parametrize("tensor", [0, 1, 3], ids=["simt_tile", "tensor_tile", "tensor_row_stationary"])
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("centres,members", [(30, 20), (130, 50)])  # 600 and 6500 points: 5 and 51 tile rows
